@@ -1,0 +1,30 @@
+"""sim_b200 -- B200-native batched-replication engine for ndebuhr/sim discrete event simulations.
+
+Host-side mirror of the reference's Rust API for the accelerated path
+(``Simulation::post/put/reset/inject_input/step/step_n/step_until``, the ten built-in models, the
+``input_modeling`` random variables and ``output_analysis``) over the C ABI of ``libsimb200.so``
+(include/simb.h).  There is no CPU fallback: without the CUDA library the engine raises.
+"""
+from .coupling import Connector, Message  # noqa: F401
+from .input_modeling import (BooleanRandomVariable, ContinuousRandomVariable,  # noqa: F401
+                             IndexRandomVariable)
+from .models import (Batcher, ExclusiveGateway, Gate, Generator, LoadBalancer, Metric, Model,  # noqa: F401
+                     ParallelGateway, Passive, Processor, StochasticGate, Stopwatch, Storage)
+
+__all__ = [
+    "Connector", "Message", "BooleanRandomVariable", "ContinuousRandomVariable", "IndexRandomVariable",
+    "Batcher", "ExclusiveGateway", "Gate", "Generator", "LoadBalancer", "Metric", "Model", "ParallelGateway",
+    "Passive", "Processor", "StochasticGate", "Stopwatch", "Storage",
+]
+
+
+def __getattr__(name):
+    # Simulation / output_analysis load the CUDA library lazily so that describing models works
+    # on machines without it.
+    if name in ("Simulation", "SimulationError", "SimbConfig"):
+        from . import simulator
+        return getattr(simulator, name)
+    if name == "output_analysis":
+        from . import output_analysis
+        return output_analysis
+    raise AttributeError(name)

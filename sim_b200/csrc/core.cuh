@@ -1,0 +1,846 @@
+// sim_b200/csrc/core.cuh -- the per-replication DEVS interpreter: one CUDA thread ("lane") owns
+// one replication; all lanes walk the model list in the same order, so the model-type dispatch is
+// warp-uniform and only the "is this model imminent / does it have mail" predicate diverges.
+//
+// Semantics follow sim/src/simulator/mod.rs:198-303 and sim/src/models/*.rs (cited per
+// function; SURVEY.md Appendices A-C).  The code is written against a small `Lane` view so the
+// SAME source also compiles as plain C++ for tests/hostsim (a unit-test harness that runs the
+// interpreter logic on the CPU against the oracle; it is never linked into libsimb200.so).
+//
+// Arithmetic rules: f64 clock arithmetic is the reference's plain subtract/add (no FMA
+// contraction: nvcc -fmad=false, g++ -ffp-contract=off) because scheduling tests `== 0.0`
+// exactly (mod.rs:239).
+#pragma once
+#include "net.h"
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#ifdef __CUDACC__
+#define SIMB_HD __host__ __device__ __forceinline__
+#define SIMB_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define SIMB_HD inline
+#define SIMB_HD_NOINLINE
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define SIMB_ON_DEVICE 1
+#else
+#define SIMB_ON_DEVICE 0
+#endif
+
+namespace simb {
+
+#define SIMB_INF (__builtin_huge_val())
+
+// ---- warp helpers (single-lane semantics on the host) -------------------------------------------
+SIMB_HD uint32_t warp_or(uint32_t v) {
+#if SIMB_ON_DEVICE
+    return __reduce_or_sync(0xFFFFFFFFu, v);
+#else
+    return v;
+#endif
+}
+SIMB_HD uint32_t warp_max(uint32_t v) {
+#if SIMB_ON_DEVICE
+    return __reduce_max_sync(0xFFFFFFFFu, v);
+#else
+    return v;
+#endif
+}
+SIMB_HD bool warp_any(bool p) {
+#if SIMB_ON_DEVICE
+    return __ballot_sync(0xFFFFFFFFu, p) != 0u;
+#else
+    return p;
+#endif
+}
+SIMB_HD int lowest_bit(uint32_t v) {
+#if SIMB_ON_DEVICE
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+SIMB_HD double bits_f64(uint64_t b) {
+#if SIMB_ON_DEVICE
+    return __longlong_as_double((long long)b);
+#else
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+#endif
+}
+SIMB_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
+#if SIMB_ON_DEVICE
+    return __umul64hi(a, b);
+#else
+    return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
+// ---- tables --------------------------------------------------------------------------------------
+struct Tables {
+    const double* exp_x;   // 257 entries (shared memory on the device)
+    const double* exp_f;
+    const double* norm_x;
+    const double* norm_f;
+};
+
+// ---- per-lane view of the replication's state tile ----------------------------------------------
+// d/w point at row 0 of this lane's column; consecutive rows are `stride` elements apart
+// (device: the shared-memory tile, stride = tile width; hostsim: the global arrays).
+struct Lane {
+    double* d;
+    uint32_t* w;
+    uint32_t stride;
+    // global ring storage, already offset to this replication's column
+    uint32_t* ring_w;
+    double* ring_d;
+    uint64_t ring_stride;
+    // registers
+    double time;
+    uint32_t err, npend, steps, events, draw_idx;
+    uint32_t phase_lo, phase_hi;
+    uint64_t hash;
+    uint64_t pcg_lo, pcg_hi;
+    uint64_t cache;       // second half of the last Philox block
+    uint32_t cache_block; // block index the cache belongs to (+1; 0 = empty)
+    uint32_t key0, key1;
+    uint64_t rep_local;
+    uint32_t traced;
+    uint32_t wait_n;
+    double wait_sum;
+
+    SIMB_HD double& D(uint32_t row) { return d[(size_t)row * stride]; }
+    SIMB_HD uint32_t& W(uint32_t row) { return w[(size_t)row * stride]; }
+    SIMB_HD uint32_t& RW(uint32_t slot) { return ring_w[(uint64_t)slot * ring_stride]; }
+    SIMB_HD double& RD(uint32_t slot) { return ring_d[(uint64_t)slot * ring_stride]; }
+    SIMB_HD uint32_t phase(uint32_t m) const {
+        return m < 16 ? (phase_lo >> (2 * m)) & 3u : (phase_hi >> (2 * (m - 16))) & 3u;
+    }
+    SIMB_HD void set_phase(uint32_t m, uint32_t p) {
+        if (m < 16) phase_lo = (phase_lo & ~(3u << (2 * m))) | (p << (2 * m));
+        else phase_hi = (phase_hi & ~(3u << (2 * (m - 16)))) | (p << (2 * (m - 16)));
+    }
+};
+
+// ---- Philox4x32-10 (Salmon et al. SC'11); one block = two u64 draws -------------------------------
+SIMB_HD void philox_block(uint32_t key0, uint32_t key1, uint32_t ctr_lo, uint64_t* a, uint64_t* b) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    uint32_t c0 = ctr_lo, c1 = 0u, c2 = 0u, c3 = 0u, k0 = key0, k1 = key1;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    *a = (uint64_t)c0 | ((uint64_t)c1 << 32);
+    *b = (uint64_t)c2 | ((uint64_t)c3 << 32);
+}
+
+template <int RNG>
+struct Engine {
+    const SimbNetDesc& net;
+    const SimbDevState& st;
+    Tables tab;
+
+    SIMB_HD Engine(const SimbNetDesc& n, const SimbDevState& s, const Tables& t) : net(n), st(s), tab(t) {}
+
+    // ---- uniform u64 source (RngCore::next_u64 on the shared DynRng, services.rs:25-27) ----------
+    SIMB_HD uint64_t next_u64(Lane& ln) {
+        if (RNG == 0) {
+            uint32_t idx = ln.draw_idx++;
+            uint32_t blk = idx >> 1;
+            if (idx & 1u) {
+                if (ln.cache_block == blk + 1u) return ln.cache;
+                uint64_t a, b;
+                philox_block(ln.key0, ln.key1, blk, &a, &b);
+                return b;
+            }
+            uint64_t a, b;
+            philox_block(ln.key0, ln.key1, blk, &a, &b);
+            ln.cache = b;
+            ln.cache_block = blk + 1u;
+            return a;
+        } else if (RNG == 1) {
+            // rand_pcg 0.3 Mcg128Xsl64: state *= MULT (mod 2^128); XSL-RR output
+            const uint64_t ML = 0x4385DF649FCCF645ull, MH = 0x2360ED051FC65DA4ull;
+            uint64_t lo = ln.pcg_lo * ML;
+            uint64_t hi = mulhi64(ln.pcg_lo, ML) + ln.pcg_lo * MH + ln.pcg_hi * ML;
+            ln.pcg_lo = lo;
+            ln.pcg_hi = hi;
+            ln.draw_idx++;
+            uint32_t rot = (uint32_t)(hi >> 58);
+            uint64_t xsl = hi ^ lo;
+            return (xsl >> rot) | (xsl << ((64u - rot) & 63u));
+        } else {
+            uint32_t idx = ln.draw_idx++;
+            if (idx >= st.ext_len) {
+                if (!ln.err) ln.err = 37;  // SIMB_ERR_STREAM_EXHAUSTED
+                return 0;
+            }
+            return st.ext[(uint64_t)idx * st.stride + ln.rep_local];
+        }
+    }
+
+    // ---- rand 0.8 float conversions ---------------------------------------
+    SIMB_HD double standard_f64(Lane& ln) {  // Standard: 53 bits -> [0,1)
+        return (double)(next_u64(ln) >> 11) * (1.0 / 9007199254740992.0);
+    }
+    SIMB_HD double open01(Lane& ln) {  // Open01: (0,1)
+        return bits_f64((next_u64(ln) >> 12) | 0x3FF0000000000000ull) - (1.0 - 2.220446049250313e-16 / 2.0);
+    }
+    // rand_distr 0.4 Exp1 (ziggurat, 256 layers)
+    SIMB_HD double sample_exp1(Lane& ln) {
+        for (;;) {
+            uint64_t bits = next_u64(ln);
+            uint32_t i = (uint32_t)bits & 0xFFu;
+            double u = bits_f64((bits >> 12) | 0x3FF0000000000000ull) - (1.0 - 2.220446049250313e-16 / 2.0);
+            double x = u * tab.exp_x[i];
+            if (x < tab.exp_x[i + 1]) return x;
+            if (i == 0) return 7.69711747013104972 - log(standard_f64(ln));
+            double f1 = tab.exp_f[i + 1], f0 = tab.exp_f[i];
+            if (f1 + (f0 - f1) * standard_f64(ln) < exp(-x)) return x;
+            if (ln.err) return x;  // external stream ran dry: do not spin
+        }
+    }
+    // rand_distr 0.4 StandardNormal (symmetric ziggurat + Marsaglia tail)
+    SIMB_HD double sample_standard_normal(Lane& ln) {
+        for (;;) {
+            uint64_t bits = next_u64(ln);
+            uint32_t i = (uint32_t)bits & 0xFFu;
+            double u = bits_f64((bits >> 12) | 0x4000000000000000ull) - 3.0;
+            double x = u * tab.norm_x[i];
+            if (fabs(x) < tab.norm_x[i + 1]) return x;
+            if (i == 0) {
+                const double R = 3.6541528853610088;
+                double tx = 1.0, ty = 0.0;
+                while (-2.0 * ty < tx * tx) {
+                    double x_ = open01(ln);
+                    double y_ = open01(ln);
+                    tx = log(x_) / R;
+                    ty = log(y_);
+                    if (ln.err) break;
+                }
+                return (u < 0.0) ? tx - R : R - tx;
+            }
+            double f1 = tab.norm_f[i + 1], f0 = tab.norm_f[i];
+            if (f1 + (f0 - f1) * standard_f64(ln) < exp(-x * x / 2.0)) return x;
+            if (ln.err) return x;
+        }
+    }
+    // Continuous::random_variate (random_variable.rs:69-89); parameter errors surface per draw
+    SIMB_HD double sample_continuous(Lane& ln, const SimbModelDesc& md) {
+        if (md.dist_err) {
+            if (!ln.err) ln.err = md.dist_err;
+            return 0.0;
+        }
+        switch (md.dist_kind) {
+            case DK_EXP:
+                return sample_exp1(ln) * md.p0;  // Exp1 * lambda_inverse
+            case DK_NORMAL: {
+                double n = sample_standard_normal(ln);
+                return md.p0 + md.p1 * n;
+            }
+            case DK_TRIANGULAR: {
+                double mn = md.p0, mx = md.p1, mode = md.p2;
+                double f = standard_f64(ln);
+                double diff_mode_min = mode - mn;
+                double range = mx - mn;
+                double f_range = f * range;
+                if (f_range < diff_mode_min) return mn + sqrt(f_range * diff_mode_min);
+                return mx - sqrt((range - f_range) * (mx - mode));
+            }
+            default: {  // DK_UNIFORM: p0 = low, p1 = scale
+                double value1_2 = bits_f64((next_u64(ln) >> 12) | 0x3FF0000000000000ull);
+                double value0_1 = value1_2 - 1.0;
+                return value0_1 * md.p1 + md.p0;
+            }
+        }
+    }
+    // rand 0.8 UniformInt<u64>::sample: widening multiply + zone rejection
+    SIMB_HD uint64_t sample_uniform_int(Lane& ln, uint64_t low, uint64_t range, uint64_t zone) {
+        for (;;) {
+            uint64_t v = next_u64(ln);
+            uint64_t hi = mulhi64(v, range), lo = v * range;
+            if (lo <= zone) return low + hi;
+            if (ln.err) return low;
+        }
+    }
+    // Index::random_variate (random_variable.rs:122-130)
+    SIMB_HD uint32_t sample_index(Lane& ln, const SimbModelDesc& md) {
+        if (md.dist_err) {
+            if (!ln.err) ln.err = md.dist_err;
+            return 0;
+        }
+        uint64_t c = sample_uniform_int(ln, md.q0, md.q1, md.q2);
+        if (!(md.flags & MF_INDEX_WEIGHTED)) return (uint32_t)(c > 0xFFFFFFFFull ? 0xFFFFFFFFull : c);
+        uint32_t idx = 0;  // first cumulative weight strictly greater than the chosen weight
+        while (idx < md.n_w && net.wcum[md.wtab + idx] <= c) idx++;
+        return idx;
+    }
+    // Boolean::random_variate (random_variable.rs:96-101)
+    SIMB_HD bool sample_bernoulli(Lane& ln, const SimbModelDesc& md) {
+        if (md.dist_err) {
+            if (!ln.err) ln.err = md.dist_err;
+            return false;
+        }
+        if (md.flags & MF_BERNOULLI_ALWAYS) return true;  // p == 1.0 consumes no draw
+        return next_u64(ln) < md.q0;
+    }
+
+    // ---- instrumentation ---------------------------------------------------------------------------
+    template <bool INSTR>
+    SIMB_HD void record(Lane& ln, uint32_t m, uint32_t action, uint32_t content, uint32_t aux = 0) {
+        if (INSTR) {
+            ln.hash = (ln.hash ^ TRACE_RECORD_WORD(m, action, aux, content)) * TRACE_HASH_PRIME;
+#if SIMB_ON_DEVICE
+            atomicAdd(&st.record_count[m * ACT_COUNT + action], 1ull);
+#else
+            st.record_count[m * ACT_COUNT + action] += 1ull;
+#endif
+            if (ln.traced) {
+                uint32_t k = st.trace_count[ln.rep_local];
+                if (k < st.trace_cap) {
+                    SimbTraceRec r;
+                    r.step = ln.steps + 1u;
+                    r.meta = (1u << 31) | m;
+                    r.content = content;
+                    r.aux = action | (aux << 8);
+                    r.time = ln.time;
+                    st.trace[(uint64_t)ln.rep_local * st.trace_cap + k] = r;
+                }
+                st.trace_count[ln.rep_local] = k + 1u;
+            }
+        }
+    }
+
+    // route one outgoing (port, content) over every matching connector, in connector order
+    // (get_message_target_ids/ports, mod.rs:155-182, 243-263)
+    template <bool INSTR>
+    SIMB_HD void emit(Lane& ln, const SimbModelDesc& md, uint32_t out_port, uint32_t content) {
+        uint32_t rb = net.route_begin[md.out_base + out_port], re = net.route_begin[md.out_base + out_port + 1];
+        for (uint32_t r = rb; r < re; r++) {
+            if (ln.npend >= net.max_pending) {
+                if (!ln.err) ln.err = 32;  // SIMB_ERR_CAPACITY: mailbox overflow
+                return;
+            }
+            SimbRoute rt = net.routes[r];
+            ln.W(net.wrow_pend + 2 * ln.npend) = content;
+            ln.W(net.wrow_pend + 2 * ln.npend + 1) = ROUTE_WORD(rt.tgt_model, rt.tgt_port, rt.connector);
+            ln.npend++;
+            if (INSTR) {
+                ln.hash = (ln.hash ^ TRACE_MESSAGE_WORD(rt.connector, content)) * TRACE_HASH_PRIME;
+#if SIMB_ON_DEVICE
+                atomicAdd(&st.conn_count[rt.connector], 1ull);
+#else
+                st.conn_count[rt.connector] += 1ull;
+#endif
+                if (ln.traced) {
+                    uint32_t k = st.trace_count[ln.rep_local];
+                    if (k < st.trace_cap) {
+                        SimbTraceRec t;
+                        t.step = ln.steps + 1u;
+                        t.meta = rt.connector;
+                        t.content = content;
+                        t.aux = 0;
+                        t.time = ln.time;
+                        st.trace[(uint64_t)ln.rep_local * st.trace_cap + k] = t;
+                    }
+                    st.trace_count[ln.rep_local] = k + 1u;
+                }
+            }
+        }
+    }
+
+    // ---- FIFO ring helpers: queue word = head(16) | len(16) ----------------------------------------
+    SIMB_HD uint32_t ring_slot(const SimbModelDesc& md, uint32_t head, uint32_t i) {
+        uint32_t s = head + i;
+        return s >= md.ring_cap ? s - md.ring_cap : s;
+    }
+    SIMB_HD bool ring_push(Lane& ln, const SimbModelDesc& md, uint32_t content, uint32_t* slot_out) {
+        uint32_t q = ln.W(md.wrow);
+        uint32_t head = q >> 16, len = q & 0xFFFFu;
+        if (len >= md.ring_cap) {
+            if (!ln.err) ln.err = 32;  // SIMB_ERR_CAPACITY: the reference's Vec is unbounded here
+            return false;
+        }
+        uint32_t s = ring_slot(md, head, len);
+        ln.RW(md.ring_w0 + s) = content;
+        ln.W(md.wrow) = (head << 16) | (len + 1u);
+        *slot_out = s;
+        return true;
+    }
+    SIMB_HD uint32_t ring_pop(Lane& ln, const SimbModelDesc& md, uint32_t* slot_out) {
+        uint32_t q = ln.W(md.wrow);
+        uint32_t head = q >> 16, len = q & 0xFFFFu;
+        uint32_t c = ln.RW(md.ring_w0 + head);
+        *slot_out = head;
+        uint32_t nh = head + 1u;
+        if (nh >= md.ring_cap) nh = 0;
+        ln.W(md.wrow) = (nh << 16) | (len - 1u);
+        return c;
+    }
+
+    // ================================================================================================
+    // events_ext per model type
+    // ================================================================================================
+    template <bool INSTR>
+    SIMB_HD void events_ext(Lane& ln, uint32_t m, const SimbModelDesc& md, uint32_t port, uint32_t content) {
+        const uint32_t urow = net.drow_until + m;
+        switch (md.type) {
+            case MT_GENERATOR:  // generator.rs:161-167: no-op
+            case MT_PASSIVE:    // tests/custom.rs:49-56
+                break;
+            case MT_PROCESSOR: {  // processor.rs:211-227
+                if (port != 0) { ln.err = 7; break; }  // InvalidMessage
+                uint32_t q = ln.W(md.wrow);
+                uint32_t len = q & 0xFFFFu;
+                bool empty = len == 0, full = len == md.cap;
+                if (empty && full) { ln.err = 5; break; }  // InvalidModelState (capacity 0)
+                if (full) {  // ignore_job :152-158
+                    record<INSTR>(ln, m, ACT_DROP, content);
+                    break;
+                }
+                uint32_t slot;
+                if (!ring_push(ln, md, content, &slot)) break;
+                if (md.flags & MF_STAT) ln.RD(md.ring_d + slot) = ln.time;
+                if (empty) {  // activate :128-150
+                    ln.set_phase(m, 1);
+                    double dv = sample_continuous(ln, md);
+                    if (ln.err) break;
+                    ln.D(urow) = dv;
+                    record<INSTR>(ln, m, ACT_ARRIVAL, content);
+                    record<INSTR>(ln, m, ACT_PROCESSING_START, content);
+                    if (md.flags & MF_STAT) {
+                        ln.wait_sum += ln.time - ln.time;  // Processing Start - Arrival = 0 here
+                        ln.wait_n++;
+                    }
+                } else {  // add_job :119-126
+                    record<INSTR>(ln, m, ACT_ARRIVAL, content);
+                }
+                break;
+            }
+            case MT_STORAGE: {  // storage.rs:151-161
+                if (port == 0) {  // hold_job :106-113
+                    ln.W(md.wrow) = content;
+                    record<INSTR>(ln, m, ACT_ARRIVAL, content);
+                } else if (port == 1) {  // get_job :101-104
+                    ln.set_phase(m, 1);
+                    ln.D(urow) = 0.0;
+                } else {
+                    ln.err = 7;
+                }
+                break;
+            }
+            case MT_LOAD_BALANCER: {  // pass_job load_balancer.rs:78-87 (any port)
+                ln.set_phase(m, 1);
+                ln.D(urow) = 0.0;
+                uint32_t slot;
+                if (!ring_push(ln, md, content, &slot)) break;
+                record<INSTR>(ln, m, ACT_ARRIVAL, content);
+                break;
+            }
+            case MT_GATE: {  // gate.rs:180-195
+                if (port == 0) {
+                    if (ln.phase(m) != 1) {  // pass_job :127-137
+                        ln.set_phase(m, 2);
+                        ln.D(urow) = 0.0;
+                        uint32_t slot;
+                        if (!ring_push(ln, md, content, &slot)) break;
+                    }
+                    record<INSTR>(ln, m, ACT_ARRIVAL, content);  // also when Closed (drop_job :139-145)
+                } else if (port == 1) {  // activate :107-115
+                    ln.set_phase(m, 0);
+                    ln.D(urow) = SIMB_INF;
+                    record<INSTR>(ln, m, ACT_ACTIVATION, content);
+                } else if (port == 2) {  // deactivate :117-125
+                    ln.set_phase(m, 1);
+                    ln.D(urow) = SIMB_INF;
+                    record<INSTR>(ln, m, ACT_DEACTIVATION, content);
+                } else {
+                    ln.err = 7;
+                }
+                break;
+            }
+            case MT_EXCLUSIVE_GATEWAY: {  // pass_job exclusive_gateway.rs:95-108 (any port)
+                ln.set_phase(m, 1);
+                ln.D(urow) = 0.0;
+                uint32_t slot;
+                if (!ring_push(ln, md, content, &slot)) break;
+                record<INSTR>(ln, m, ACT_ARRIVAL, content, port == SIMB_PORT_UNKNOWN ? 0u : port + 1u);
+                break;
+            }
+            case MT_PARALLEL_GATEWAY: {  // parallel_gateway.rs:160-172, increment_collection :100-116
+                if (port == SIMB_PORT_UNKNOWN) { ln.err = 7; break; }
+                uint32_t cnt = ln.W(md.wrow);
+                uint32_t i = 0;
+                for (; i < cnt; i++)
+                    if (ln.RW(md.ring_w0 + i) == content) break;
+                if (i < cnt) {
+                    ln.RW(md.ring_w1 + i) += 1u;
+                } else {
+                    if (cnt >= md.ring_cap) { ln.err = 32; break; }
+                    ln.RW(md.ring_w0 + cnt) = content;
+                    ln.RW(md.ring_w1 + cnt) = 1u;
+                    ln.W(md.wrow) = cnt + 1u;
+                }
+                record<INSTR>(ln, m, ACT_ARRIVAL, content, port + 1u);
+                ln.D(urow) = 0.0;
+                break;
+            }
+            case MT_STOCHASTIC_GATE: {  // stochastic_gate.rs:163-172, receive_job :101-122
+                if (port != 0) { ln.err = 7; break; }
+                ln.D(urow) = 0.0;
+                bool pass = sample_bernoulli(ln, md);  // Bernoulli draw AT ARRIVAL
+                if (ln.err) break;
+                uint32_t slot;
+                if (!ring_push(ln, md, content, &slot)) break;
+                ln.RW(md.ring_w1 + slot) = pass ? 1u : 0u;
+                record<INSTR>(ln, m, ACT_ARRIVAL, content);
+                break;
+            }
+            case MT_STOPWATCH: {  // stopwatch.rs:271-282
+                if (port == 2) {  // get_job :211-214
+                    ln.set_phase(m, 1);
+                    ln.D(urow) = 0.0;
+                    break;
+                }
+                if (port > 2) { ln.err = 7; break; }
+                record<INSTR>(ln, m, port == 0 ? ACT_START : ACT_STOP, content);
+                // matching_or_new_job :137-155 on a bounded table of INCOMPLETE jobs:
+                // word0 = entries, word1 = best content, word2 = next insertion seq, word3 = best seq;
+                // entry: c0 = name, c1 = seq<<2 | has_stop<<1 | has_start, d = the time present.
+                uint32_t cnt = ln.W(md.wrow);
+                uint32_t i = 0;
+                for (; i < cnt; i++)
+                    if (ln.RW(md.ring_w0 + i) == content) break;
+                uint32_t mine = port == 0 ? 1u : 2u, other = port == 0 ? 2u : 1u;
+                if (i == cnt) {
+                    if (cnt >= md.ring_cap) { ln.err = 32; break; }
+                    uint32_t seq = ln.W(md.wrow + 2);
+                    ln.W(md.wrow + 2) = seq + 1u;
+                    ln.RW(md.ring_w0 + cnt) = content;
+                    ln.RW(md.ring_w1 + cnt) = (seq << 2) | mine;
+                    ln.RD(md.ring_d + cnt) = ln.time;
+                    ln.W(md.wrow) = cnt + 1u;
+                    break;
+                }
+                uint32_t fl = ln.RW(md.ring_w1 + i);
+                if (!(fl & other)) {  // same side again: overwrite the time
+                    ln.RD(md.ring_d + i) = ln.time;
+                    break;
+                }
+                // both sides now known: duration = stop - start (some_duration :95-100)
+                double t_other = ln.RD(md.ring_d + i);
+                double dur = port == 0 ? t_other - ln.time : ln.time - t_other;
+                uint32_t seq = fl >> 2;
+                uint32_t best_c = ln.W(md.wrow + 1), best_seq = ln.W(md.wrow + 3);
+                double best_d = ln.D(md.drow);
+                bool better;
+                if (best_c == SIMB_CONTENT_NONE) better = (md.flags & MF_METRIC_MAX) ? dur > -SIMB_INF : dur < SIMB_INF;
+                else if (md.flags & MF_METRIC_MAX) better = dur > best_d || (dur == best_d && seq < best_seq);
+                else better = dur < best_d || (dur == best_d && seq < best_seq);
+                if (better) {
+                    ln.W(md.wrow + 1) = content;
+                    ln.W(md.wrow + 3) = seq;
+                    ln.D(md.drow) = dur;
+                }
+                // drop the completed entry (swap with last; lookup is by name, order by seq)
+                uint32_t last = cnt - 1u;
+                if (i != last) {
+                    ln.RW(md.ring_w0 + i) = ln.RW(md.ring_w0 + last);
+                    ln.RW(md.ring_w1 + i) = ln.RW(md.ring_w1 + last);
+                    ln.RD(md.ring_d + i) = ln.RD(md.ring_d + last);
+                }
+                ln.W(md.wrow) = last;
+                break;
+            }
+            case MT_BATCHER: {  // batcher.rs:192-206 (any port)
+                uint32_t q = ln.W(md.wrow);
+                uint32_t len = q & 0xFFFFu;
+                bool room = (uint64_t)len + 1ull < (uint64_t)md.cap;
+                uint32_t ph = ln.phase(m);
+                if (room && ph == 2) { ln.err = 5; break; }  // (Release, true) => InvalidModelState
+                if (room) {
+                    if (ph == 0) {  // start_batch :103-112
+                        ln.set_phase(m, 1);
+                        ln.D(urow) = md.p0;
+                    }  // add_to_batch :93-101 leaves the timer alone
+                } else {  // fill_batch :114-123
+                    ln.set_phase(m, 2);
+                    ln.D(urow) = 0.0;
+                }
+                uint32_t slot;
+                if (!ring_push(ln, md, content, &slot)) break;
+                record<INSTR>(ln, m, ACT_ARRIVAL, content);
+                break;
+            }
+            default:
+                break;
+        }
+    }
+
+    // ================================================================================================
+    // events_int per model type
+    // ================================================================================================
+    // pop `n` jobs from the FIFO ring and send them out of `out_port`.  All records of one
+    // events_int call precede its messages (the reference routes the returned Vec afterwards,
+    // mod.rs:240-263), so the trace order is records first, then messages.
+    template <bool INSTR>
+    SIMB_HD void release_n(Lane& ln, uint32_t m, const SimbModelDesc& md, uint32_t n, uint32_t out_port, uint32_t aux) {
+        if (INSTR) {
+            uint32_t head = ln.W(md.wrow) >> 16;
+            for (uint32_t i = 0; i < n; i++) record<INSTR>(ln, m, ACT_DEPARTURE, ln.RW(md.ring_w0 + ring_slot(md, head, i)), aux);
+        }
+        for (uint32_t i = 0; i < n && !ln.err; i++) {
+            uint32_t slot;
+            uint32_t c = ring_pop(ln, md, &slot);
+            emit<INSTR>(ln, md, out_port, c);
+        }
+    }
+
+    template <bool INSTR>
+    SIMB_HD void events_int(Lane& ln, uint32_t m, const SimbModelDesc& md) {
+        const uint32_t urow = net.drow_until + m;
+        switch (md.type) {
+            case MT_GENERATOR: {  // generator.rs:169-177
+                double dv = sample_continuous(ln, md);  // the draw comes first (:102-109, :129-136)
+                if (ln.err) break;
+                if (ln.phase(m) == 1) {  // release_job :98-123
+                    ln.D(urow) = dv;
+                    uint32_t last = ln.W(md.wrow) + 1u;
+                    if (last >= SIMB_NUM_LITERAL) { ln.err = 32; break; }  // content code space exhausted
+                    ln.W(md.wrow) = last;
+                    uint32_t c = md.prefix | last;
+                    record<INSTR>(ln, m, ACT_GENERATION, c);
+                    emit<INSTR>(ln, md, 0, c);
+                } else {  // initialize_generation :125-146
+                    ln.set_phase(m, 1);
+                    ln.D(urow) = dv;
+                    record<INSTR>(ln, m, ACT_INITIALIZATION, SIMB_CONTENT_NONE);
+                }
+                break;
+            }
+            case MT_PROCESSOR: {  // processor.rs:229-238
+                uint32_t q = ln.W(md.wrow);
+                uint32_t head = q >> 16, len = q & 0xFFFFu;
+                if (ln.phase(m) == 0) {
+                    if (len == 0) {  // passivate :192-196
+                        ln.D(urow) = SIMB_INF;
+                        break;
+                    }
+                    ln.set_phase(m, 1);  // process_next :160-175
+                    double dv = sample_continuous(ln, md);
+                    if (ln.err) break;
+                    ln.D(urow) = dv;
+                    record<INSTR>(ln, m, ACT_PROCESSING_START, ln.RW(md.ring_w0 + head));
+                    if (md.flags & MF_STAT) {
+                        ln.wait_sum += ln.time - ln.RD(md.ring_d + head);
+                        ln.wait_n++;
+                    }
+                    break;
+                }
+                if (len == 0) { ln.err = 34; break; }  // queue.remove(0) on an empty Vec panics
+                uint32_t slot;
+                uint32_t c = ring_pop(ln, md, &slot);  // release_job :177-190
+                ln.set_phase(m, 0);
+                ln.D(urow) = 0.0;
+                record<INSTR>(ln, m, ACT_DEPARTURE, c);
+                emit<INSTR>(ln, md, 0, c);
+                break;
+            }
+            case MT_STORAGE: {  // storage.rs:163-171
+                ln.D(urow) = SIMB_INF;
+                if (ln.phase(m) == 1) {  // release_job :115-130
+                    ln.set_phase(m, 0);
+                    uint32_t c = ln.W(md.wrow);
+                    record<INSTR>(ln, m, ACT_DEPARTURE, c);
+                    if (c != SIMB_CONTENT_NONE) emit<INSTR>(ln, md, 0, c);
+                }
+                break;
+            }
+            case MT_LOAD_BALANCER: {  // load_balancer.rs:134-142
+                uint32_t len = ln.W(md.wrow) & 0xFFFFu;
+                if (len == 0) {  // passivate
+                    ln.set_phase(m, 0);
+                    ln.D(urow) = SIMB_INF;
+                    break;
+                }
+                if (md.n_out == 0) { ln.err = 34; break; }  // `% 0` panics
+                ln.D(urow) = 0.0;  // send_job :95-111 (pre-increment)
+                uint32_t next = ln.W(md.wrow + 1) + 1u;
+                if (next >= md.n_out) next = 0;
+                ln.W(md.wrow + 1) = next;
+                release_n<INSTR>(ln, m, md, 1, next, next + 1u);
+                break;
+            }
+            case MT_GATE: {  // send_jobs gate.rs:149-165
+                ln.set_phase(m, 0);
+                ln.D(urow) = SIMB_INF;
+                release_n<INSTR>(ln, m, md, ln.W(md.wrow) & 0xFFFFu, 0, 0);
+                break;
+            }
+            case MT_EXCLUSIVE_GATEWAY: {  // exclusive_gateway.rs:153-161
+                ln.D(urow) = SIMB_INF;
+                if (ln.phase(m) == 1) {  // send_jobs :110-134: one draw per firing
+                    ln.set_phase(m, 0);
+                    uint32_t idx = sample_index(ln, md);
+                    if (ln.err) break;
+                    if (idx >= md.n_out) { ln.err = 34; break; }  // flow_paths[idx] out of bounds panics
+                    release_n<INSTR>(ln, m, md, ln.W(md.wrow) & 0xFFFFu, idx, idx + 1u);
+                }
+                break;
+            }
+            case MT_PARALLEL_GATEWAY: {  // parallel_gateway.rs:174-182
+                uint32_t cnt = ln.W(md.wrow);
+                uint32_t i = 0;
+                for (; i < cnt; i++)  // canonical choice: earliest-inserted full collection
+                    if (ln.RW(md.ring_w1 + i) == md.n_in) break;
+                if (i == cnt) {  // passivate
+                    ln.D(urow) = SIMB_INF;
+                    break;
+                }
+                ln.D(urow) = 0.0;  // send_job :118-143
+                uint32_t c = ln.RW(md.ring_w0 + i);
+                for (uint32_t j = i; j + 1u < cnt; j++) {  // remove, keeping insertion order
+                    ln.RW(md.ring_w0 + j) = ln.RW(md.ring_w0 + j + 1u);
+                    ln.RW(md.ring_w1 + j) = ln.RW(md.ring_w1 + j + 1u);
+                }
+                ln.W(md.wrow) = cnt - 1u;
+                if (INSTR)
+                    for (uint32_t p = 0; p < md.n_out; p++) record<INSTR>(ln, m, ACT_DEPARTURE, c, p + 1u);
+                for (uint32_t p = 0; p < md.n_out && !ln.err; p++) emit<INSTR>(ln, md, p, c);
+                break;
+            }
+            case MT_STOCHASTIC_GATE: {  // stochastic_gate.rs:174-183
+                uint32_t len = ln.W(md.wrow) & 0xFFFFu;
+                if (len == 0) {
+                    ln.D(urow) = SIMB_INF;
+                    break;
+                }
+                ln.D(urow) = 0.0;
+                uint32_t slot;
+                uint32_t c = ring_pop(ln, md, &slot);
+                if (ln.RW(md.ring_w1 + slot)) {  // pass_job :129-141
+                    record<INSTR>(ln, m, ACT_PASS, c);
+                    emit<INSTR>(ln, md, 0, c);
+                } else {  // block_job :143-148
+                    record<INSTR>(ln, m, ACT_BLOCK, c);
+                }
+                break;
+            }
+            case MT_STOPWATCH: {  // stopwatch.rs:284-293
+                ln.D(urow) = SIMB_INF;
+                if (ln.phase(m) == 1) {  // release_minimum / release_maximum :216-250
+                    ln.set_phase(m, 0);
+                    uint32_t c = ln.W(md.wrow + 1);
+                    record<INSTR>(ln, m, (md.flags & MF_METRIC_MAX) ? ACT_MAXIMUM_FETCH : ACT_MINIMUM_FETCH, c);
+                    if (c != SIMB_CONTENT_NONE) emit<INSTR>(ln, md, 0, c);
+                }
+                break;
+            }
+            case MT_BATCHER: {  // batcher.rs:208-221
+                uint32_t len = ln.W(md.wrow) & 0xFFFFu;
+                bool le = len <= md.cap, ge2 = (uint64_t)len >= 2ull * (uint64_t)md.cap;
+                if (le && ge2) { ln.err = 5; break; }
+                if (le) {  // release_full_queue :125-141
+                    ln.set_phase(m, 0);
+                    ln.D(urow) = SIMB_INF;
+                    release_n<INSTR>(ln, m, md, len, 0, 0);
+                } else if (ge2) {  // release_multiple :161-177
+                    ln.set_phase(m, 2);
+                    ln.D(urow) = 0.0;
+                    release_n<INSTR>(ln, m, md, md.cap, 0, 0);
+                } else {  // release_partial_queue :143-159
+                    ln.set_phase(m, 1);
+                    ln.D(urow) = md.p0;
+                    release_n<INSTR>(ln, m, md, md.cap, 0, 0);
+                }
+                break;
+            }
+            default:  // MT_PASSIVE never becomes imminent
+                break;
+        }
+    }
+
+    // ================================================================================================
+    // Simulation::step (mod.rs:198-272) for one lane.  `live` lanes execute;
+    // the others only take part in the warp-level votes.
+    // ================================================================================================
+    template <bool INSTR>
+    SIMB_HD void step(Lane& ln, bool live) {
+        const uint32_t M = net.n_models;
+        const bool had = live && ln.npend > 0;
+        uint32_t nev = 0;
+        // ---- external events: model order, then message order (:202-223) ----
+        if (warp_any(had)) {
+            uint32_t tmask = 0;
+            const uint32_t np = had ? ln.npend : 0u;
+            for (uint32_t j = 0; j < np; j++) {
+                uint32_t t = ROUTE_TGT(ln.W(net.wrow_pend + 2 * j + 1));
+                if (t < M) tmask |= 1u << t;  // a target id matching no model is silently dropped
+            }
+            uint32_t wm = warp_or(tmask);
+            while (wm) {
+                const int m = lowest_bit(wm);
+                wm &= wm - 1u;
+                if (((tmask >> m) & 1u) && !ln.err) {
+                    const SimbModelDesc& md = net.models[m];
+                    for (uint32_t j = 0; j < np && !ln.err; j++) {
+                        uint32_t rw = ln.W(net.wrow_pend + 2 * j + 1);
+                        if (ROUTE_TGT(rw) != (uint32_t)m) continue;
+                        nev++;
+                        events_ext<INSTR>(ln, (uint32_t)m, md, ROUTE_PORT(rw), ln.W(net.wrow_pend + 2 * j));
+                    }
+                }
+            }
+        }
+        // A failed events_ext aborts the step (`?` at :222); the replication freezes.
+        const bool go = live && !ln.err;
+        // ---- time advance (:225-236) ----
+        double dt = 0.0;
+        if (go && !had) {
+            dt = SIMB_INF;
+            for (uint32_t m = 0; m < M; m++) dt = fmin(dt, ln.D(net.drow_until + m));
+        }
+        uint32_t zmask = 0;
+        if (go) {
+            for (uint32_t m = 0; m < M; m++) {
+                double u = ln.D(net.drow_until + m);
+                if (!had && net.models[m].type != MT_PASSIVE) {
+                    u = u - dt;
+                    ln.D(net.drow_until + m) = u;
+                }
+                if (u == 0.0) zmask |= 1u << m;
+            }
+            ln.time = ln.time + dt;
+            ln.npend = 0;  // the mailbox is consumed; events_int refills it from slot 0
+        }
+        // ---- internal events in model order (:237-268) ----
+        uint32_t wm = warp_or(zmask);
+        while (wm) {
+            const int m = lowest_bit(wm);
+            wm &= wm - 1u;
+            if (((zmask >> m) & 1u) && !ln.err) {
+                nev++;
+                events_int<INSTR>(ln, (uint32_t)m, net.models[m]);
+            }
+        }
+        if (go) {
+            ln.events += nev;
+            if (!ln.err) ln.steps++;
+        } else if (live) {
+            ln.events += nev;
+        }
+    }
+};
+
+}  // namespace simb

@@ -1,0 +1,643 @@
+// sim_b200/csrc/lower.cpp -- JSON (SURVEY.md Appendix E wire schema) -> SimbNetDesc.
+// Replaces, for the batched path, Model::deserialize + model_factory::create
+// (sim/src/models/model.rs:43-50, model_factory.rs:65-77) and the per-step string matching of
+// Simulation::get_message_target_ids/ports (sim/src/simulator/mod.rs:155-182): ids, ports and
+// connectors are resolved ONCE into integer routes kept in connector order.
+#include "lower.hpp"
+
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "json.hpp"
+
+namespace simb {
+
+using json::Value;
+
+static const char* ACTION_NAMES[ACT_COUNT] = {
+    "Initialization", "Generation", "Arrival", "Processing Start", "Drop", "Departure",
+    "Activation", "Deactivation", "Pass", "Block", "Start", "Stop", "Minimum Fetch", "Maximum Fetch"};
+const char* action_name(int a) { return (a >= 0 && a < ACT_COUNT) ? ACTION_NAMES[a] : "?"; }
+
+const char* status_name(int s) {
+    switch (s) {
+        case 0: return "Ok";
+        case 1: return "InvalidModelConfiguration";
+        case 2: return "ModelNotFound";
+        case 3: return "PortNotFound";
+        case 4: return "ModelCloneError";
+        case 5: return "InvalidModelState";
+        case 6: return "EventSchedulingError";
+        case 7: return "InvalidMessage";
+        case 8: return "SerializationError";
+        case 9: return "EmptyPolynomial";
+        case 10: return "PrerequisiteCalcError";
+        case 11: return "FloatConvError";
+        case 12: return "DroppedMessageError";
+        case 13: return "JSONError";
+        case 14: return "BetaError";
+        case 15: return "ExpError";
+        case 16: return "GammaError";
+        case 17: return "NormalError";
+        case 18: return "TriangularError";
+        case 19: return "WeibullError";
+        case 20: return "BernoulliError";
+        case 21: return "GeoError";
+        case 22: return "PoissonError";
+        case 23: return "WeightedError";
+        case 32: return "CapacityError";
+        case 33: return "UnsupportedModel";
+        case 34: return "Panic";
+        case 35: return "CudaError";
+        case 36: return "InvalidArgument";
+        case 37: return "StreamExhausted";
+    }
+    return "Unknown";
+}
+
+int HostNet::find_model(const std::string& id) const {
+    for (size_t i = 0; i < models.size(); i++)
+        if (models[i].id == id) return (int)i;
+    return -1;
+}
+uint32_t HostNet::intern(const std::string& s, bool* overflow) {
+    for (size_t i = 0; i < names.size(); i++)
+        if (names[i] == s) return (uint32_t)i;
+    if (names.size() >= SIMB_MAX_NAMES) {
+        if (overflow) *overflow = true;
+        return 0;
+    }
+    names.push_back(s);
+    return (uint32_t)(names.size() - 1);
+}
+// "<prefix> <n>" with n decimal, no leading zero, n < 0xFFFFFF  ->  intern(prefix) << 24 | n
+// anything else                                               ->  intern(whole) << 24 | 0xFFFFFF
+uint32_t HostNet::content_code(const std::string& content, bool* overflow) {
+    size_t sp = content.rfind(' ');
+    if (sp != std::string::npos && sp > 0 && sp + 1 < content.size()) {
+        size_t nd = content.size() - sp - 1;
+        const char* dg = content.c_str() + sp + 1;
+        bool ok = nd <= 8 && !(nd > 1 && dg[0] == '0');
+        uint64_t n = 0;
+        for (size_t i = 0; ok && i < nd; i++) {
+            if (dg[i] < '0' || dg[i] > '9') ok = false;
+            else n = n * 10 + (uint64_t)(dg[i] - '0');
+        }
+        if (ok && n < SIMB_NUM_LITERAL) return (intern(content.substr(0, sp), overflow) << 24) | (uint32_t)n;
+    }
+    return (intern(content, overflow) << 24) | SIMB_NUM_LITERAL;
+}
+std::string HostNet::render(uint32_t code) const {
+    if (code == SIMB_CONTENT_NONE) return "";
+    uint32_t p = code >> 24, n = code & 0xFFFFFFu;
+    std::string s = p < names.size() ? names[p] : "?";
+    if (n == SIMB_NUM_LITERAL) return s;
+    return s + " " + std::to_string(n);
+}
+uint32_t HostNet::resolve_in_port(int m, const std::string& port) const {
+    const HostModel& hm = models[m];
+    for (size_t i = 0; i < hm.ports_in.size(); i++)
+        if (hm.ports_in[i] == port) return (uint32_t)i;  // first match wins, as the if-chains do
+    return SIMB_PORT_UNKNOWN;
+}
+
+namespace {
+
+struct Ctx {
+    std::string* err;
+    int fail(int code, const std::string& msg) {
+        if (err && err->empty()) *err = msg;
+        return code;
+    }
+};
+
+bool get_str(const Value& obj, const char* key, std::string* out) {
+    const Value* v = obj.get(key);
+    if (!v || !v->is_string()) return false;
+    *out = v->str;
+    return true;
+}
+bool get_num(const Value& obj, const char* key, double* out) {
+    const Value* v = obj.get(key);
+    if (!v) return false;
+    if (v->is_number()) {
+        *out = v->num;
+        return true;
+    }
+    // serde_json writes non-finite floats as null; YAML-style spellings are accepted too
+    if (v->kind == Value::Null) {
+        *out = std::numeric_limits<double>::infinity();
+        return true;
+    }
+    if (v->is_string()) {
+        if (v->str == ".inf" || v->str == "inf" || v->str == "Infinity") {
+            *out = std::numeric_limits<double>::infinity();
+            return true;
+        }
+    }
+    return false;
+}
+bool get_str_list(const Value& obj, const char* key, std::vector<std::string>* out) {
+    const Value* v = obj.get(key);
+    if (!v || !v->is_array()) return false;
+    for (auto& e : v->arr) {
+        if (!e.is_string()) return false;
+        out->push_back(e.str);
+    }
+    return true;
+}
+
+// Continuous (random_variable.rs:17-28): {"exp":{"lambda":..}} etc.  Inner field names keep their
+// Rust spelling (std_dev).
+int lower_continuous(Ctx& c, const Value* v, SimbModelDesc* md) {
+    if (!v || !v->is_object() || v->obj.size() != 1) return c.fail(13, "expected a one-variant random variable object");
+    const std::string& kind = v->obj[0].first;
+    const Value& p = v->obj[0].second;
+    md->dist_err = 0;
+    if (kind == "exp") {
+        double lambda;
+        if (!get_num(p, "lambda", &lambda)) return c.fail(13, "exp: missing field `lambda`");
+        md->dist_kind = DK_EXP;
+        if (!(lambda > 0.0)) md->dist_err = 15;  // Exp::new fails per draw
+        md->p0 = 1.0 / lambda;                    // lambda_inverse
+        return 0;
+    }
+    if (kind == "normal") {
+        double mean, sd;
+        if (!get_num(p, "mean", &mean) || !get_num(p, "std_dev", &sd)) return c.fail(13, "normal: missing field");
+        md->dist_kind = DK_NORMAL;
+        if (!std::isfinite(sd)) md->dist_err = 17;
+        md->p0 = mean;
+        md->p1 = sd;
+        return 0;
+    }
+    if (kind == "triangular") {
+        double mn, mx, mode;
+        if (!get_num(p, "min", &mn) || !get_num(p, "max", &mx) || !get_num(p, "mode", &mode))
+            return c.fail(13, "triangular: missing field");
+        md->dist_kind = DK_TRIANGULAR;
+        if (!(mx >= mode) || !(mode >= mn) || !(mx != mn)) md->dist_err = 18;
+        md->p0 = mn;
+        md->p1 = mx;
+        md->p2 = mode;
+        return 0;
+    }
+    if (kind == "uniform") {
+        double low, high;
+        if (!get_num(p, "min", &low) || !get_num(p, "max", &high)) return c.fail(13, "uniform: missing field");
+        md->dist_kind = DK_UNIFORM;
+        // rand 0.8 UniformFloat::new panics unless low < high and both finite
+        if (!(low < high) || !std::isfinite(low) || !std::isfinite(high) || !std::isfinite(high - low)) {
+            md->dist_err = 34;
+            return 0;
+        }
+        const double max_rand = 1.0 - 2.220446049250313e-16;
+        double scale = high - low;
+        while (scale * max_rand + low >= high) {
+            uint64_t b;
+            std::memcpy(&b, &scale, 8);
+            b -= 1;
+            std::memcpy(&scale, &b, 8);
+        }
+        md->p0 = low;
+        md->p1 = scale;
+        return 0;
+    }
+    if (kind == "beta" || kind == "gamma" || kind == "logNormal" || kind == "weibull")
+        return c.fail(33, "random variable `" + kind + "` is outside the accelerated path (SURVEY.md 8f-3)");
+    return c.fail(13, "unknown variant `" + kind + "`");
+}
+
+void uniform_int_params(uint64_t low, uint64_t high, SimbModelDesc* md) {
+    uint64_t range = (high - 1) - low + 1;
+    uint64_t reject = (UINT64_MAX - range + 1) % range;
+    md->q0 = low;
+    md->q1 = range;
+    md->q2 = UINT64_MAX - reject;
+}
+
+int lower_index(Ctx& c, const Value* v, SimbModelDesc* md, SimbNetDesc* net, uint32_t* n_wcum) {
+    if (!v || !v->is_object() || v->obj.size() != 1) return c.fail(13, "expected a one-variant index random variable");
+    const std::string& kind = v->obj[0].first;
+    const Value& p = v->obj[0].second;
+    md->dist_err = 0;
+    if (kind == "uniform") {
+        const Value* mn = p.get("min");
+        const Value* mx = p.get("max");
+        if (!mn || !mx || !mn->is_uint || !mx->is_uint) return c.fail(13, "index uniform: min/max must be unsigned integers");
+        if (!(mn->u < mx->u)) md->dist_err = 34;  // Uniform::new asserts low < high
+        else uniform_int_params(mn->u, mx->u, md);
+        return 0;
+    }
+    if (kind == "weightedIndex") {
+        const Value* w = p.get("weights");
+        if (!w || !w->is_array()) return c.fail(13, "weightedIndex: missing field `weights`");
+        md->flags |= MF_INDEX_WEIGHTED;
+        if (w->arr.empty()) {
+            md->dist_err = 23;
+            return 0;
+        }
+        md->wtab = (uint16_t)*n_wcum;
+        uint64_t total = 0;
+        for (size_t i = 0; i < w->arr.size(); i++) {
+            if (!w->arr[i].is_uint) return c.fail(13, "weightedIndex: weights must be unsigned integers");
+            if (i > 0) {
+                if (*n_wcum >= SIMB_MAX_WEIGHTS) return c.fail(32, "too many gateway weights");
+                net->wcum[(*n_wcum)++] = total;
+            }
+            total += w->arr[i].u;
+        }
+        md->n_w = (uint16_t)(w->arr.size() - 1);
+        if (total == 0) md->dist_err = 23;  // AllWeightsZero
+        else uniform_int_params(0, total, md);
+        return 0;
+    }
+    return c.fail(13, "unknown variant `" + kind + "`");
+}
+
+struct PendingModel {
+    // lowering scratch per model
+    uint32_t n_words = 0, n_dwords = 0;
+    bool ring0 = false, ring1 = false, ringd = false;
+    uint32_t ring_cap = 0;
+    double u0 = std::numeric_limits<double>::infinity();
+    uint32_t phase0 = 0;
+    std::vector<uint32_t> words0;
+    std::vector<std::string> preload;  // queue contents from `state`
+    uint32_t preload_next_port = 0;
+};
+
+uint32_t clamp_u32(uint64_t v, uint32_t hi) { return v > hi ? hi : (uint32_t)v; }
+
+}  // namespace
+
+int lower_network(const char* models_json, const char* connectors_json, const LowerOptions& opt, HostNet* out,
+                  std::string* err) {
+    Ctx c{err};
+    if (!models_json || !connectors_json || !out) return c.fail(36, "null argument");
+    Value jm, jc;
+    {
+        json::Parser p(models_json);
+        if (!p.parse(jm)) return c.fail(13, "models: " + p.err);
+        json::Parser q(connectors_json);
+        if (!q.parse(jc)) return c.fail(13, "connectors: " + q.err);
+    }
+    if (!jm.is_array() || !jc.is_array()) return c.fail(13, "models and connectors must be JSON arrays");
+    if (jm.arr.size() > SIMB_MAX_MODELS) return c.fail(32, "more than 32 models");
+    if (jm.arr.empty()) return c.fail(1, "a simulation needs at least one model");
+
+    HostNet& hn = *out;
+    hn = HostNet();
+    SimbNetDesc& net = hn.desc;
+    std::memset(&net, 0, sizeof net);
+    net.n_models = (uint32_t)jm.arr.size();
+    std::vector<PendingModel> pm(jm.arr.size());
+    uint32_t n_wcum = 0;
+    const uint32_t qcap = opt.queue_capacity ? clamp_u32(opt.queue_capacity, 65535) : 64;
+    const uint32_t tcap = qcap < 4 ? 4 : (qcap > 16 ? 16 : qcap);  // transient queues (drain every step)
+    bool overflow = false;
+
+    // ---- pass 1: models -------------------------------------------------------------------------
+    for (size_t i = 0; i < jm.arr.size(); i++) {
+        const Value& j = jm.arr[i];
+        if (!j.is_object()) return c.fail(13, "model entries must be objects");
+        HostModel hm;
+        if (!get_str(j, "id", &hm.id)) return c.fail(13, "model: missing field `id`");
+        if (!get_str(j, "type", &hm.type)) return c.fail(13, "model " + hm.id + ": missing field `type`");
+        if (const Value* sr = j.get("storeRecords")) hm.store_records = sr->kind == Value::Bool && sr->b;
+        SimbModelDesc& md = net.models[i];
+        PendingModel& p = pm[i];
+        md.dist_kind = DK_NONE;
+        md.cap = SIMB_CAP_INF;
+        if (hm.store_records) md.flags |= MF_STORE_RECORDS;
+        const Value* pin = j.get("portsIn");
+        const Value* pout = j.get("portsOut");
+        const Value* state = j.get("state");
+        auto need_ports = [&](bool in, bool outp) -> bool {
+            return (!in || (pin && pin->is_object())) && (!outp || (pout && pout->is_object()));
+        };
+        auto port = [&](const Value* obj, const char* key, std::vector<std::string>* dst) -> bool {
+            std::string s;
+            if (!obj || !get_str(*obj, key, &s)) return false;
+            dst->push_back(s);
+            return true;
+        };
+        const std::string& t = hm.type;
+        if (t == "Generator") {  // generator.rs:24-40
+            md.type = MT_GENERATOR;
+            if (!need_ports(false, true) || !port(pout, "job", &hm.ports_out)) return c.fail(13, hm.id + ": portsOut.job missing");
+            int e = lower_continuous(c, j.get("messageInterdepartureTime"), &md);
+            if (e) return e;
+            md.prefix = hn.intern(hm.ports_out[0], &overflow) << 24;
+            p.n_words = 1;  // last_job
+            p.words0 = {0};
+            p.u0 = 0.0;     // State::default (:60-70)
+            if (state && state->is_object()) {
+                std::string ph;
+                if (get_str(*state, "phase", &ph)) p.phase0 = ph == "Generating" ? 1 : 0;
+                get_num(*state, "untilNextEvent", &p.u0);
+                double lj;
+                if (get_num(*state, "lastJob", &lj)) p.words0[0] = (uint32_t)lj;
+            }
+        } else if (t == "Processor") {  // processor.rs:24-38
+            md.type = MT_PROCESSOR;
+            if (!need_ports(true, true) || !port(pin, "job", &hm.ports_in) || !port(pout, "job", &hm.ports_out))
+                return c.fail(13, hm.id + ": portsIn.job / portsOut.job missing");
+            int e = lower_continuous(c, j.get("serviceTime"), &md);
+            if (e) return e;
+            uint64_t cap = UINT64_MAX;  // max_usize default (:28-29,40-42)
+            if (const Value* qc = j.get("queueCapacity")) {
+                if (!qc->is_uint) return c.fail(13, hm.id + ": queueCapacity must be an unsigned integer");
+                cap = qc->u;
+            }
+            p.ring0 = true;
+            if (cap <= 4096) {
+                md.cap = (uint32_t)cap;
+                p.ring_cap = cap ? (uint32_t)cap : 1;
+            } else {
+                md.cap = SIMB_CAP_INF;  // never "full"; the device ring raises SIMB_ERR_CAPACITY instead
+                p.ring_cap = qcap;
+            }
+            p.n_words = 1;  // head|len
+            p.words0 = {0};
+            if (state && state->is_object()) {
+                std::string ph;
+                if (get_str(*state, "phase", &ph)) p.phase0 = ph == "Active" ? 1 : 0;
+                get_num(*state, "untilNextEvent", &p.u0);
+                get_str_list(*state, "queue", &p.preload);
+                if (p.preload.size() > 65535) return c.fail(32, hm.id + ": preloaded queue too long");
+                if (p.preload.size() > p.ring_cap) p.ring_cap = (uint32_t)p.preload.size();
+            }
+        } else if (t == "Storage") {  // storage.rs:15-24
+            md.type = MT_STORAGE;
+            if (!need_ports(true, true) || !port(pin, "put", &hm.ports_in) || !port(pin, "get", &hm.ports_in) ||
+                !port(pout, "stored", &hm.ports_out))
+                return c.fail(13, hm.id + ": portsIn.put/get or portsOut.stored missing");
+            p.n_words = 1;
+            p.words0 = {SIMB_CONTENT_NONE};
+            if (state && state->is_object()) {
+                std::string ph, job;
+                if (get_str(*state, "phase", &ph)) p.phase0 = ph == "JobFetch" ? 1 : 0;
+                get_num(*state, "untilNextEvent", &p.u0);
+                if (get_str(*state, "job", &job)) p.preload = {job};  // interned after all generators
+            }
+        } else if (t == "LoadBalancer") {  // load_balancer.rs:15-24
+            md.type = MT_LOAD_BALANCER;
+            if (!need_ports(true, true) || !port(pin, "job", &hm.ports_in) || !get_str_list(*pout, "flowPaths", &hm.ports_out))
+                return c.fail(13, hm.id + ": portsIn.job / portsOut.flowPaths missing");
+            p.ring0 = true;
+            p.ring_cap = tcap;
+            p.n_words = 2;  // head|len, next_port_out
+            p.words0 = {0, 0};
+            if (state && state->is_object()) {
+                std::string ph;
+                if (get_str(*state, "phase", &ph)) p.phase0 = ph == "LoadBalancing" ? 1 : 0;
+                get_num(*state, "untilNextEvent", &p.u0);
+                double np;
+                if (get_num(*state, "nextPortOut", &np)) p.words0[1] = (uint32_t)np;
+                get_str_list(*state, "jobs", &p.preload);
+                if (p.preload.size() > p.ring_cap) p.ring_cap = clamp_u32(p.preload.size(), 65535);
+            }
+        } else if (t == "Gate") {  // gate.rs:19-28
+            md.type = MT_GATE;
+            if (!need_ports(true, true) || !port(pin, "job", &hm.ports_in) || !port(pin, "activation", &hm.ports_in) ||
+                !port(pin, "deactivation", &hm.ports_in) || !port(pout, "job", &hm.ports_out))
+                return c.fail(13, hm.id + ": gate ports missing");
+            p.ring0 = true;
+            p.ring_cap = tcap;
+            p.n_words = 1;
+            p.words0 = {0};
+            if (state && state->is_object()) {
+                std::string ph;
+                if (get_str(*state, "phase", &ph)) p.phase0 = ph == "Closed" ? 1 : ph == "Pass" ? 2 : 0;
+                get_num(*state, "untilNextEvent", &p.u0);
+            }
+        } else if (t == "ExclusiveGateway") {  // exclusive_gateway.rs:20-32
+            md.type = MT_EXCLUSIVE_GATEWAY;
+            if (!need_ports(true, true) || !get_str_list(*pin, "flowPaths", &hm.ports_in) ||
+                !get_str_list(*pout, "flowPaths", &hm.ports_out))
+                return c.fail(13, hm.id + ": flowPaths missing");
+            int e = lower_index(c, j.get("portWeights"), &md, &net, &n_wcum);
+            if (e) return e;
+            p.ring0 = true;
+            p.ring_cap = tcap;
+            p.n_words = 1;
+            p.words0 = {0};
+        } else if (t == "ParallelGateway") {  // parallel_gateway.rs:19-28
+            md.type = MT_PARALLEL_GATEWAY;
+            if (!need_ports(true, true) || !get_str_list(*pin, "flowPaths", &hm.ports_in) ||
+                !get_str_list(*pout, "flowPaths", &hm.ports_out))
+                return c.fail(13, hm.id + ": flowPaths missing");
+            p.ring0 = p.ring1 = true;  // (content, count) table
+            p.ring_cap = qcap;
+            p.n_words = 1;  // entries
+            p.words0 = {0};
+        } else if (t == "StochasticGate") {  // stochastic_gate.rs:19-31
+            md.type = MT_STOCHASTIC_GATE;
+            if (!need_ports(true, true) || !port(pin, "job", &hm.ports_in) || !port(pout, "job", &hm.ports_out))
+                return c.fail(13, hm.id + ": ports missing");
+            const Value* pd = j.get("passDistribution");
+            const Value* b = pd ? pd->get("bernoulli") : nullptr;
+            double pr;
+            if (!b || !get_num(*b, "p", &pr)) return c.fail(13, hm.id + ": passDistribution.bernoulli.p missing");
+            if (!(pr >= 0.0 && pr < 1.0)) {  // rand 0.8 Bernoulli::new
+                if (pr == 1.0) md.flags |= MF_BERNOULLI_ALWAYS;
+                else md.dist_err = 20;
+            } else {
+                md.q0 = (uint64_t)(pr * (2.0 * (double)(1ull << 63)));
+            }
+            p.ring0 = p.ring1 = true;  // (content, pass)
+            p.ring_cap = tcap;
+            p.n_words = 1;
+            p.words0 = {0};
+        } else if (t == "Stopwatch") {  // stopwatch.rs:21-32
+            md.type = MT_STOPWATCH;
+            if (!need_ports(true, true) || !port(pin, "start", &hm.ports_in) || !port(pin, "stop", &hm.ports_in) ||
+                !port(pin, "metric", &hm.ports_in) || !port(pout, "job", &hm.ports_out))
+                return c.fail(13, hm.id + ": stopwatch ports missing");
+            std::string metric;
+            if (get_str(j, "metric", &metric)) {
+                if (metric == "Maximum") md.flags |= MF_METRIC_MAX;
+                else if (metric != "Minimum") return c.fail(13, hm.id + ": unknown metric `" + metric + "`");
+            }
+            p.ring0 = p.ring1 = p.ringd = true;  // incomplete-job table
+            p.ring_cap = qcap;
+            p.n_words = 4;  // entries, best content, next seq, best seq
+            p.words0 = {0, SIMB_CONTENT_NONE, 0, 0};
+            p.n_dwords = 1;  // best duration
+        } else if (t == "Batcher") {  // batcher.rs:22-33
+            md.type = MT_BATCHER;
+            if (!need_ports(true, true) || !port(pin, "job", &hm.ports_in) || !port(pout, "job", &hm.ports_out))
+                return c.fail(13, hm.id + ": ports missing");
+            double mbt;
+            const Value* mbs = j.get("maxBatchSize");
+            if (!get_num(j, "maxBatchTime", &mbt) || !mbs || !mbs->is_uint) return c.fail(13, hm.id + ": maxBatchTime/maxBatchSize missing");
+            md.p0 = mbt;
+            md.cap = clamp_u32(mbs->u, 0xFFFFFFFEu);
+            p.ring0 = true;
+            p.ring_cap = clamp_u32(2ull * (uint64_t)md.cap + 8ull, 65535);
+            p.n_words = 1;
+            p.words0 = {0};
+        } else if (t == "Passive") {  // sim/tests/custom.rs:18-86
+            md.type = MT_PASSIVE;
+            if (pin && pin->is_object()) port(pin, "job", &hm.ports_in);
+        } else {
+            return c.fail(33, "model type `" + t + "` cannot run on the device (custom and Coupled models are out of scope)");
+        }
+        md.n_in = (uint8_t)(hm.ports_in.size() > 254 ? 254 : hm.ports_in.size());
+        md.n_out = (uint8_t)hm.ports_out.size();
+        if (hm.ports_out.size() > 64) return c.fail(32, hm.id + ": too many output ports");
+        hn.models.push_back(hm);
+    }
+    for (size_t i = 0; i < hn.models.size(); i++)
+        for (size_t k = i + 1; k < hn.models.size(); k++)
+            if (hn.models[i].id == hn.models[k].id) return c.fail(1, "duplicate model id `" + hn.models[i].id + "`");
+
+    // ---- connectors (coupling.rs:7-17) ----------------------------------------------------------
+    for (auto& j : jc.arr) {
+        if (!j.is_object()) return c.fail(13, "connector entries must be objects");
+        HostConnector hc;
+        if (!get_str(j, "id", &hc.id) || !get_str(j, "sourceID", &hc.source_id) || !get_str(j, "targetID", &hc.target_id) ||
+            !get_str(j, "sourcePort", &hc.source_port) || !get_str(j, "targetPort", &hc.target_port))
+            return c.fail(13, "connector: missing field (id, sourceID, targetID, sourcePort, targetPort)");
+        hn.connectors.push_back(hc);
+    }
+    if (hn.connectors.size() > 0xFFFE) return c.fail(32, "too many connectors");
+    net.n_connectors = (uint32_t)hn.connectors.size();
+
+    // ---- routes: (model, out-port) -> connectors in connector order (mod.rs:155-182) -------------
+    uint32_t n_routes = 0, n_outports = 0, pending_bound = 0;
+    for (size_t i = 0; i < hn.models.size(); i++) {
+        SimbModelDesc& md = net.models[i];
+        md.out_base = (uint16_t)n_outports;
+        uint32_t fan_total = 0;
+        for (size_t k = 0; k < hn.models[i].ports_out.size(); k++) {
+            if (n_outports >= SIMB_MAX_OUT_PORTS) return c.fail(32, "too many output ports in the network");
+            net.route_begin[n_outports++] = (uint16_t)n_routes;
+            for (size_t ci = 0; ci < hn.connectors.size(); ci++) {
+                const HostConnector& hc = hn.connectors[ci];
+                if (hc.source_id != hn.models[i].id || hc.source_port != hn.models[i].ports_out[k]) continue;
+                if (n_routes >= SIMB_MAX_ROUTES) return c.fail(32, "too many routes");
+                int tm = hn.find_model(hc.target_id);
+                SimbRoute r;
+                r.tgt_model = tm < 0 ? 0xFF : (uint8_t)tm;  // unknown target: never delivered, but it
+                                                            // still makes the next step zero-time
+                r.tgt_port = tm < 0 ? SIMB_PORT_UNKNOWN : (uint8_t)hn.resolve_in_port(tm, hc.target_port);
+                r.connector = (uint16_t)ci;
+                net.routes[n_routes++] = r;
+                fan_total++;
+            }
+        }
+        net.route_begin[n_outports] = (uint16_t)n_routes;
+        // mailbox bound: messages one firing of this model can emit
+        uint32_t fan_max = 0;
+        for (size_t k = 0; k < hn.models[i].ports_out.size(); k++) {
+            uint32_t f = net.route_begin[md.out_base + k + 1] - net.route_begin[md.out_base + k];
+            if (f > fan_max) fan_max = f;
+        }
+        uint32_t inbound = 0;
+        for (auto& hc : hn.connectors)
+            if (hc.target_id == hn.models[i].id) inbound++;
+        switch (md.type) {
+            case MT_PARALLEL_GATEWAY: pending_bound += fan_total; break;
+            case MT_GATE:
+            case MT_EXCLUSIVE_GATEWAY: pending_bound += fan_max * (inbound ? inbound : 1); break;
+            case MT_BATCHER: pending_bound += fan_max * (md.cap > 64 ? 64 : md.cap); break;
+            default: pending_bound += fan_max; break;
+        }
+    }
+    net.n_routes = n_routes;
+    uint32_t mp = opt.max_pending ? opt.max_pending : (pending_bound ? pending_bound : 1);
+    if (mp > 255) mp = 255;
+    net.max_pending = mp;
+
+    // ---- statistic model ------------------------------------------------------------------------
+    if (!opt.stat_model_id.empty()) {
+        int sm = hn.find_model(opt.stat_model_id);
+        if (sm < 0) return c.fail(2, "stat_model_id `" + opt.stat_model_id + "` is not a model of this simulation");
+        if (net.models[sm].type != MT_PROCESSOR) return c.fail(1, "stat_model_id must name a Processor");
+        net.models[sm].flags |= MF_STAT;
+        pm[sm].ringd = true;
+        hn.stat_model = sm;
+    }
+
+    // ---- state tile layout ------------------------------------------------------------------------
+    uint16_t dr = 0, wr = 0;
+    net.drow_time = dr++;
+    net.drow_until = dr;
+    dr += (uint16_t)net.n_models;
+    if (hn.stat_model >= 0) net.drow_wait = dr++;
+    net.wrow_ctl = wr++;
+    net.wrow_rng = wr;
+    wr += (opt.rng_kind == 1) ? 4 : 1;
+    net.wrow_steps = wr++;
+    net.wrow_events = wr++;
+    if (opt.instrument) {
+        net.wrow_hash = wr;
+        wr += 2;
+    }
+    net.wrow_phase = wr;
+    net.n_phase_words = (uint16_t)((net.n_models + 15) / 16);
+    wr += net.n_phase_words;
+    if (hn.stat_model >= 0) net.wrow_waitn = wr++;
+    for (size_t i = 0; i < pm.size(); i++) {
+        net.models[i].wrow = wr;
+        wr += (uint16_t)pm[i].n_words;
+        if (pm[i].n_dwords) {
+            net.models[i].drow = dr;
+            dr += (uint16_t)pm[i].n_dwords;
+        }
+    }
+    net.wrow_pend = wr;
+    wr += (uint16_t)(2 * net.max_pending);
+    net.n_drows = dr;
+    net.n_wrows = wr;
+
+    // ---- rings ------------------------------------------------------------------------------------
+    uint32_t rw = 0, rd = 0;
+    for (size_t i = 0; i < pm.size(); i++) {
+        SimbModelDesc& md = net.models[i];
+        md.ring_cap = pm[i].ring_cap;
+        if (pm[i].ring0) {
+            md.ring_w0 = rw;
+            rw += md.ring_cap;
+        }
+        if (pm[i].ring1) {
+            md.ring_w1 = rw;
+            rw += md.ring_cap;
+        }
+        if (pm[i].ringd) {
+            md.ring_d = rd;
+            rd += md.ring_cap;
+        }
+    }
+    hn.ring_w_slots = rw;
+    hn.ring_d_slots = rd;
+
+    // ---- initial row values ---------------------------------------------------------------------
+    hn.d_init.assign(net.n_drows, 0.0);
+    hn.w_init.assign(net.n_wrows, 0u);
+    uint32_t phase_words[2] = {0, 0};
+    for (size_t i = 0; i < pm.size(); i++) {
+        const SimbModelDesc& md = net.models[i];
+        hn.d_init[net.drow_until + i] = pm[i].u0;
+        phase_words[i / 16] |= (pm[i].phase0 & 3u) << (2 * (i % 16));
+        for (size_t k = 0; k < pm[i].words0.size(); k++) hn.w_init[md.wrow + k] = pm[i].words0[k];
+        if (md.type == MT_STOPWATCH) hn.d_init[md.drow] = 0.0;
+        if (md.type == MT_STORAGE) {
+            if (!pm[i].preload.empty()) hn.w_init[md.wrow] = hn.content_code(pm[i].preload[0], &overflow);
+        } else if (!pm[i].preload.empty()) {  // `state.queue` / `state.jobs` injected on input (tests/web.rs:30-46)
+            for (size_t k = 0; k < pm[i].preload.size(); k++)
+                hn.ring_preload.push_back(RingPreload{md.ring_w0 + (uint32_t)k, hn.content_code(pm[i].preload[k], &overflow)});
+            hn.w_init[md.wrow] = (uint32_t)pm[i].preload.size();  // head 0, len n
+        }
+        if (net.models[i].dist_kind == DK_EXP) net.uses_exp = 1;
+        if (net.models[i].dist_kind == DK_NORMAL) net.uses_normal = 1;
+    }
+    for (uint32_t k = 0; k < net.n_phase_words; k++) hn.w_init[net.wrow_phase + k] = phase_words[k];
+    if (overflow) return c.fail(32, "content intern table overflow (more than 255 distinct names)");
+    return 0;
+}
+
+}  // namespace simb

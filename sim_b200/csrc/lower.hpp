@@ -1,0 +1,60 @@
+// sim_b200/csrc/lower.hpp -- descriptor lowering: the native equivalent of the reference's
+// serde + model_factory path (sim/src/models/model.rs:28-50, model_factory.rs:65-77,
+// sim_derive/src/lib.rs:9-32): JSON models/connectors -> validated SimbNetDesc + host metadata.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "net.h"
+
+namespace simb {
+
+struct LowerOptions {
+    uint32_t queue_capacity = 64;
+    uint32_t max_pending = 0;
+    bool instrument = false;
+    int rng_kind = 0;
+    std::string stat_model_id;
+};
+
+struct HostModel {
+    std::string id, type;
+    std::vector<std::string> ports_in, ports_out;
+    bool store_records = false;
+};
+struct HostConnector {
+    std::string id, source_id, target_id, source_port, target_port;
+};
+struct RingPreload {
+    uint32_t slot;   // absolute slot in ring_w
+    uint32_t value;
+};
+
+struct HostNet {
+    SimbNetDesc desc;
+    std::vector<HostModel> models;
+    std::vector<HostConnector> connectors;
+    std::vector<std::string> names;       // content intern table (prefixes and literals)
+    std::vector<double> d_init;           // initial value of every f64 row
+    std::vector<uint32_t> w_init;         // initial value of every u32 row (ctl / rng rows are special-cased)
+    std::vector<RingPreload> ring_preload;
+    uint32_t ring_w_slots = 0, ring_d_slots = 0;
+    int stat_model = -1;
+
+    int find_model(const std::string& id) const;
+    uint32_t intern(const std::string& s, bool* overflow);
+    // canonical content code of an arbitrary string (DESIGN.md "content codes")
+    uint32_t content_code(const std::string& content, bool* overflow);
+    std::string render(uint32_t code) const;
+    // index of `port` among model m's input ports as the device sees it
+    uint32_t resolve_in_port(int m, const std::string& port) const;
+};
+
+// returns a simb_status; *err receives a human-readable reason
+int lower_network(const char* models_json, const char* connectors_json, const LowerOptions& opt, HostNet* out,
+                  std::string* err);
+
+const char* action_name(int action);
+const char* status_name(int status);
+
+}  // namespace simb

@@ -1,0 +1,346 @@
+"""Test networks.  The first group restates the networks of the reference's own tests
+(sim/tests/simulations.rs, sim/tests/web.rs, sim/tests/custom.rs; cited per function); the second
+group are the BASELINE.json configurations with the concrete shapes of SURVEY.md 8(d)."""
+from sim_b200 import (Batcher, BooleanRandomVariable, Connector, ContinuousRandomVariable, ExclusiveGateway, Gate,
+                      Generator, IndexRandomVariable, LoadBalancer, Metric, Model, ParallelGateway, Passive, Processor,
+                      StochasticGate, Stopwatch, Storage)
+
+Exp = ContinuousRandomVariable.Exp
+
+
+def _storage(i, store=False):
+    return Model.new(i, Storage.new("store", "read", "stored", store))
+
+
+def mm1(store_records=False, capacity=14, lam_gen=0.5, lam_proc=0.333333):
+    """simulations.rs:20-72 (BASELINE config 1/2): Generator Exp(0.5) -> Processor Exp(0.333333) cap 14 -> Storage."""
+    models = [
+        Model.new("generator-01", Generator.new(Exp(lam_gen), None, "job", store_records, None)),
+        Model.new("processor-01", Processor.new(Exp(lam_proc), capacity, "job", "processed", store_records, None)),
+        _storage("storage-01", store_records),
+    ]
+    connectors = [
+        Connector.new("connector-01", "generator-01", "processor-01", "job", "job"),
+        Connector.new("connector-02", "processor-01", "storage-01", "processed", "store"),
+    ]
+    return models, connectors
+
+
+def generator_storage():
+    """simulations.rs:132-160 step_until_activities"""
+    models = [Model.new("generator-01", Generator.new(Exp(0.5), None, "job", False, None)), _storage("storage-01")]
+    connectors = [Connector.new("connector-01", "generator-01", "storage-01", "job", "store")]
+    return models, connectors
+
+
+def exclusive_gateway(store_records=False):
+    """simulations.rs:258-345"""
+    models = [
+        Model.new("generator-01", Generator.new(Exp(5.0), None, "job", store_records, None)),
+        Model.new("exclusive-01", ExclusiveGateway.new(["in"], ["s01", "s02", "s03"],
+                                                        IndexRandomVariable.WeightedIndex([6, 3, 1]), store_records, None)),
+        _storage("storage-01", store_records), _storage("storage-02", store_records), _storage("storage-03", store_records),
+    ]
+    connectors = [
+        Connector.new("connector-01", "generator-01", "exclusive-01", "job", "in"),
+        Connector.new("connector-02", "exclusive-01", "storage-01", "s01", "store"),
+        Connector.new("connector-03", "exclusive-01", "storage-02", "s02", "store"),
+        Connector.new("connector-04", "exclusive-01", "storage-03", "s03", "store"),
+    ]
+    return models, connectors
+
+
+def gate_blocking(store_records=False):
+    """simulations.rs:382-463"""
+    models = [
+        Model.new("generator-01", Generator.new(Exp(10.0), None, "job", False, None)),
+        Model.new("generator-02", Generator.new(Exp(10.0), None, "job", False, None)),
+        Model.new("generator-03", Generator.new(Exp(1.0), None, "job", False, None)),
+        Model.new("gate-01", Gate.new("job", "activation", "deactivation", "job", store_records)),
+        _storage("storage-01"),
+    ]
+    connectors = [
+        Connector.new("connector-01", "generator-01", "gate-01", "job", "activation"),
+        Connector.new("connector-02", "generator-02", "gate-01", "job", "deactivation"),
+        Connector.new("connector-03", "generator-03", "gate-01", "job", "job"),
+        Connector.new("connector-04", "gate-01", "storage-01", "job", "store"),
+    ]
+    return models, connectors
+
+
+def load_balancer(store_records=False):
+    """simulations.rs:499-584"""
+    models = [
+        Model.new("generator-01", Generator.new(Exp(0.01), None, "job", False, None)),
+        Model.new("load-balancer-01", LoadBalancer.new("request", ["server-1", "server-2", "server-3"], store_records)),
+        _storage("storage-01"), _storage("storage-02"), _storage("storage-03"),
+    ]
+    connectors = [
+        Connector.new("connector-01", "generator-01", "load-balancer-01", "job", "request"),
+        Connector.new("connector-02", "load-balancer-01", "storage-01", "server-1", "store"),
+        Connector.new("connector-03", "load-balancer-01", "storage-02", "server-2", "store"),
+        Connector.new("connector-04", "load-balancer-01", "storage-03", "server-3", "store"),
+    ]
+    return models, connectors
+
+
+def storage_exchange():
+    """simulations.rs:608-638 injection_initiated_stored_value_exchange"""
+    models = [_storage("storage-01"), _storage("storage-02")]
+    connectors = [
+        Connector.new("connector-01", "storage-02", "storage-01", "stored", "store"),
+        Connector.new("connector-02", "storage-01", "storage-02", "stored", "store"),
+    ]
+    return models, connectors
+
+
+def parallel_gateway(store_records=False):
+    """simulations.rs:681-763"""
+    models = [
+        Model.new("generator-01", Generator.new(Exp(5.0), None, "job", False, None)),
+        Model.new("parallel-01", ParallelGateway.new(["in"], ["alpha", "beta", "delta"], store_records)),
+        Model.new("parallel-02", ParallelGateway.new(["alpha", "beta", "delta"], ["out"], store_records)),
+        _storage("storage-01"),
+    ]
+    connectors = [
+        Connector.new("connector-01", "generator-01", "parallel-01", "job", "in"),
+        Connector.new("connector-02", "parallel-01", "parallel-02", "alpha", "alpha"),
+        Connector.new("connector-03", "parallel-01", "parallel-02", "beta", "beta"),
+        Connector.new("connector-04", "parallel-01", "parallel-02", "delta", "delta"),
+        Connector.new("connector-05", "parallel-02", "storage-01", "out", "store"),
+    ]
+    return models, connectors
+
+
+def status_pair():
+    """simulations.rs:790-823 match_status_reporting"""
+    models = [
+        Model.new("generator-01", Generator.new(Exp(5.0), None, "job", False, None)),
+        Model.new("load-balancer-01", LoadBalancer.new("request", ["alpha", "beta", "delta"], False)),
+    ]
+    return models, []
+
+
+def stochastic_gate(store_records=False, p=0.2):
+    """simulations.rs:826-872"""
+    models = [
+        Model.new("generator-01", Generator.new(Exp(5.0), None, "job", False, None)),
+        Model.new("stochastic-gate-01", StochasticGate.new(BooleanRandomVariable.Bernoulli(p), "job", "job", store_records, None)),
+        _storage("storage-01"),
+    ]
+    connectors = [
+        Connector.new("connector-01", "generator-01", "stochastic-gate-01", "job", "job"),
+        Connector.new("connector-02", "stochastic-gate-01", "storage-01", "job", "store"),
+    ]
+    return models, connectors
+
+
+def batcher(store_records=False, max_time=10.0, max_size=10, lam=1.0):
+    """simulations.rs:896-939"""
+    models = [
+        Model.new("generator-01", Generator.new(Exp(lam), None, "job", False, None)),
+        Model.new("batcher-01", Batcher.new("job", "job", max_time, max_size, store_records)),
+        _storage("storage-01"),
+    ]
+    connectors = [
+        Connector.new("connector-01", "generator-01", "batcher-01", "job", "job"),
+        Connector.new("connector-02", "batcher-01", "storage-01", "job", "store"),
+    ]
+    return models, connectors
+
+
+def stopwatch(store_records=False):
+    """simulations.rs:967-1070 (note connector-04 names a port the processor does not have: it never fires)"""
+    models = [
+        Model.new("generator-01", Generator.new(Exp(0.01), None, "job", False, None)),
+        Model.new("processor-01", Processor.new(Exp(0.333333), 14, "job", "processed", False, None)),
+        _storage("storage-01"),
+        Model.new("stopwatch-01", Stopwatch.new("start", "stop", "min", "min", Metric.Minimum, store_records)),
+        Model.new("stopwatch-02", Stopwatch.new("start", "stop", "max", "max", Metric.Maximum, store_records)),
+    ]
+    connectors = [
+        Connector.new("connector-01", "generator-01", "processor-01", "job", "job"),
+        Connector.new("connector-02", "generator-01", "stopwatch-01", "job", "start"),
+        Connector.new("connector-03", "generator-01", "stopwatch-02", "job", "start"),
+        Connector.new("connector-04", "processor-01", "storage-01", "job", "store"),
+        Connector.new("connector-05", "processor-01", "stopwatch-01", "processed", "stop"),
+        Connector.new("connector-06", "processor-01", "stopwatch-02", "processed", "stop"),
+        Connector.new("connector-07", "stopwatch-01", "storage-01", "min", "store"),
+        Connector.new("connector-06", "stopwatch-02", "storage-01", "max", "store"),
+    ]
+    return models, connectors
+
+
+def processor_from_queue(n_jobs=100):
+    """web.rs:13-69: Processor preloaded through the JSON `state` block -> Storage"""
+    state = {"phase": "Passive", "untilNextEvent": 0.0, "queue": ["job %d" % i for i in range(1, n_jobs + 1)],
+             "records": []}
+    proc = Processor.new(Exp(3.0), None, "job", "processed job", False, None)
+    proc.state = state
+    models = [Model.new("processor-01", proc), _storage("storage-01")]
+    connectors = [Connector.new("connector-01", "processor-01", "storage-01", "processed job", "store")]
+    return models, connectors
+
+
+def processor_network():
+    """web.rs:130-302: six processors, fan-out of one out-port over two connectors"""
+    lams = [1.0, 2.0, 3.0, 5.0, 7.0, 11.0]
+    models = []
+    for i, lam in enumerate(lams):
+        p = Processor.new(Exp(lam), None, "job", "processed job", False, None)
+        if i == 0:
+            p.state = {"phase": "Passive", "untilNextEvent": 0.0, "untilJobCompletion": 0.0,
+                       "queue": ["job %d" % k for k in range(10)], "records": []}
+        models.append(Model.new("processor-%d" % i, p))
+    models.append(Model.new("storage-0", Storage.new("store", "read", "stored", False)))
+    C = Connector.new
+    connectors = [
+        C("connector-01", "processor-0", "processor-1", "processed job", "job"),
+        C("connector-02", "processor-1", "processor-4", "processed job", "job"),
+        C("connector-03", "processor-4", "storage-0", "processed job", "store"),
+        C("connector-04", "processor-1", "processor-3", "processed job", "job"),
+        C("connector-05", "processor-0", "processor-2", "processed job", "job"),
+        C("connector-06", "processor-2", "processor-5", "processed job", "job"),
+        C("connector-07", "processor-3", "processor-5", "processed job", "job"),
+        C("connector-08", "processor-5", "storage-0", "processed job", "store"),
+    ]
+    return models, connectors
+
+
+def generator_passive():
+    """custom.rs:89-112"""
+    models = [Model.new("generator-01", Generator.new(Exp(0.5), None, "job", False, None)),
+              Model.new("passive-01", Passive.new("job"))]
+    connectors = [Connector.new("connector-01", "generator-01", "passive-01", "job", "job")]
+    return models, connectors
+
+
+# ---- BASELINE.json configurations (shapes fixed in SURVEY.md 8(d)) -----------------------------------
+def tandem():
+    """config 3: generator Exp(1.0) -> load balancer (3 paths) -> 3x stage-1 processor Exp(0.4) cap 8 ->
+    processor-2 Triangular(0.2,1.4,0.6) cap 8 -> processor-3 Uniform(0.3,0.9) cap 8 -> storage  (9 models)."""
+    T = ContinuousRandomVariable
+    models = [
+        Model.new("generator", Generator.new(Exp(1.0), None, "job", False, None)),
+        Model.new("load-balancer", LoadBalancer.new("job", ["a", "b", "c"], False)),
+        Model.new("stage1-a", Processor.new(Exp(0.4), 8, "job", "done", False, None)),
+        Model.new("stage1-b", Processor.new(Exp(0.4), 8, "job", "done", False, None)),
+        Model.new("stage1-c", Processor.new(Exp(0.4), 8, "job", "done", False, None)),
+        Model.new("processor-2", Processor.new(T.Triangular(0.2, 1.4, 0.6), 8, "job", "done", False, None)),
+        Model.new("processor-3", Processor.new(T.Uniform(0.3, 0.9), 8, "job", "done", False, None)),
+        _storage("storage"),
+    ]
+    C = Connector.new
+    connectors = [
+        C("c1", "generator", "load-balancer", "job", "job"),
+        C("c2", "load-balancer", "stage1-a", "a", "job"),
+        C("c3", "load-balancer", "stage1-b", "b", "job"),
+        C("c4", "load-balancer", "stage1-c", "c", "job"),
+        C("c5", "stage1-a", "processor-2", "done", "job"),
+        C("c6", "stage1-b", "processor-2", "done", "job"),
+        C("c7", "stage1-c", "processor-2", "done", "job"),
+        C("c8", "processor-2", "processor-3", "done", "job"),
+        C("c9", "processor-3", "storage", "done", "store"),
+    ]
+    return models, connectors
+
+
+def gateway_network():
+    """config 4 (16 models): generator Exp(2) -> parallel split (1->3) -> {processor Exp; stochastic gate p=.9 ->
+    processor Normal(1,.1); exclusive [6,3,1] -> 3 processors -> (merge)} ... -> batcher(10,10) -> storage, with a
+    stopwatch across the network and a gate on the exclusive branch."""
+    T = ContinuousRandomVariable
+    models = [
+        Model.new("generator", Generator.new(Exp(2.0), None, "job", False, None)),
+        Model.new("split", ParallelGateway.new(["in"], ["p", "q", "r"], False)),
+        Model.new("proc-p", Processor.new(Exp(4.0), None, "job", "done", False, None)),
+        Model.new("sgate-q", StochasticGate.new(BooleanRandomVariable.Bernoulli(0.9), "job", "job", False, None)),
+        Model.new("proc-q", Processor.new(T.Normal(0.25, 0.02), 16, "job", "done", False, None)),
+        Model.new("xgw-r", ExclusiveGateway.new(["in"], ["x", "y", "z"], IndexRandomVariable.WeightedIndex([6, 3, 1]),
+                                                False, None)),
+        Model.new("proc-x", Processor.new(Exp(3.0), 16, "job", "done", False, None)),
+        Model.new("proc-y", Processor.new(T.Triangular(0.1, 0.5, 0.2), 16, "job", "done", False, None)),
+        Model.new("proc-z", Processor.new(T.Uniform(0.1, 0.4), 16, "job", "done", False, None)),
+        Model.new("gate-r", Gate.new("job", "activation", "deactivation", "job", False)),
+        Model.new("lb", LoadBalancer.new("job", ["one", "two"], False)),
+        Model.new("batcher", Batcher.new("job", "job", 10.0, 10, False)),
+        Model.new("stopwatch", Stopwatch.new("start", "stop", "metric", "job", Metric.Minimum, False)),
+        _storage("storage-p"), _storage("storage-q"), _storage("storage-r"),
+    ]
+    C = Connector.new
+    connectors = [
+        C("c01", "generator", "split", "job", "in"),
+        C("c02", "generator", "stopwatch", "job", "start"),
+        C("c03", "split", "proc-p", "p", "job"),
+        C("c04", "split", "sgate-q", "q", "job"),
+        C("c05", "split", "xgw-r", "r", "in"),
+        C("c06", "proc-p", "storage-p", "done", "store"),
+        C("c07", "proc-p", "stopwatch", "done", "stop"),
+        C("c08", "sgate-q", "proc-q", "job", "job"),
+        C("c09", "proc-q", "lb", "done", "job"),
+        C("c10", "lb", "batcher", "one", "job"),
+        C("c11", "lb", "storage-q", "two", "store"),
+        C("c12", "batcher", "storage-q", "job", "store"),
+        C("c13", "xgw-r", "proc-x", "x", "job"),
+        C("c14", "xgw-r", "proc-y", "y", "job"),
+        C("c15", "xgw-r", "proc-z", "z", "job"),
+        C("c16", "proc-x", "gate-r", "done", "job"),
+        C("c17", "proc-y", "gate-r", "done", "job"),
+        C("c18", "proc-z", "gate-r", "done", "deactivation"),
+        C("c19", "proc-x", "gate-r", "done", "activation"),
+        C("c20", "gate-r", "storage-r", "job", "store"),
+    ]
+    return models, connectors
+
+
+def large_mixed():
+    """config 5 (32 models): two gateway sub-networks and the tandem share one generator through a split."""
+    models, connectors = [], []
+    models.append(Model.new("source", Generator.new(Exp(3.0), None, "job", False, None)))
+    models.append(Model.new("fanout", ParallelGateway.new(["in"], ["g1", "g2", "t"], False)))
+    connectors.append(Connector.new("s0", "source", "fanout", "job", "in"))
+
+    def sub(prefix, ms, cs, entry_port, entry_model, entry_target_port):
+        for m in ms:
+            if m.inner.type_name == "Generator":
+                continue
+            models.append(Model.new(prefix + m.id, m.inner))
+        for c in cs:
+            src = c.source_id
+            if src == "generator":
+                if c.target_id == entry_model and c.target_port == entry_target_port:
+                    connectors.append(Connector.new(prefix + c.id, "fanout", prefix + c.target_id, entry_port, c.target_port))
+                else:
+                    connectors.append(Connector.new(prefix + c.id, "fanout", prefix + c.target_id, entry_port, c.target_port))
+                continue
+            connectors.append(Connector.new(prefix + c.id, prefix + c.source_id, prefix + c.target_id, c.source_port,
+                                            c.target_port))
+
+    g_models, g_conn = gateway_network()
+    # trim each gateway sub-network to 11 models: drop the three storages and the stopwatch (and their connectors)
+    drop = {"storage-p", "storage-q", "stopwatch", "lb"}
+    gm = [m for m in g_models if m.id not in drop]
+    gc = [c for c in g_conn if c.source_id not in drop and c.target_id not in drop]
+    sub("a/", gm, gc, "g1", "split", "in")
+    sub("b/", gm, gc, "g2", "split", "in")
+    t_models, t_conn = tandem()
+    tm = [m for m in t_models if m.id not in ("storage",)]
+    tc = [c for c in t_conn if c.target_id != "storage"]
+    sub("t/", tm, tc, "t", "load-balancer", "job")
+    models.append(_storage("sink"))
+    connectors.append(Connector.new("t/sink", "t/processor-3", "sink", "done", "store"))
+    models.append(Model.new("monitor", Stopwatch.new("start", "stop", "metric", "job", Metric.Maximum, False)))
+    connectors.append(Connector.new("m/start", "fanout", "monitor", "g1", "start"))
+    connectors.append(Connector.new("m/stop", "a/proc-p", "monitor", "done", "stop"))
+    assert len(models) <= 32, len(models)
+    return models, connectors
+
+
+ALL = {
+    "mm1": mm1, "generator_storage": generator_storage, "exclusive_gateway": exclusive_gateway,
+    "gate_blocking": gate_blocking, "load_balancer": load_balancer, "parallel_gateway": parallel_gateway,
+    "stochastic_gate": stochastic_gate, "batcher": batcher, "stopwatch": stopwatch,
+    "processor_from_queue": processor_from_queue, "processor_network": processor_network,
+    "generator_passive": generator_passive, "tandem": tandem, "gateway_network": gateway_network,
+    "large_mixed": large_mixed,
+}
