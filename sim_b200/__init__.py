@@ -21,10 +21,9 @@ __all__ = [
 def __getattr__(name):
     # Simulation / output_analysis load the CUDA library lazily so that describing models works
     # on machines without it.
+    import importlib
     if name in ("Simulation", "SimulationError", "SimbConfig"):
-        from . import simulator
-        return getattr(simulator, name)
-    if name == "output_analysis":
-        from . import output_analysis
-        return output_analysis
+        return getattr(importlib.import_module(".simulator", __name__), name)
+    if name in ("output_analysis", "simulator"):
+        return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

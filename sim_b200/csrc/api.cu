@@ -1,0 +1,850 @@
+// sim_b200/csrc/api.cu -- the C ABI of libsimb200.so (include/simb.h): handle management, the
+// host drivers of Simulation::step / step_n / step_until over the CUDA engine, observation and
+// statistics read-back.  No CPU fallback: every entry that needs the device fails with
+// SIMB_ERR_CUDA when CUDA is unavailable.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/simb.h"
+#include "engine.cuh"
+#include "lower.hpp"
+#include "output_analysis.hpp"
+
+using namespace simb;
+
+static thread_local std::string g_last_error;
+
+struct simb_sim {
+    HostNet hn;
+    LowerOptions opt;
+    simb_config cfg;
+    std::string stat_model_id;
+    SimbDevState st;
+    EngineDims dims;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // device allocations
+    double* d_dinit = nullptr;
+    uint32_t* d_winit = nullptr;
+    uint32_t* d_pre_slots = nullptr;
+    uint32_t* d_pre_vals = nullptr;
+    uint32_t n_pre = 0;
+    uint64_t* d_ext = nullptr;
+    double* d_psum = nullptr;
+    unsigned long long* d_pcnt = nullptr;
+    unsigned long long* d_overflow = nullptr;
+    uint32_t n_red_blocks = 0;
+    uint32_t K = 1;
+    uint32_t epoch = 0;
+    uint64_t launches = 0;
+    double kernel_ms = 0.0;
+    bool instrument = false;
+    int rng_kind = 0;
+};
+
+namespace {
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t _e = (cudaError_t)(expr);                                                              \
+        if (_e != cudaSuccess)                                                                             \
+            return fail(SIMB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+    } while (0)
+
+void free_device(simb_sim* s) {
+    auto F = [](void* p) {
+        if (p) cudaFree(p);
+    };
+    F(s->st.d);
+    F(s->st.w);
+    F(s->st.ring_w);
+    F(s->st.ring_d);
+    F(s->st.trace);
+    F(s->st.trace_count);
+    F(s->st.conn_count);
+    F(s->st.record_count);
+    F(s->st.totals);
+    F(s->d_dinit);
+    F(s->d_winit);
+    F(s->d_pre_slots);
+    F(s->d_pre_vals);
+    F(s->d_ext);
+    F(s->d_psum);
+    F(s->d_pcnt);
+    F(s->d_overflow);
+    std::memset(&s->st, 0, sizeof s->st);
+    s->d_dinit = nullptr;
+    s->d_winit = nullptr;
+    s->d_pre_slots = s->d_pre_vals = nullptr;
+    s->d_ext = nullptr;
+    s->d_psum = nullptr;
+    s->d_pcnt = nullptr;
+    s->d_overflow = nullptr;
+}
+
+template <class T>
+int dev_alloc(T** p, size_t count, bool zero) {
+    size_t bytes = (count ? count : 1) * sizeof(T);
+    CUDA_TRY(cudaMalloc((void**)p, bytes));
+    if (zero) CUDA_TRY(cudaMemset(*p, 0, bytes));
+    return 0;
+}
+
+// allocate + initialise device state for s->hn (already lowered)
+int build_device(simb_sim* s, uint32_t keep_mask, const simb_sim* old) {
+    (void)old;
+    const SimbNetDesc& net = s->hn.desc;
+    const uint64_t n = s->cfg.replications;
+    int e = engine_configure(net, n, s->rng_kind, s->instrument, &s->dims);
+    if (e) return fail(SIMB_ERR_CUDA, std::string("engine_configure: ") + cudaGetErrorString((cudaError_t)e));
+    const uint64_t stride = (n + 255) / 256 * 256;
+    SimbDevState& st = s->st;
+    std::memset(&st, 0, sizeof st);
+    st.stride = stride;
+    st.n = n;
+    st.rep_offset = s->cfg.replication_offset;
+    st.seed = s->cfg.seed;
+    int r;
+    if ((r = dev_alloc(&st.d, (size_t)net.n_drows * stride, false))) return r;
+    if ((r = dev_alloc(&st.w, (size_t)net.n_wrows * stride, false))) return r;
+    if ((r = dev_alloc(&st.ring_w, (size_t)(s->hn.ring_w_slots + 1) * stride, true))) return r;
+    if ((r = dev_alloc(&st.ring_d, (size_t)(s->hn.ring_d_slots + 1) * stride, true))) return r;
+    st.trace_reps = 0;
+    st.trace_cap = 0;
+    if (s->instrument) {
+        st.trace_reps = (uint32_t)std::min<uint64_t>(s->cfg.trace_replications, n);
+        st.trace_cap = s->cfg.trace_capacity ? s->cfg.trace_capacity : 4096;
+        if ((r = dev_alloc(&st.trace, (size_t)st.trace_reps * st.trace_cap, true))) return r;
+        if ((r = dev_alloc(&st.trace_count, (size_t)stride, true))) return r;
+        if ((r = dev_alloc(&st.conn_count, (size_t)net.n_connectors + 1, true))) return r;
+        if ((r = dev_alloc(&st.record_count, (size_t)net.n_models * ACT_COUNT, true))) return r;
+    }
+    if ((r = dev_alloc(&st.totals, 4, true))) return r;
+    if ((r = dev_alloc(&s->d_dinit, net.n_drows, false))) return r;
+    if ((r = dev_alloc(&s->d_winit, net.n_wrows, false))) return r;
+    CUDA_TRY(cudaMemcpy(s->d_dinit, s->hn.d_init.data(), net.n_drows * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(s->d_winit, s->hn.w_init.data(), net.n_wrows * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    s->n_pre = (uint32_t)s->hn.ring_preload.size();
+    if (s->n_pre) {
+        std::vector<uint32_t> slots(s->n_pre), vals(s->n_pre);
+        for (uint32_t i = 0; i < s->n_pre; i++) {
+            slots[i] = s->hn.ring_preload[i].slot;
+            vals[i] = s->hn.ring_preload[i].value;
+        }
+        if ((r = dev_alloc(&s->d_pre_slots, s->n_pre, false))) return r;
+        if ((r = dev_alloc(&s->d_pre_vals, s->n_pre, false))) return r;
+        CUDA_TRY(cudaMemcpy(s->d_pre_slots, slots.data(), s->n_pre * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(s->d_pre_vals, vals.data(), s->n_pre * 4, cudaMemcpyHostToDevice));
+    }
+    s->n_red_blocks = engine_reduce_blocks(n);
+    if ((r = dev_alloc(&s->d_psum, s->n_red_blocks, true))) return r;
+    if ((r = dev_alloc(&s->d_pcnt, s->n_red_blocks, true))) return r;
+    if ((r = dev_alloc(&s->d_overflow, 1, true))) return r;
+    CUDA_TRY(engine_launch_init(net, st, s->d_dinit, s->d_winit, s->d_pre_slots, s->d_pre_vals, s->n_pre, s->rng_kind,
+                                s->instrument, keep_mask, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int first_error(simb_sim* s, uint64_t failed_hint) {
+    if (!failed_hint) return 0;
+    std::vector<uint32_t> ctl(s->st.n);
+    CUDA_TRY(cudaMemcpy(ctl.data(), s->st.w + (uint64_t)s->hn.desc.wrow_ctl * s->st.stride, s->st.n * 4, cudaMemcpyDeviceToHost));
+    for (uint64_t r = 0; r < s->st.n; r++)
+        if (CTL_ERR(ctl[r]))
+            return fail((int)CTL_ERR(ctl[r]), "replication " + std::to_string(r) + " failed with " + status_name((int)CTL_ERR(ctl[r])));
+    return 0;
+}
+
+// drive the step kernel.  mode 0: exactly n steps; mode 1: until every replication's clock >= until.
+int run_steps(simb_sim* s, int mode, uint64_t n, double until) {
+    const SimbNetDesc& net = s->hn.desc;
+    SimbLaunch la;
+    std::memset(&la, 0, sizeof la);
+    la.mode = (uint32_t)mode;
+    la.until = until;
+    if (mode == 1) {
+        s->epoch = (s->epoch % 255u) + 1u;
+        la.epoch = s->epoch;
+    }
+    unsigned long long tot[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+    uint64_t issued = 0;
+    if (mode == 0) {
+        uint64_t left = n;
+        while (left > 0) {
+            la.k = (uint32_t)std::min<uint64_t>(left, s->K);
+            left -= la.k;
+            const bool last = left == 0;
+            if (last) CUDA_TRY(cudaMemsetAsync(s->st.totals + 2, 0, 2 * sizeof(unsigned long long), s->stream));
+            CUDA_TRY(engine_launch_step(net, s->st, la, s->dims, s->rng_kind, s->instrument, last, s->stream));
+            issued++;
+        }
+        if (n > 0) CUDA_TRY(cudaMemcpyAsync(tot, s->st.totals, sizeof tot, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+    } else {
+        la.k = s->K;
+        // launches between termination checks: about 256 steps' worth
+        const uint32_t round = std::max<uint32_t>(1u, 256u / std::max<uint32_t>(1u, s->K));
+        for (;;) {
+            for (uint32_t i = 0; i < round; i++) {
+                const bool last = i + 1 == round;
+                if (last) CUDA_TRY(cudaMemsetAsync(s->st.totals + 2, 0, 2 * sizeof(unsigned long long), s->stream));
+                CUDA_TRY(engine_launch_step(net, s->st, la, s->dims, s->rng_kind, s->instrument, last, s->stream));
+                issued++;
+            }
+            CUDA_TRY(cudaMemcpyAsync(tot, s->st.totals, sizeof tot, cudaMemcpyDeviceToHost, s->stream));
+            CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+            if (tot[2] == 0) break;  // no replication still below `until`
+        }
+    }
+    float ms = 0.f;
+    if (issued) {
+        CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        s->kernel_ms += ms;
+        s->launches += issued;
+    }
+    return first_error(s, tot[3]);
+}
+
+int column_w(simb_sim* s, uint64_t rep, std::vector<uint32_t>* out) {
+    const SimbNetDesc& net = s->hn.desc;
+    out->assign(net.n_wrows, 0);
+    CUDA_TRY(cudaMemcpy2D(out->data(), 4, s->st.w + rep, s->st.stride * 4, 4, net.n_wrows, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int column_d(simb_sim* s, uint64_t rep, std::vector<double>* out) {
+    const SimbNetDesc& net = s->hn.desc;
+    out->assign(net.n_drows, 0);
+    CUDA_TRY(cudaMemcpy2D(out->data(), 8, s->st.d + rep, s->st.stride * 8, 8, net.n_drows, cudaMemcpyDeviceToHost));
+    return 0;
+}
+void put_str(char* dst, size_t cap, const std::string& v) {
+    if (!dst || !cap) return;
+    size_t n = std::min(cap - 1, v.size());
+    std::memcpy(dst, v.data(), n);
+    dst[n] = 0;
+}
+int copy_row_w(simb_sim* s, uint32_t row, uint32_t* out, uint64_t capacity) {
+    if (!out || capacity < s->st.n) return fail(SIMB_ERR_INVALID_ARGUMENT, "output buffer smaller than the replication count");
+    CUDA_TRY(cudaMemcpy(out, s->st.w + (uint64_t)row * s->st.stride, s->st.n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int copy_row_d(simb_sim* s, uint32_t row, double* out, uint64_t capacity) {
+    if (!out || capacity < s->st.n) return fail(SIMB_ERR_INVALID_ARGUMENT, "output buffer smaller than the replication count");
+    CUDA_TRY(cudaMemcpy(out, s->st.d + (uint64_t)row * s->st.stride, s->st.n * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// subject string of a record, as the reference formats it per model (file:line in core.cuh)
+std::string record_subject(const simb_sim* s, uint32_t model, uint32_t action, uint32_t aux, uint32_t content) {
+    const HostModel& hm = s->hn.models[model];
+    const uint8_t type = s->hn.desc.models[model].type;
+    std::string job = s->hn.render(content);
+    if (content == SIMB_CONTENT_NONE) {
+        if (action == ACT_INITIALIZATION) return "";
+        return "None";  // Storage release with no job / Stopwatch fetch with no completed job
+    }
+    if (aux) {
+        const std::vector<std::string>& ports =
+            (action == ACT_ARRIVAL && (type == MT_EXCLUSIVE_GATEWAY || type == MT_PARALLEL_GATEWAY)) ? hm.ports_in : hm.ports_out;
+        std::string p = aux - 1 < ports.size() ? ports[aux - 1] : "?";
+        return job + " on " + p;
+    }
+    if (action == ACT_ARRIVAL && type == MT_EXCLUSIVE_GATEWAY) return job + " on ?";
+    return job;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* simb_last_error_message(void) { return g_last_error.c_str(); }
+const char* simb_status_name(int status) { return status_name(status); }
+int simb_abi_version(void) { return SIMB_ABI_VERSION; }
+int simb_device_count(int* count) {
+    if (!count) return fail(SIMB_ERR_INVALID_ARGUMENT, "null count");
+    *count = 0;
+    CUDA_TRY(cudaGetDeviceCount(count));
+    return 0;
+}
+
+int simb_post_json(const char* models_json, const char* connectors_json, const simb_config* config, simb_sim** out) {
+    if (!out || !config || !models_json || !connectors_json) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (config->struct_size != sizeof(simb_config)) return fail(SIMB_ERR_INVALID_ARGUMENT, "simb_config.struct_size mismatch");
+    if (config->replications == 0) return fail(SIMB_ERR_INVALID_ARGUMENT, "replications must be > 0");
+    if (config->rng_kind < 0 || config->rng_kind > 2) return fail(SIMB_ERR_INVALID_ARGUMENT, "unknown rng_kind");
+    simb_sim* s = new simb_sim();
+    s->cfg = *config;
+    if (config->stat_model_id) s->stat_model_id = config->stat_model_id;
+    s->cfg.stat_model_id = nullptr;
+    s->instrument = (config->flags & SIMB_FLAG_INSTRUMENT) != 0;
+    s->rng_kind = config->rng_kind;
+    s->K = config->steps_per_launch ? config->steps_per_launch : 8;
+    s->opt.queue_capacity = config->queue_capacity;
+    s->opt.max_pending = config->max_pending;
+    s->opt.instrument = s->instrument;
+    s->opt.rng_kind = s->rng_kind;
+    s->opt.stat_model_id = s->stat_model_id;
+    std::string err;
+    int e = lower_network(models_json, connectors_json, s->opt, &s->hn, &err);
+    if (e) {
+        delete s;
+        return fail(e, err);
+    }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        delete s;
+        return fail(SIMB_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(ce) +
+                                       "); libsimb200 has no CPU fallback");
+    }
+    std::memset(&s->st, 0, sizeof s->st);
+    auto bail = [&](int code) {
+        free_device(s);
+        if (s->ev0) cudaEventDestroy(s->ev0);
+        if (s->ev1) cudaEventDestroy(s->ev1);
+        if (s->stream) cudaStreamDestroy(s->stream);
+        delete s;
+        return code;
+    };
+    if (cudaSetDevice(config->device) != cudaSuccess) return bail(fail(SIMB_ERR_CUDA, "cudaSetDevice failed"));
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(fail(SIMB_ERR_CUDA, "cudaStreamCreate failed"));
+    if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess)
+        return bail(fail(SIMB_ERR_CUDA, "cudaEventCreate failed"));
+    e = build_device(s, 0, nullptr);
+    if (e) return bail(e);
+    *out = s;
+    return 0;
+}
+
+int simb_put_json(simb_sim* s, const char* models_json, const char* connectors_json) {
+    if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");
+    // Simulation::put (mod.rs:82-85): new models (fresh state) and connectors; the clock, the
+    // pending messages and the RNG position are kept.
+    HostNet hn;
+    std::string err;
+    int e = lower_network(models_json, connectors_json, s->opt, &hn, &err);
+    if (e) return fail(e, err);
+    const SimbNetDesc& o = s->hn.desc;
+    const SimbNetDesc& nw = hn.desc;
+    const bool same_layout = o.n_drows == nw.n_drows && o.n_wrows == nw.n_wrows && o.wrow_pend == nw.wrow_pend &&
+                             o.max_pending == nw.max_pending && o.wrow_rng == nw.wrow_rng &&
+                             s->hn.ring_w_slots == hn.ring_w_slots && s->hn.ring_d_slots == hn.ring_d_slots &&
+                             s->hn.ring_preload.size() == hn.ring_preload.size();
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    if (!same_layout) {
+        // different shape: keep clock / RNG position only if the rows line up; otherwise start fresh
+        std::vector<double> time(s->st.n);
+        std::vector<uint32_t> rng(s->st.n * (s->rng_kind == 1 ? 4 : 1));
+        CUDA_TRY(cudaMemcpy(time.data(), s->st.d + (uint64_t)o.drow_time * s->st.stride, s->st.n * 8, cudaMemcpyDeviceToHost));
+        const uint32_t rr = s->rng_kind == 1 ? 4 : 1;
+        for (uint32_t k = 0; k < rr; k++)
+            CUDA_TRY(cudaMemcpy(rng.data() + (size_t)k * s->st.n, s->st.w + (uint64_t)(o.wrow_rng + k) * s->st.stride, s->st.n * 4,
+                                cudaMemcpyDeviceToHost));
+        free_device(s);
+        s->hn = hn;
+        e = build_device(s, 0, nullptr);
+        if (e) return e;
+        const SimbNetDesc& n2 = s->hn.desc;
+        CUDA_TRY(cudaMemcpy(s->st.d + (uint64_t)n2.drow_time * s->st.stride, time.data(), s->st.n * 8, cudaMemcpyHostToDevice));
+        for (uint32_t k = 0; k < rr; k++)
+            CUDA_TRY(cudaMemcpy(s->st.w + (uint64_t)(n2.wrow_rng + k) * s->st.stride, rng.data() + (size_t)k * s->st.n, s->st.n * 4,
+                                cudaMemcpyHostToDevice));
+        return 0;
+    }
+    s->hn = hn;
+    CUDA_TRY(cudaMemcpy(s->d_dinit, s->hn.d_init.data(), nw.n_drows * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(s->d_winit, s->hn.w_init.data(), nw.n_wrows * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (s->n_pre) {
+        std::vector<uint32_t> slots(s->n_pre), vals(s->n_pre);
+        for (uint32_t i = 0; i < s->n_pre; i++) {
+            slots[i] = s->hn.ring_preload[i].slot;
+            vals[i] = s->hn.ring_preload[i].value;
+        }
+        CUDA_TRY(cudaMemcpy(s->d_pre_slots, slots.data(), s->n_pre * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(s->d_pre_vals, vals.data(), s->n_pre * 4, cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(engine_launch_init(s->hn.desc, s->st, s->d_dinit, s->d_winit, s->d_pre_slots, s->d_pre_vals, s->n_pre, s->rng_kind,
+                                s->instrument, 1u | 2u | 4u, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int simb_reset(simb_sim* s) {
+    if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    CUDA_TRY(engine_launch_reset(s->hn.desc, s->st, true, true, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+int simb_reset_messages(simb_sim* s) {
+    if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    CUDA_TRY(engine_launch_reset(s->hn.desc, s->st, true, false, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+int simb_reset_global_time(simb_sim* s) {
+    if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    CUDA_TRY(engine_launch_reset(s->hn.desc, s->st, false, true, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+int simb_set_rng(simb_sim* s, int rng_kind, uint64_t seed) {
+    if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");
+    if (rng_kind != s->rng_kind)
+        return fail(SIMB_ERR_INVALID_ARGUMENT, "the RNG kind is fixed at post time (it decides the state layout); only the seed can change");
+    s->cfg.seed = seed;
+    s->st.seed = seed;
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    CUDA_TRY(engine_launch_set_rng(s->hn.desc, s->st, s->rng_kind, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+int simb_set_rng_stream(simb_sim* s, const uint64_t* draws, uint64_t per_rep) {
+    if (!s || !draws) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    if (s->rng_kind != SIMB_RNG_EXTERNAL) return fail(SIMB_ERR_INVALID_ARGUMENT, "handle was not posted with SIMB_RNG_EXTERNAL");
+    if (per_rep > 0xFFFFFFFFull) return fail(SIMB_ERR_INVALID_ARGUMENT, "too many draws per replication");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    if (s->d_ext) cudaFree(s->d_ext);
+    s->d_ext = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&s->d_ext, std::max<uint64_t>(1, per_rep * s->st.stride) * 8));
+    // caller layout [i][replications] -> device layout [i][stride]
+    CUDA_TRY(cudaMemcpy2D(s->d_ext, s->st.stride * 8, draws, s->st.n * 8, s->st.n * 8, per_rep, cudaMemcpyHostToDevice));
+    s->st.ext = s->d_ext;
+    s->st.ext_len = (uint32_t)per_rep;
+    CUDA_TRY(engine_launch_set_rng(s->hn.desc, s->st, s->rng_kind, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+int simb_destroy(simb_sim* s) {
+    if (!s) return 0;
+    cudaSetDevice(s->cfg.device);
+    free_device(s);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return 0;
+}
+
+int simb_inject_input(simb_sim* s, const char* target_id, const char* target_port, const char* content,
+                      const uint8_t* replica_mask) {
+    if (!s || !target_id || !target_port || !content) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    const int tm = s->hn.find_model(target_id);  // unknown target: kept, never delivered (mod.rs:204-216)
+    bool overflow = false;
+    const uint32_t code = s->hn.content_code(content, &overflow);
+    if (overflow) return fail(SIMB_ERR_CAPACITY, "content intern table overflow");
+    const uint32_t port = tm < 0 ? SIMB_PORT_UNKNOWN : s->hn.resolve_in_port(tm, target_port);
+    const uint32_t rw = ROUTE_WORD(tm < 0 ? 0xFF : tm, port, 0xFFFF);
+    uint8_t* d_mask = nullptr;
+    if (replica_mask) {
+        CUDA_TRY(cudaMalloc((void**)&d_mask, s->st.n));
+        CUDA_TRY(cudaMemcpy(d_mask, replica_mask, s->st.n, cudaMemcpyHostToDevice));
+    }
+    cudaMemsetAsync(s->d_overflow, 0, sizeof(unsigned long long), s->stream);
+    int e = engine_launch_inject(s->hn.desc, s->st, code, rw, d_mask, s->d_overflow, s->stream);
+    unsigned long long ov = 0;
+    cudaMemcpyAsync(&ov, s->d_overflow, sizeof ov, cudaMemcpyDeviceToHost, s->stream);
+    cudaError_t ce = cudaStreamSynchronize(s->stream);
+    if (d_mask) cudaFree(d_mask);
+    if (e || ce != cudaSuccess) return fail(SIMB_ERR_CUDA, "inject kernel failed");
+    if (ov) return fail(SIMB_ERR_CAPACITY, std::to_string(ov) + " replications have a full mailbox; raise simb_config.max_pending");
+    return 0;
+}
+int simb_step(simb_sim* s) {
+    if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    const uint32_t k = s->K;
+    s->K = 1;
+    int e = run_steps(s, 0, 1, 0.0);
+    s->K = k;
+    return e;
+}
+int simb_step_n(simb_sim* s, uint64_t n) {
+    if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    return run_steps(s, 0, n, 0.0);
+}
+int simb_step_until(simb_sim* s, double until) {
+    if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    return run_steps(s, 1, 0, until);
+}
+int simb_synchronize(simb_sim* s) {
+    if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int simb_get_global_time(simb_sim* s, double* out, uint64_t capacity) {
+    if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    return copy_row_d(s, s->hn.desc.drow_time, out, capacity);
+}
+int simb_get_until_next_event(simb_sim* s, const char* model_id, double* out, uint64_t capacity) {
+    if (!s || !model_id) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    const int m = s->hn.find_model(model_id);
+    if (m < 0) return fail(SIMB_ERR_MODEL_NOT_FOUND, std::string("no model `") + model_id + "`");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    return copy_row_d(s, s->hn.desc.drow_until + m, out, capacity);
+}
+int simb_get_messages(simb_sim* s, uint64_t rep, simb_message* out, uint64_t capacity, uint64_t* count) {
+    if (!s || !count) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    if (rep >= s->st.n) return fail(SIMB_ERR_INVALID_ARGUMENT, "replication index out of range");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    const SimbNetDesc& net = s->hn.desc;
+    std::vector<uint32_t> w;
+    std::vector<double> d;
+    int e = column_w(s, rep, &w);
+    if (e) return e;
+    if ((e = column_d(s, rep, &d))) return e;
+    const uint32_t np = CTL_NPEND(w[net.wrow_ctl]);
+    *count = np;
+    for (uint32_t j = 0; j < np && j < capacity && out; j++) {
+        const uint32_t content = w[net.wrow_pend + 2 * j], rw = w[net.wrow_pend + 2 * j + 1];
+        simb_message& m = out[j];
+        std::memset(&m, 0, sizeof m);
+        const uint32_t conn = ROUTE_CONN(rw);
+        if (conn == 0xFFFF) {  // injected: Message::new("manual","manual",..) in the reference's tests
+            put_str(m.source_id, sizeof m.source_id, "manual");
+            put_str(m.source_port, sizeof m.source_port, "manual");
+            const uint32_t tm = ROUTE_TGT(rw);
+            if (tm < net.n_models) {
+                put_str(m.target_id, sizeof m.target_id, s->hn.models[tm].id);
+                const uint32_t p = ROUTE_PORT(rw);
+                if (p < s->hn.models[tm].ports_in.size()) put_str(m.target_port, sizeof m.target_port, s->hn.models[tm].ports_in[p]);
+            }
+        } else if (conn < s->hn.connectors.size()) {
+            const HostConnector& c = s->hn.connectors[conn];
+            put_str(m.source_id, sizeof m.source_id, c.source_id);
+            put_str(m.source_port, sizeof m.source_port, c.source_port);
+            put_str(m.target_id, sizeof m.target_id, c.target_id);
+            put_str(m.target_port, sizeof m.target_port, c.target_port);
+        }
+        put_str(m.content, sizeof m.content, s->hn.render(content));
+        m.time = d[net.drow_time];  // Message.time = global_time at emission = the current clock
+    }
+    return 0;
+}
+int simb_get_status(simb_sim* s, const char* model_id, uint64_t rep, char* out, uint64_t capacity) {
+    if (!s || !model_id || !out) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    const int m = s->hn.find_model(model_id);
+    if (m < 0) return fail(SIMB_ERR_MODEL_NOT_FOUND, std::string("no model `") + model_id + "`");  // mod.rs:111
+    if (rep >= s->st.n) return fail(SIMB_ERR_INVALID_ARGUMENT, "replication index out of range");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    const SimbNetDesc& net = s->hn.desc;
+    const SimbModelDesc& md = net.models[m];
+    const HostModel& hm = s->hn.models[m];
+    std::vector<uint32_t> w;
+    int e = column_w(s, rep, &w);
+    if (e) return e;
+    const uint32_t ph = (w[net.wrow_phase + m / 16] >> (2 * (m % 16))) & 3u;
+    auto head_job = [&]() -> std::string {
+        const uint32_t head = w[md.wrow] >> 16;
+        uint32_t c = 0;
+        cudaMemcpy(&c, s->st.ring_w + (uint64_t)(md.ring_w0 + head) * s->st.stride + rep, 4, cudaMemcpyDeviceToHost);
+        return s->hn.render(c);
+    };
+    std::string r;
+    switch (md.type) {
+        case MT_GENERATOR: r = "Generating " + hm.ports_out[0] + "s"; break;            // generator.rs:189-191
+        case MT_PROCESSOR: r = ph == 1 ? "Processing" : "Passive"; break;                // processor.rs:249-256
+        case MT_STORAGE:                                                                 // storage.rs:182-188
+            r = w[md.wrow] == SIMB_CONTENT_NONE ? "Empty" : "Storing " + s->hn.render(w[md.wrow]);
+            break;
+        case MT_LOAD_BALANCER: r = "Listening for " + hm.ports_in[0] + "s"; break;       // load_balancer.rs:154-156
+        case MT_GATE: r = ph == 0 ? "Open" : ph == 1 ? "Closed" : "Passing " + head_job(); break;  // gate.rs:207-213
+        case MT_EXCLUSIVE_GATEWAY: r = ph == 1 ? "Passing " + head_job() : "Passive"; break;       // exclusive_gateway.rs:173-178
+        case MT_PARALLEL_GATEWAY: r = "Active"; break;                                   // parallel_gateway.rs:193-195
+        case MT_STOCHASTIC_GATE: r = "Gating"; break;                                    // stochastic_gate.rs:194-196
+        case MT_STOPWATCH: r = "Measuring durations"; break;  // the running average of stopwatch.rs:306-322 is not kept on the device
+        case MT_BATCHER: r = ph == 0 ? "Passive" : ph == 1 ? "Creating batch" : "Releasing batch"; break;  // batcher.rs:232-238
+        default: r = "Passive"; break;                                                   // tests/custom.rs:77-79
+    }
+    put_str(out, capacity, r);
+    return 0;
+}
+int simb_get_errors(simb_sim* s, int32_t* out, uint64_t capacity) {
+    if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    int e = copy_row_w(s, s->hn.desc.wrow_ctl, reinterpret_cast<uint32_t*>(out), capacity);
+    if (e) return e;
+    for (uint64_t r = 0; r < s->st.n; r++) out[r] = (int32_t)CTL_ERR((uint32_t)out[r]);
+    return 0;
+}
+int simb_get_steps(simb_sim* s, uint32_t* out, uint64_t capacity) {
+    if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    return copy_row_w(s, s->hn.desc.wrow_steps, out, capacity);
+}
+int simb_get_events(simb_sim* s, uint32_t* out, uint64_t capacity) {
+    if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    return copy_row_w(s, s->hn.desc.wrow_events, out, capacity);
+}
+int simb_get_draws(simb_sim* s, uint32_t* out, uint64_t capacity) {
+    if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");
+    if (s->rng_kind == SIMB_RNG_PCG64MCG) return fail(SIMB_ERR_INVALID_ARGUMENT, "the PCG state does not keep a draw count");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    return copy_row_w(s, s->hn.desc.wrow_rng, out, capacity);
+}
+int simb_get_counters(simb_sim* s, simb_counters* out) {
+    if (!s || !out) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    const SimbNetDesc& net = s->hn.desc;
+    uint32_t nb = 0;
+    CUDA_TRY(engine_launch_reduce(net, s->st, 2, 0.0, s->d_psum, s->d_pcnt, &nb, s->stream));
+    std::vector<unsigned long long> a(nb), b(nb);
+    CUDA_TRY(cudaMemcpyAsync(a.data(), s->d_psum, nb * 8, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(b.data(), s->d_pcnt, nb * 8, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    std::memset(out, 0, sizeof *out);
+    for (uint32_t i = 0; i < nb; i++) {
+        out->steps += a[i];
+        out->events += b[i];
+    }
+    out->launches = s->launches;
+    out->kernel_ms = s->kernel_ms;
+    out->state_bytes_per_replication = (uint64_t)net.n_drows * 8 + (uint64_t)net.n_wrows * 4;
+    std::vector<uint32_t> ctl(s->st.n);
+    CUDA_TRY(cudaMemcpy(ctl.data(), s->st.w + (uint64_t)net.wrow_ctl * s->st.stride, s->st.n * 4, cudaMemcpyDeviceToHost));
+    for (uint64_t r = 0; r < s->st.n; r++) out->failed += CTL_ERR(ctl[r]) ? 1 : 0;
+    return 0;
+}
+int simb_reset_counters(simb_sim* s) {
+    if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");
+    s->launches = 0;
+    s->kernel_ms = 0.0;
+    return 0;
+}
+
+int simb_get_trace_hash(simb_sim* s, uint64_t* out, uint64_t capacity) {
+    if (!s || !out) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!s->instrument) return fail(SIMB_ERR_INVALID_ARGUMENT, "handle was not posted with SIMB_FLAG_INSTRUMENT");
+    if (capacity < s->st.n) return fail(SIMB_ERR_INVALID_ARGUMENT, "output buffer smaller than the replication count");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    std::vector<uint32_t> lo(s->st.n), hi(s->st.n);
+    int e = copy_row_w(s, s->hn.desc.wrow_hash, lo.data(), s->st.n);
+    if (e) return e;
+    if ((e = copy_row_w(s, s->hn.desc.wrow_hash + 1, hi.data(), s->st.n))) return e;
+    for (uint64_t r = 0; r < s->st.n; r++) out[r] = (uint64_t)lo[r] | ((uint64_t)hi[r] << 32);
+    return 0;
+}
+int simb_get_message_counts(simb_sim* s, uint64_t* out, uint64_t capacity) {
+    if (!s || !out) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!s->instrument) return fail(SIMB_ERR_INVALID_ARGUMENT, "handle was not posted with SIMB_FLAG_INSTRUMENT");
+    if (capacity < s->hn.desc.n_connectors) return fail(SIMB_ERR_INVALID_ARGUMENT, "output buffer smaller than the connector count");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    CUDA_TRY(cudaMemcpy(out, s->st.conn_count, s->hn.desc.n_connectors * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int simb_get_record_counts(simb_sim* s, uint64_t* out, uint64_t capacity) {
+    if (!s || !out) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!s->instrument) return fail(SIMB_ERR_INVALID_ARGUMENT, "handle was not posted with SIMB_FLAG_INSTRUMENT");
+    const uint64_t n = (uint64_t)s->hn.desc.n_models * ACT_COUNT;
+    if (capacity < n) return fail(SIMB_ERR_INVALID_ARGUMENT, "output buffer too small");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    CUDA_TRY(cudaMemcpy(out, s->st.record_count, n * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+static int fetch_trace(simb_sim* s, uint64_t rep, std::vector<SimbTraceRec>* recs) {
+    if (!s->instrument) return fail(SIMB_ERR_INVALID_ARGUMENT, "handle was not posted with SIMB_FLAG_INSTRUMENT");
+    if (rep >= s->st.trace_reps) return fail(SIMB_ERR_INVALID_ARGUMENT, "replication is not traced (simb_config.trace_replications)");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    uint32_t cnt = 0;
+    CUDA_TRY(cudaMemcpy(&cnt, s->st.trace_count + rep, 4, cudaMemcpyDeviceToHost));
+    if (cnt > s->st.trace_cap)
+        return fail(SIMB_ERR_CAPACITY, "trace buffer overflow: " + std::to_string(cnt) + " events > trace_capacity");
+    recs->resize(cnt);
+    if (cnt) CUDA_TRY(cudaMemcpy(recs->data(), s->st.trace + rep * s->st.trace_cap, (size_t)cnt * sizeof(SimbTraceRec), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int simb_get_trace(simb_sim* s, uint64_t rep, simb_trace_event* out, uint64_t capacity, uint64_t* count) {
+    if (!s || !count) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    std::vector<SimbTraceRec> recs;
+    int e = fetch_trace(s, rep, &recs);
+    if (e) return e;
+    *count = recs.size();
+    for (size_t i = 0; i < recs.size() && i < capacity && out; i++) {
+        simb_trace_event& t = out[i];
+        std::memset(&t, 0, sizeof t);
+        t.step = recs[i].step;
+        t.kind = (uint8_t)(recs[i].meta >> 31);
+        t.index = (uint16_t)(recs[i].meta & 0xFFFFu);
+        t.action = (uint8_t)(recs[i].aux & 0xFFu);
+        t.aux = (uint8_t)((recs[i].aux >> 8) & 0xFFu);
+        t.content = recs[i].content;
+        t.time = recs[i].time;
+    }
+    return 0;
+}
+int simb_get_records(simb_sim* s, const char* model_id, uint64_t rep, simb_record* out, uint64_t capacity, uint64_t* count) {
+    if (!s || !model_id || !count) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    const int m = s->hn.find_model(model_id);
+    if (m < 0) return fail(SIMB_ERR_MODEL_NOT_FOUND, std::string("no model `") + model_id + "`");  // mod.rs:123
+    std::vector<SimbTraceRec> recs;
+    int e = fetch_trace(s, rep, &recs);
+    if (e) return e;
+    uint64_t k = 0;
+    if (s->hn.models[m].store_records) {  // record() is a no-op unless store_records (e.g. processor.rs:198-206)
+        for (auto& r : recs) {
+            if (!(r.meta >> 31) || (r.meta & 0xFFFFu) != (uint32_t)m) continue;
+            if (out && k < capacity) {
+                simb_record& o = out[k];
+                std::memset(&o, 0, sizeof o);
+                o.time = r.time;
+                put_str(o.action, sizeof o.action, action_name((int)(r.aux & 0xFFu)));
+                put_str(o.subject, sizeof o.subject, record_subject(s, (uint32_t)m, r.aux & 0xFFu, (r.aux >> 8) & 0xFFu, r.content));
+            }
+            k++;
+        }
+    }
+    *count = k;
+    return 0;
+}
+int simb_render_content(simb_sim* s, uint32_t content, char* out, uint64_t capacity) {
+    if (!s || !out) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    put_str(out, capacity, s->hn.render(content));
+    return 0;
+}
+int simb_intern_content(simb_sim* s, const char* content, uint32_t* out) {
+    if (!s || !content || !out) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    bool overflow = false;
+    *out = s->hn.content_code(content, &overflow);
+    return overflow ? fail(SIMB_ERR_CAPACITY, "content intern table overflow") : 0;
+}
+
+// ---- statistics ---------------------------------------------------------------------------------------
+int simb_get_wait_stats(simb_sim* s, double* sum, uint32_t* count, uint64_t capacity) {
+    if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");
+    if (s->hn.stat_model < 0) return fail(SIMB_ERR_INVALID_ARGUMENT, "no stat_model_id was configured");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    int e = 0;
+    if (sum && (e = copy_row_d(s, s->hn.desc.drow_wait, sum, capacity))) return e;
+    if (count && (e = copy_row_w(s, s->hn.desc.wrow_waitn, count, capacity))) return e;
+    return 0;
+}
+static int stat_reduce(simb_sim* s, int which, double mean, double* sum, uint64_t* n) {
+    if (s->hn.stat_model < 0) return fail(SIMB_ERR_INVALID_ARGUMENT, "no stat_model_id was configured");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    uint32_t nb = 0;
+    CUDA_TRY(engine_launch_reduce(s->hn.desc, s->st, which, mean, s->d_psum, s->d_pcnt, &nb, s->stream));
+    std::vector<double> ps(nb);
+    std::vector<unsigned long long> pc(nb);
+    CUDA_TRY(cudaMemcpyAsync(ps.data(), s->d_psum, nb * 8, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(pc.data(), s->d_pcnt, nb * 8, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    double t = 0.0;
+    uint64_t c = 0;
+    for (uint32_t i = 0; i < nb; i++) {  // fixed order: results do not depend on scheduling
+        t += ps[i];
+        c += pc[i];
+    }
+    if (sum) *sum = t;
+    if (n) *n = c;
+    return 0;
+}
+int simb_stat_partial(simb_sim* s, double* sum_of_means, uint64_t* n) {
+    if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");
+    return stat_reduce(s, 0, 0.0, sum_of_means, n);
+}
+int simb_stat_partial_sqdev(simb_sim* s, double mean, double* sum_sqdev) {
+    if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");
+    return stat_reduce(s, 1, mean, sum_sqdev, nullptr);
+}
+int simb_independent_sample_ci(simb_sim* s, double alpha, simb_ci* out) {
+    if (!s || !out) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    double sum = 0, sq = 0;
+    uint64_t n = 0;
+    int e = stat_reduce(s, 0, 0.0, &sum, &n);
+    if (e) return e;
+    if (n == 0) return fail(SIMB_ERR_PREREQUISITE_CALC, "no replication has a defined mean yet");
+    const double mean = sum / (double)n;  // sample_mean (output_analysis/mod.rs:23-28)
+    if ((e = stat_reduce(s, 1, mean, &sq, nullptr))) return e;
+    const double variance = sq / (double)n;  // sample_variance divides by n (mod.rs:32-40)
+    return simb_oa_confidence_interval(mean, variance, n, alpha, out);
+}
+int simb_oa_confidence_interval(double mean, double variance, uint64_t n, double alpha, simb_ci* out) {
+    if (!out) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    double lo, hi;
+    int e = oa::independent_ci(mean, variance, n, alpha, &lo, &hi);
+    if (e) return fail(e, "t_score: alpha must be one of .1 .05 .025 .01 .005 .001 .0005 (t_scores.rs:10-22)");
+    out->mean = mean;
+    out->variance = variance;
+    out->lower = lo;
+    out->upper = hi;
+    out->n = n;
+    return 0;
+}
+int simb_oa_independent_sample(const double* points, uint64_t n, double alpha, simb_ci* out) {
+    if (!points || !out || n == 0) return fail(SIMB_ERR_INVALID_ARGUMENT, "null or empty sample");
+    double mean, var;
+    oa::mean_variance(points, n, &mean, &var);
+    return simb_oa_confidence_interval(mean, var, n, alpha, out);
+}
+int simb_oa_steady_state(const double* series, uint64_t n, double alpha, simb_ci* out, uint64_t* deletion_point,
+                         uint64_t* batch_size, uint64_t* batch_count) {
+    if (!series || !out) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    oa::SteadyState ss;
+    int e = oa::steady_state(series, n, alpha, &ss);
+    if (e) return fail(e, e == SIMB_ERR_PANIC ? "the reference panics on this input (series shorter than 2, or unknown alpha)"
+                                              : "steady state analysis failed");
+    out->mean = ss.mean;
+    out->variance = ss.variance;
+    out->lower = ss.lower;
+    out->upper = ss.upper;
+    out->n = ss.batch_count;
+    if (deletion_point) *deletion_point = ss.deletion_point;
+    if (batch_size) *batch_size = ss.batch_size;
+    if (batch_count) *batch_count = ss.batch_count;
+    return 0;
+}
+int simb_oa_t_score(double alpha, uint64_t df, double* out) {
+    if (!out) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    int e = oa::t_score(alpha, df, out);
+    return e ? fail(e, "t_score: unsupported alpha or df == 0") : 0;
+}
+uint64_t simb_usize_sqrt(uint64_t n) { return oa::usize_sqrt(n); }
+
+int simb_describe(simb_sim* s, char* out, uint64_t capacity) {
+    if (!s || !out) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    const SimbNetDesc& net = s->hn.desc;
+    char buf[1024];
+    std::snprintf(buf, sizeof buf,
+                  "{\"models\": %u, \"connectors\": %u, \"routes\": %u, \"f64_rows\": %u, \"u32_rows\": %u, "
+                  "\"state_bytes_per_replication\": %u, \"max_pending\": %u, \"ring_u32_slots\": %u, \"ring_f64_slots\": %u, "
+                  "\"tile\": %u, \"smem_bytes\": %u, \"steps_per_launch\": %u, \"stride\": %llu, \"replications\": %llu, "
+                  "\"rng_kind\": %d, \"instrument\": %d, \"netdesc_bytes\": %u}",
+                  net.n_models, net.n_connectors, net.n_routes, net.n_drows, net.n_wrows, net.n_drows * 8u + net.n_wrows * 4u,
+                  net.max_pending, s->hn.ring_w_slots, s->hn.ring_d_slots, s->dims.tile, s->dims.smem_bytes, s->K,
+                  (unsigned long long)s->st.stride, (unsigned long long)s->st.n, s->rng_kind, s->instrument ? 1 : 0,
+                  (unsigned)sizeof(SimbNetDesc));
+    put_str(out, capacity, buf);
+    return 0;
+}
+int simb_model_count(simb_sim* s, uint64_t* models, uint64_t* connectors) {
+    if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");
+    if (models) *models = s->hn.desc.n_models;
+    if (connectors) *connectors = s->hn.desc.n_connectors;
+    return 0;
+}
+
+}  // extern "C"

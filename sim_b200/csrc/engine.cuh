@@ -1,0 +1,49 @@
+// sim_b200/csrc/engine.cuh -- host-callable launch interface of the CUDA engine (engine.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "net.h"
+
+namespace simb {
+
+struct EngineDims {
+    uint32_t tile;        // replications per CTA (= threads per CTA)
+    uint32_t smem_bytes;  // dynamic shared memory per CTA
+    uint32_t grid;        // CTAs per launch
+};
+
+// chooses the tile width for a layout and sets the kernel attributes; returns cudaError_t
+int engine_configure(const SimbNetDesc& net, uint64_t stride_hint, int rng_kind, bool instrument, EngineDims* dims);
+
+// one step-kernel launch: every live replication executes up to la.k Simulation::step()s
+int engine_launch_step(const SimbNetDesc& net, const SimbDevState& st, const SimbLaunch& la, const EngineDims& dims,
+                       int rng_kind, bool instrument, bool count_active, cudaStream_t stream);
+
+// state initialisation (Simulation::post / put): row constants, RNG state, absent padding lanes.
+// keep_mask bit 0: keep clock, bit 1: keep mailbox (ctl.npend + pending rows), bit 2: keep RNG rows
+int engine_launch_init(const SimbNetDesc& net, const SimbDevState& st, const double* d_init, const uint32_t* w_init,
+                       const uint32_t* preload_slots, const uint32_t* preload_values, uint32_t n_preload, int rng_kind,
+                       bool instrument, uint32_t keep_mask, cudaStream_t stream);
+
+// Simulation::reset_messages / reset_global_time (mod.rs:131-144)
+int engine_launch_reset(const SimbNetDesc& net, const SimbDevState& st, bool messages, bool clock, cudaStream_t stream);
+
+// Simulation::inject_input (mod.rs:189-191) on every replication whose mask byte is non-zero (mask
+// may be null = all).  *overflow (device counter) is incremented for replications whose mailbox is full.
+int engine_launch_inject(const SimbNetDesc& net, const SimbDevState& st, uint32_t content, uint32_t route_word,
+                         const uint8_t* mask, unsigned long long* overflow, cudaStream_t stream);
+
+// re-seed (Simulation::set_rng): resets draw index / PCG state
+int engine_launch_set_rng(const SimbNetDesc& net, const SimbDevState& st, int rng_kind, cudaStream_t stream);
+
+// reductions: per-block partial sums written to `partials` (one double + one u64 count per block)
+// which = 0: sum over replications of wait_sum/wait_n where wait_n > 0 (count = number of such)
+// which = 1: sum of (wait_sum/wait_n - mean)^2 over the same set
+// which = 2: sum of steps (as double) / count = sum of events -- u64 exact in `counts`
+int engine_launch_reduce(const SimbNetDesc& net, const SimbDevState& st, int which, double mean, double* partial_sums,
+                         unsigned long long* partial_counts, uint32_t* n_blocks, cudaStream_t stream);
+
+uint32_t engine_reduce_blocks(uint64_t n);
+
+}  // namespace simb

@@ -1,0 +1,214 @@
+"""GPU parity tests: the CUDA engine (through the C ABI, via sim_b200.Simulation) against the CPU
+oracle on identical per-replication uniform streams.  Discrete results (event order, message and
+record counts, step / event / draw counts) must match bit-exactly -- they are compared through the
+per-replication trace hash and, for traced replications, event by event -- and f64 clocks within
+1e-12 relative (north_star)."""
+import numpy as np
+import pytest
+
+import networks
+import oracle_api
+from sim_b200 import Message
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-12
+
+
+def _sim(models, conns, n, **kw):
+    from sim_b200 import Simulation
+    kw.setdefault("instrument", True)
+    return Simulation.post(models, conns, replications=n, **kw)
+
+
+def _close(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    both_nan = np.isnan(a) & np.isnan(b)
+    both_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
+    ok = both_nan | both_inf | (np.abs(a - b) <= REL * np.maximum(1.0, np.maximum(np.abs(a), np.abs(b))))
+    return bool(ok.all())
+
+
+@pytest.mark.parametrize("name", sorted(networks.ALL))
+@pytest.mark.parametrize("k", [1, 7])
+def test_step_n_matches_oracle(name, k):
+    models, conns = networks.ALL[name]()
+    n, steps = 96, 1500
+    sim = _sim(models, conns, n, seed=42, steps_per_launch=k)
+    sim.step_n(steps)
+    ref = oracle_api.OracleSimulation(models, conns).run_batch(42, 0, n, threads=8, nsteps=steps)
+    assert ref["err"] == 0
+    assert (sim.get_errors() == 0).all()
+    assert (sim.get_trace_hash() == ref["hash"]).all()
+    assert (sim.get_steps() == ref["steps"]).all()
+    assert (sim.get_events() == ref["events"]).all()
+    assert _close(sim.get_global_time(), ref["time"])
+    c = sim.get_counters()
+    assert c["steps"] == ref["totals"]["steps"]
+    assert c["events"] == ref["totals"]["ext"] + ref["totals"]["int"]
+
+
+def test_trace_event_by_event_mm1():
+    models, conns = networks.mm1(store_records=True)
+    sim = _sim(models, conns, 8, seed=7, trace_replications=2, trace_capacity=20000, steps_per_launch=5)
+    sim.step_n(3000)
+    for r in range(2):
+        o = oracle_api.OracleSimulation(models, conns)
+        o.set_rng_philox(7, r)
+        o.trace_enable(True)
+        e, _ = o.step_n(3000, collect=False)
+        assert e == 0
+        a, b = o.trace(), sim.get_trace(r)
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            assert {k: x[k] for k in ("step", "kind", "index", "action", "aux", "content")} == \
+                   {k: y[k] for k in ("step", "kind", "index", "action", "aux", "content")}
+            assert _close(x["time"], y["time"])
+        # get_records parity (time, action, subject) for every model
+        for m in models:
+            e, recs = o.get_records(m.id)
+            got = sim.get_records(m.id, r)
+            assert [(x[1], x[2]) for x in recs] == [(x[1], x[2]) for x in got]
+            assert _close([x[0] for x in recs], [x[0] for x in got])
+
+
+def test_step_until_and_wait_statistic():
+    """BASELINE config 1/2 shape: step_until + IID mean waiting time over replications."""
+    n, until = 512, 400.0
+    models, conns = networks.mm1()
+    sim = _sim(models, conns, n, seed=42, stat_model_id="processor-01", steps_per_launch=16)
+    sim.step_until(until)
+    rec_models, _ = networks.mm1(store_records=True)  # the oracle derives waits from records (web.rs:571-597)
+    ref = oracle_api.OracleSimulation(rec_models, conns).run_batch(42, 0, n, threads=8, until=until,
+                                                                   stat_model_id="processor-01")
+    assert (sim.get_trace_hash() == ref["hash"]).all()
+    assert (sim.get_steps() == ref["steps"]).all()
+    t = sim.get_global_time()
+    assert (t >= until).all() and _close(t, ref["time"])
+    s, cnt = sim.get_wait_stats()
+    assert (cnt == ref["wait_n"]).all()
+    assert _close(s, ref["wait_sum"])
+    means = ref["wait_sum"][ref["wait_n"] > 0] / ref["wait_n"][ref["wait_n"] > 0]
+    e, want = oracle_api.independent_sample(means, 0.05)
+    got = sim.independent_sample_ci(0.05)
+    assert got["n"] == means.size
+    for key in ("mean", "variance", "lower", "upper"):
+        assert abs(got[key] - want[key]) <= 1e-10 * max(1.0, abs(want[key])), key
+    # a second step_until continues every replication (at least one more step each, mod.rs:279-286)
+    before = sim.get_steps().copy()
+    sim.step_until(until)
+    assert (sim.get_steps() == before + 1).all()
+
+
+def test_reference_default_stream_pcg():
+    """Replication 0 under SIMB_RNG_PCG64MCG seed 42 consumes the reference's default stream
+    Pcg64Mcg::new(42) (dynamic_rng.rs:7-9)."""
+    from sim_b200.simulator import RNG_PCG64MCG
+    models, conns = networks.mm1()
+    sim = _sim(models, conns, 4, seed=42, rng_kind=RNG_PCG64MCG, steps_per_launch=3)
+    sim.step_n(3000)
+    for r in range(4):
+        o = oracle_api.OracleSimulation(models, conns)
+        o.set_rng_pcg(42 + r)
+        o.trace_enable(False)
+        o.step_n(3000, collect=False)
+        assert o.trace_hash() == int(sim.get_trace_hash()[r])
+        assert _close(o.get_global_time(), sim.get_global_time()[r])
+
+
+def test_external_uniform_stream():
+    """Fed an explicit u64 draw stream, the engine consumes it exactly like the oracle does."""
+    from sim_b200.simulator import RNG_EXTERNAL
+    models, conns = networks.tandem()
+    n, per_rep = 32, 4000
+    draws = np.stack([oracle_api.pcg_fill(1000 + r, per_rep) for r in range(n)], axis=1)
+    sim = _sim(models, conns, n, rng_kind=RNG_EXTERNAL, steps_per_launch=4)
+    sim.set_rng_stream(draws)
+    sim.step_n(1200)
+    assert (sim.get_errors() == 0).all()
+    used = sim.get_draws()
+    for r in range(0, n, 5):
+        o = oracle_api.OracleSimulation(models, conns)
+        o.set_rng_external(draws[:, r])
+        o.trace_enable(False)
+        e, _ = o.step_n(1200, collect=False)
+        assert e == 0
+        assert o.trace_hash() == int(sim.get_trace_hash()[r])
+        assert o.rng_draws() == int(used[r])
+
+
+def test_structural_fixtures_on_device():
+    # load_balancer_round_robin_outputs (simulations.rs:586-603): 28 steps -> 3 arrivals per storage
+    models, conns = networks.load_balancer()
+    sim = _sim(models, conns, 33, seed=1)
+    sim.step_n(28)
+    assert (sim.get_message_counts() == np.array([9, 3, 3, 3]) * 33).all()
+    # exclusive gateway (simulations.rs:348-374): 601 steps -> exactly 200 routed jobs
+    models, conns = networks.exclusive_gateway()
+    sim = _sim(models, conns, 10, seed=1)
+    sim.step_n(601)
+    assert int(sim.get_message_counts()[1:].sum()) == 200 * 10
+    # processor network (web.rs:303-316): 720 steps -> 30 storage arrivals
+    models, conns = networks.processor_network()
+    sim = _sim(models, conns, 5, seed=3)
+    sim.step_n(720)
+    mc = sim.get_message_counts()
+    assert int(mc[2] + mc[7]) == 30 * 5
+    # custom passive (custom.rs:113-118): 9 steps -> 4 messages
+    models, conns = networks.generator_passive()
+    sim = _sim(models, conns, 3, seed=9)
+    sim.step_n(9)
+    assert int(sim.get_message_counts()[0]) == 4 * 3
+
+
+def test_injection_exchange_on_device():
+    """injection_initiated_stored_value_exchange (simulations.rs:608-678)."""
+    models, conns = networks.storage_exchange()
+    sim = _sim(models, conns, 5, max_pending=4)
+    sim.inject_input(Message.new("manual", "manual", "storage-01", "store", 0.0, "42"))
+    sim.step()
+    sim.inject_input(Message.new("manual", "manual", "storage-01", "read", 0.0, ""))
+    sim.step()
+    sim.inject_input(Message.new("manual", "manual", "storage-02", "read", 0.0, ""))
+    sim.step()
+    for r in (0, 4):
+        msgs = sim.get_messages(r)
+        assert msgs[0].content == "42"
+        assert msgs[0].target_id == "storage-01"
+    assert (sim.get_global_time() == 0.0).all()
+    assert sim.get_status("storage-02", 0) == "Storing 42"
+
+
+def test_processor_from_queue_cadence():
+    """processor_from_queue_response_time_is_correct (web.rs:71-95): message exactly on even steps."""
+    models, conns = networks.processor_from_queue()
+    sim = _sim(models, conns, 4, seed=5)
+    for step in range(1, 41):
+        sim.step()
+        msgs = sim.get_messages(1)
+        if step % 2 == 0:
+            assert len(msgs) == 1 and msgs[0].content == "job %d" % (step // 2)
+        else:
+            assert msgs == []
+
+
+def test_errors_are_sticky_and_named():
+    from sim_b200 import SimulationError
+    models, conns = networks.mm1()
+    sim = _sim(models, conns, 6)
+    mask = np.array([0, 1, 0, 0, 1, 0], np.uint8)
+    sim.inject_input(Message.new("manual", "manual", "processor-01", "no-such-port", 0.0, "x"), replica_mask=mask)
+    with pytest.raises(SimulationError) as ei:
+        sim.step_n(10)
+    assert ei.value.name == "InvalidMessage"  # processor.rs:225
+    assert (sim.get_errors() == np.array([0, 7, 0, 0, 7, 0])).all()
+    steps = sim.get_steps()
+    assert steps[1] == 0 and steps[0] == 10
+
+
+def test_status_strings():
+    models, conns = networks.status_pair()
+    sim = _sim(models, conns, 2)
+    assert sim.get_status("generator-01") == "Generating jobs"
+    assert sim.get_status("load-balancer-01") == "Listening for requests"
