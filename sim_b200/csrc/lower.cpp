@@ -295,7 +295,9 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
     std::vector<PendingModel> pm(jm.arr.size());
     uint32_t n_wcum = 0;
     const uint32_t qcap = opt.queue_capacity ? clamp_u32(opt.queue_capacity, 65535) : 64;
-    const uint32_t tcap = qcap < 4 ? 4 : (qcap > 16 ? 16 : qcap);  // transient queues (drain every step)
+    // transient queues (LoadBalancer, Gate, gateways: they drain within a step or two) default to 16
+    // slots; an explicit simb_config.queue_capacity applies to every queue
+    const uint32_t tcap = opt.queue_capacity ? (qcap < 4 ? 4 : qcap) : 16;
     bool overflow = false;
 
     // ---- pass 1: models -------------------------------------------------------------------------

@@ -115,9 +115,9 @@ int steady_state(const double* x, uint64_t n, double alpha, SteadyState* out) {
     int e = t_score(alpha, batches, &t_lo);
     if (e) return e;
     if ((e = t_score(alpha, batches - 1, &t_hi))) return e;
-    const double se = std::sqrt(bv) / std::sqrt((double)batches);
-    out->lower = bm - t_lo * se;
-    out->upper = bm + t_hi * se;
+    // same association as the source: (t * sqrt(var)) / sqrt(n)
+    out->lower = bm - t_lo * std::sqrt(bv) / std::sqrt((double)batches);
+    out->upper = bm + t_hi * std::sqrt(bv) / std::sqrt((double)batches);
     return 0;
 }
 

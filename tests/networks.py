@@ -285,9 +285,9 @@ def gateway_network():
         C("c14", "xgw-r", "proc-y", "y", "job"),
         C("c15", "xgw-r", "proc-z", "z", "job"),
         C("c16", "proc-x", "gate-r", "done", "job"),
-        C("c17", "proc-y", "gate-r", "done", "job"),
+        C("c17", "proc-y", "gate-r", "done", "activation"),
         C("c18", "proc-z", "gate-r", "done", "deactivation"),
-        C("c19", "proc-x", "gate-r", "done", "activation"),
+        C("c19", "proc-y", "storage-r", "done", "store"),
         C("c20", "gate-r", "storage-r", "job", "store"),
     ]
     return models, connectors

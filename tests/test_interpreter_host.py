@@ -1,0 +1,167 @@
+"""CPU tier for the device interpreter: sim_b200/csrc/core.cuh + lower.cpp compiled as plain C++
+(tests/hostsim, a unit-test harness -- never part of the product) against the oracle, on identical
+per-replication streams.  The same comparisons run against the real CUDA kernels in
+test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import hostsim_api as H
+import networks
+import oracle_api as O
+
+
+def _oracle(models, conns, seed, rep, steps=None, until=None, store=False):
+    o = O.OracleSimulation(models, conns)
+    o.set_rng_philox(seed, rep)
+    o.trace_enable(store)
+    e, _ = (o.step_n(steps, collect=False) if steps is not None else o.step_until(until, collect=False))
+    return e, o
+
+
+@pytest.mark.parametrize("name", sorted(networks.ALL))
+def test_step_n_hash_counts_time(name):
+    models, conns = networks.ALL[name]()
+    n, steps = 6, 2500
+    hs = H.HostSim(models, conns, n=n, seed=42)
+    hs.step_n(steps)
+    for r in range(n):
+        e, o = _oracle(models, conns, 42, r, steps=steps)
+        c = o.counters()
+        assert e == 0 and hs.errors()[r] == 0
+        assert o.trace_hash() == int(hs.hash()[r])
+        assert (c["steps"], c["events"], o.rng_draws()) == (int(hs.steps()[r]), int(hs.events()[r]), int(hs.draws()[r]))
+        assert o.get_global_time() == hs.time()[r]  # same libm on both sides here: bit-equal
+
+
+def test_full_trace_and_counts_gateway_network():
+    models, conns = networks.gateway_network()
+    hs = H.HostSim(models, conns, n=2, seed=3, trace_reps=2, trace_cap=100000)
+    hs.step_n(4000)
+    tot_conn = np.zeros(len(conns), np.uint64)
+    for r in range(2):
+        e, o = _oracle(models, conns, 3, r, steps=4000, store=True)
+        assert o.trace() == hs.trace(r)
+        tot_conn += np.array(o.connector_messages(), np.uint64)
+    assert (hs.conn_counts() == tot_conn).all()
+
+
+def test_replication_offset_is_a_pure_relabelling():
+    """Sharding invariance: local replication r of a shard with offset k is global replication k + r."""
+    models, conns = networks.tandem()
+    a = H.HostSim(models, conns, n=8, seed=9)
+    b = H.HostSim(models, conns, n=3, seed=9, rep_offset=5)
+    a.step_n(1500)
+    b.step_n(1500)
+    assert (a.hash()[5:8] == b.hash()).all() and (a.time()[5:8] == b.time()).all()
+
+
+def test_step_until_semantics_and_wait_statistic():
+    models, conns = networks.mm1()
+    rec_models, _ = networks.mm1(store_records=True)
+    hs = H.HostSim(models, conns, n=5, seed=42, stat_model_id="processor-01")
+    hs.step_until(300.0)
+    s, cnt = hs.wait()
+    for r in range(5):
+        e, o = _oracle(rec_models, conns, 42, r, until=300.0)
+        assert o.trace_hash() == int(hs.hash()[r]) and o.get_global_time() == hs.time()[r]
+        ws, wn = o.mean_wait("processor-01")
+        assert wn == cnt[r] and abs(ws - s[r]) <= 1e-12 * max(1.0, abs(ws))
+    before = hs.steps().copy()
+    hs.step_until(300.0)  # already past `until`: exactly one more step each (mod.rs:279-286)
+    assert (hs.steps() == before + 1).all()
+
+
+def test_pcg_mode_is_the_reference_default_stream():
+    models, conns = networks.mm1()
+    hs = H.HostSim(models, conns, n=3, seed=42, rng_kind=1)
+    hs.step_n(2000)
+    for r in range(3):
+        o = O.OracleSimulation(models, conns)
+        o.set_rng_pcg(42 + r)  # r = 0: Pcg64Mcg::new(42), dynamic_rng.rs:7-9
+        o.trace_enable(False)
+        o.step_n(2000, collect=False)
+        assert o.trace_hash() == int(hs.hash()[r]) and o.get_global_time() == hs.time()[r]
+
+
+def test_external_stream_mode():
+    models, conns = networks.exclusive_gateway()
+    n, per = 4, 3000
+    draws = np.stack([O.pcg_fill(77 + r, per) for r in range(n)], axis=1)
+    hs = H.HostSim(models, conns, n=n, rng_kind=2)
+    hs.set_stream(draws)
+    hs.step_n(900)
+    for r in range(n):
+        o = O.OracleSimulation(models, conns)
+        o.set_rng_external(draws[:, r])
+        o.trace_enable(False)
+        o.step_n(900, collect=False)
+        assert o.trace_hash() == int(hs.hash()[r]) and o.rng_draws() == int(hs.draws()[r])
+    short = H.HostSim(models, conns, n=1, rng_kind=2)
+    short.set_stream(draws[:5, :1])
+    short.step_n(900)
+    assert short.errors()[0] == 37  # SIMB_ERR_STREAM_EXHAUSTED
+
+
+def test_injection_and_storage_exchange():
+    models, conns = networks.storage_exchange()
+    hs = H.HostSim(models, conns, n=2, max_pending=4)
+    assert hs.inject_input("storage-01", "store", "42") == 0
+    hs.step_n(1)
+    hs.inject_input("storage-01", "read", "")
+    hs.step_n(1)
+    assert [p[0] for p in hs.pending(0)] == ["42"]
+    hs.inject_input("storage-02", "read", "")
+    hs.step_n(1)
+    assert hs.pending(1)[0][0] == "42" and (hs.time() == 0.0).all()
+
+
+def test_gate_strands_jobs_when_activation_arrives_in_the_same_step():
+    """gate.rs quirk: an activation arriving while Pass with queued jobs resets
+    until_next_event to +INF and strands them until the next job arrives."""
+    from sim_b200 import Connector, ContinuousRandomVariable, Gate, Generator, Model, Storage
+    models = [Model.new("gen", Generator.new(ContinuousRandomVariable.Exp(1.0), None, "job", False, None)),
+              Model.new("gate", Gate.new("job", "activation", "deactivation", "job", False)),
+              Model.new("store", Storage.new("store", "read", "stored", False))]
+    conns = [Connector.new("c1", "gen", "gate", "job", "job"), Connector.new("c2", "gen", "gate", "job", "activation"),
+             Connector.new("c3", "gate", "store", "job", "store")]
+    hs = H.HostSim(models, conns, n=1, seed=1, trace_reps=1, trace_cap=10000, queue_capacity=64)
+    hs.step_n(40)
+    e, o = _oracle(models, conns, 1, 0, steps=40, store=True)
+    assert o.trace() == hs.trace(0)
+    assert hs.conn_counts()[2] == 0  # every job is stranded: nothing ever reaches the storage
+    assert hs.errors()[0] == 0
+    hs.step_n(400)                   # ... until the bounded device queue overflows (no reference analogue)
+    assert hs.errors()[0] == 32      # SIMB_ERR_CAPACITY
+
+
+def test_runtime_errors_match_the_oracle():
+    for kw, want in ((dict(capacity=0), 5), (dict(lam_gen=0.0), 15), (dict(lam_proc=-1.0), 15)):
+        models, conns = networks.mm1(**kw)
+        hs = H.HostSim(models, conns, n=1)
+        hs.step_n(5)
+        o = O.OracleSimulation(models, conns)
+        o.set_rng_philox(42, 0)
+        assert o.step_n(5)[0] == want and hs.errors()[0] == want
+    models, conns = networks.mm1()
+    hs = H.HostSim(models, conns, n=1)
+    hs.inject_input("processor-01", "bogus", "x")
+    hs.step_n(3)
+    assert hs.errors()[0] == 7 and hs.steps()[0] == 0
+
+
+def test_unbounded_reference_queue_overflows_with_capacity_error():
+    """Processor default capacity is usize::MAX (processor.rs:40-42); the device ring is bounded."""
+    models, conns = networks.mm1(capacity=None, lam_gen=5.0, lam_proc=0.5)  # rho = 10: the queue explodes
+    hs = H.HostSim(models, conns, n=1, queue_capacity=8)
+    hs.step_n(400)
+    assert hs.errors()[0] == 32
+    big = H.HostSim(models, conns, n=1, queue_capacity=4096)
+    big.step_n(400)
+    assert big.errors()[0] == 0
+
+
+def test_all_passive_network():
+    models, conns = networks.storage_exchange()
+    hs = H.HostSim(models, conns, n=1)
+    hs.step_n(1)
+    assert hs.time()[0] == float("inf") and np.isnan(hs.until(0)[0])

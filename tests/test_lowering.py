@@ -1,0 +1,71 @@
+"""Descriptor lowering (sim_b200/csrc/lower.cpp): the JSON wire schema of the reference's serde
+attributes, error codes, and the layout that the roofline accounting uses."""
+import json
+
+import pytest
+
+import hostsim_api as H
+import networks
+
+
+def _lower(models_json, connectors_json="[]", **kw):
+    return H.HostSim(None, None, raw_json=(models_json, connectors_json), **kw)
+
+
+def test_mm1_layout_is_frozen():
+    """DESIGN.md "state layout": M/M/1 = 4 f64 rows + 14 u32 rows = 88 B per replication
+    (92 B with the waiting-time accumulators)."""
+    models, conns = networks.mm1()
+    lay = H.HostSim(models, conns, n=1, instrument=False).layout()
+    assert (lay["n_drows"], lay["n_wrows"], lay["max_pending"], lay["ring_w_slots"]) == (4, 12, 2, 14)
+    lay = H.HostSim(models, conns, n=1, instrument=False, stat_model_id="processor-01").layout()
+    assert (lay["n_drows"], lay["n_wrows"], lay["ring_d_slots"]) == (5, 13, 14)
+
+
+def test_field_order_is_irrelevant_and_unknown_fields_are_ignored():
+    # tests/web.rs:321-414 (YAML field order) / web.rs:150 (`untilJobCompletion` is not a field)
+    a = [{"type": "Processor", "id": "p", "portsIn": {"job": "job"}, "portsOut": {"job": "out"},
+          "serviceTime": {"exp": {"lambda": 1.0}}, "queueCapacity": 3}]
+    b = [{"queueCapacity": 3, "serviceTime": {"exp": {"lambda": 1.0}}, "portsOut": {"job": "out"},
+          "untilJobCompletion": 0.0, "portsIn": {"job": "job"}, "id": "p", "type": "Processor"}]
+    assert _lower(json.dumps(a)).layout() == _lower(json.dumps(b)).layout()
+
+
+@pytest.mark.parametrize("doc,status", [
+    ("[{\"id\": \"x\", \"type\": \"Coupled\"}]", 33),           # out of scope: SIMB_ERR_UNSUPPORTED_MODEL
+    ("[{\"id\": \"x\", \"type\": \"MyCustomModel\"}]", 33),
+    ("[{\"id\": \"x\"}]", 13),                                   # missing field `type`
+    ("[{\"id\": \"g\", \"type\": \"Generator\", \"portsIn\": {}, \"portsOut\": {\"job\": \"job\"}}]", 13),
+    ("[{\"id\": \"g\", \"type\": \"Generator\", \"portsIn\": {}, \"portsOut\": {\"job\": \"job\"}, "
+     "\"messageInterdepartureTime\": {\"gamma\": {\"shape\": 1, \"scale\": 1}}}]", 33),
+    ("not json", 13),
+    ("[]", 1),
+])
+def test_rejections(doc, status):
+    with pytest.raises(RuntimeError) as ei:
+        _lower(doc)
+    assert "(%d)" % status in str(ei.value)
+
+
+def test_stat_model_must_be_a_processor():
+    models, conns = networks.mm1()
+    with pytest.raises(RuntimeError, match=r"\(2\)"):
+        H.HostSim(models, conns, stat_model_id="nope")
+    with pytest.raises(RuntimeError, match=r"\(1\)"):
+        H.HostSim(models, conns, stat_model_id="storage-01")
+
+
+def test_state_block_preloads_processor_queue():
+    # tests/web.rs:30-46
+    models, conns = networks.processor_from_queue(7)
+    hs = H.HostSim(models, conns, n=1)
+    assert hs.layout()["ring_w_slots"] >= 7
+    hs.step_n(2)
+    assert [p[0] for p in hs.pending(0)] == ["job 1"]
+
+
+def test_every_network_fits_the_descriptor():
+    for name, f in networks.ALL.items():
+        models, conns = f()
+        lay = H.HostSim(models, conns, n=1).layout()
+        assert lay["n_models"] == len(models) and lay["n_connectors"] == len(conns), name
