@@ -185,6 +185,7 @@ int run_steps(simb_sim* s, int mode, uint64_t n, double until) {
             la.k = (uint32_t)std::min<uint64_t>(left, s->K);
             left -= la.k;
             const bool last = left == 0;
+            la.settle = last ? 1u : 0u;  // the state the caller can observe owes no deferred draw
             if (last) CUDA_TRY(cudaMemsetAsync(s->st.totals + 2, 0, 2 * sizeof(unsigned long long), s->stream));
             CUDA_TRY(engine_launch_step(net, s->st, la, s->dims, s->rng_kind, s->instrument, last, s->stream));
             issued++;
@@ -199,6 +200,7 @@ int run_steps(simb_sim* s, int mode, uint64_t n, double until) {
         for (;;) {
             for (uint32_t i = 0; i < round; i++) {
                 const bool last = i + 1 == round;
+                la.settle = last ? 1u : 0u;
                 if (last) CUDA_TRY(cudaMemsetAsync(s->st.totals + 2, 0, 2 * sizeof(unsigned long long), s->stream));
                 CUDA_TRY(engine_launch_step(net, s->st, la, s->dims, s->rng_kind, s->instrument, last, s->stream));
                 issued++;

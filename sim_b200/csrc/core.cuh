@@ -106,9 +106,13 @@ struct Lane {
     uint32_t phase_lo, phase_hi;
     uint64_t hash;
     uint64_t pcg_lo, pcg_hi;
-    uint64_t cache;       // second half of the last Philox block
-    uint32_t cache_block; // block index the cache belongs to (+1; 0 = empty)
+    uint64_t c0, c1, c2, c3;  // next draws of the Philox stream: c0 is draw number draw_idx
+    uint32_t ccount;          // valid entries in c0..c3
     uint32_t key0, key1;
+    uint32_t tmask;           // bit m: the mailbox holds a message for model m
+    uint32_t dm_int, dm_ext;  // deferred continuous draws: "until_next_event[m] = sample(dist[m])" still
+                              // owed from the previous internal phase / this external phase
+    uint32_t absent;
     uint64_t rep_local;
     uint32_t traced;
     uint32_t wait_n;
@@ -145,6 +149,21 @@ SIMB_HD void philox_block(uint32_t key0, uint32_t key1, uint32_t ctr_lo, uint64_
     *b = (uint64_t)c2 | ((uint64_t)c3 << 32);
 }
 
+struct U64Pair {
+    uint64_t a, b;
+};
+// out-of-line copy for the rarely taken refill inside next_u64 (arguments and result by value, so the
+// caller's Lane stays in registers)
+#ifdef __CUDACC__
+static __device__ __host__ __noinline__ U64Pair philox_pair_cold(uint32_t key0, uint32_t key1, uint32_t ctr_lo) {
+#else
+static inline U64Pair philox_pair_cold(uint32_t key0, uint32_t key1, uint32_t ctr_lo) {
+#endif
+    U64Pair r;
+    philox_block(key0, key1, ctr_lo, &r.a, &r.b);
+    return r;
+}
+
 template <int RNG>
 struct Engine {
     const SimbNetDesc& net;
@@ -153,22 +172,39 @@ struct Engine {
 
     SIMB_HD Engine(const SimbNetDesc& n, const SimbDevState& s, const Tables& t) : net(n), st(s), tab(t) {}
 
+    // Append the next Philox block to the per-lane draw cache (call only with ccount <= 2).  Draw
+    // number i is word pair (i & 1) of block i >> 1, so the cache is a pure prefetch of the stream.
+    SIMB_HD void cache_push(Lane& ln, uint32_t nxt, uint64_t a, uint64_t b) {
+        if (nxt & 1u) a = b;  // only right after a state load that left an odd draw index
+        const uint32_t n = ln.ccount;
+        if (n == 0) { ln.c0 = a; ln.c1 = b; }
+        else if (n == 1) { ln.c1 = a; ln.c2 = b; }
+        else { ln.c2 = a; ln.c3 = b; }
+        ln.ccount = n + ((nxt & 1u) ? 1u : 2u);
+    }
+    SIMB_HD void philox_refill(Lane& ln) {
+        const uint32_t nxt = ln.draw_idx + ln.ccount;
+        uint64_t a, b;
+        philox_block(ln.key0, ln.key1, nxt >> 1, &a, &b);
+        cache_push(ln, nxt, a, b);
+    }
+    SIMB_HD void philox_refill_cold(Lane& ln) {
+        const uint32_t nxt = ln.draw_idx + ln.ccount;
+        const U64Pair p = philox_pair_cold(ln.key0, ln.key1, nxt >> 1);
+        cache_push(ln, nxt, p.a, p.b);
+    }
+
     // ---- uniform u64 source (RngCore::next_u64 on the shared DynRng, services.rs:25-27) ----------
     SIMB_HD uint64_t next_u64(Lane& ln) {
         if (RNG == 0) {
-            uint32_t idx = ln.draw_idx++;
-            uint32_t blk = idx >> 1;
-            if (idx & 1u) {
-                if (ln.cache_block == blk + 1u) return ln.cache;
-                uint64_t a, b;
-                philox_block(ln.key0, ln.key1, blk, &a, &b);
-                return b;
-            }
-            uint64_t a, b;
-            philox_block(ln.key0, ln.key1, blk, &a, &b);
-            ln.cache = b;
-            ln.cache_block = blk + 1u;
-            return a;
+            if (ln.ccount == 0) philox_refill_cold(ln);  // rare: the step refills at a warp-uniform point
+            const uint64_t v = ln.c0;
+            ln.c0 = ln.c1;
+            ln.c1 = ln.c2;
+            ln.c2 = ln.c3;
+            ln.ccount--;
+            ln.draw_idx++;
+            return v;
         } else if (RNG == 1) {
             // rand_pcg 0.3 Mcg128Xsl64: state *= MULT (mod 2^128); XSL-RR output
             const uint64_t ML = 0x4385DF649FCCF645ull, MH = 0x2360ED051FC65DA4ull;
@@ -296,6 +332,37 @@ struct Engine {
         return next_u64(ln) < md.q0;
     }
 
+    // ---- deferred continuous draws ------------------------------------------------------------------
+    // A handler that must set until_next_event[m] to a fresh variate only notes the debt; the step
+    // pays all debts at ONE warp-converged point (after the external phase, before the time advance),
+    // so the sampler code is executed once per step instead of once per drawing site.  The uniform
+    // stream is consumed in exactly the reference's order: debts are paid oldest first (previous
+    // internal phase in model order, then this external phase in model order) and any draw that must
+    // happen inline (Bernoulli at arrival, gateway index) first pays the debts that precede it.
+    SIMB_HD bool defer_draw(Lane& ln, uint32_t m, const SimbModelDesc& md, bool ext_phase) {
+        if (md.dist_err) {  // parameter errors surface at draw time (random_variable.rs:72-87)
+            if (!ln.err) ln.err = md.dist_err;
+            return false;
+        }
+        if (ext_phase) ln.dm_ext |= 1u << m;
+        else ln.dm_int |= 1u << m;
+        return true;
+    }
+    SIMB_HD void flush_draws(Lane& ln) {
+        while (ln.dm_int | ln.dm_ext) {
+            uint32_t m;
+            if (ln.dm_int) {
+                m = (uint32_t)lowest_bit(ln.dm_int);
+                ln.dm_int &= ln.dm_int - 1u;
+            } else {
+                m = (uint32_t)lowest_bit(ln.dm_ext);
+                ln.dm_ext &= ln.dm_ext - 1u;
+            }
+            const double dv = sample_continuous(ln, net.models[m]);
+            ln.D(net.drow_until + m) = dv;
+        }
+    }
+
     // ---- instrumentation ---------------------------------------------------------------------------
     template <bool INSTR>
     SIMB_HD void record(Lane& ln, uint32_t m, uint32_t action, uint32_t content, uint32_t aux = 0) {
@@ -336,6 +403,7 @@ struct Engine {
             ln.W(net.wrow_pend + 2 * ln.npend) = content;
             ln.W(net.wrow_pend + 2 * ln.npend + 1) = ROUTE_WORD(rt.tgt_model, rt.tgt_port, rt.connector);
             ln.npend++;
+            if (rt.tgt_model < SIMB_MAX_MODELS) ln.tmask |= 1u << rt.tgt_model;
             if (INSTR) {
                 ln.hash = (ln.hash ^ TRACE_MESSAGE_WORD(rt.connector, content)) * TRACE_HASH_PRIME;
 #if SIMB_ON_DEVICE
@@ -389,6 +457,72 @@ struct Engine {
         return c;
     }
 
+    // ---- per-lane context <-> state tile -----------------------------------------------------------
+    // Before: ln.d / ln.w / ln.stride / ln.ring_* / ln.rep_local are set.  Returns the ctl word.
+    SIMB_HD uint32_t lane_load(Lane& ln, bool instr) {
+        ln.time = ln.D(net.drow_time);
+        const uint32_t ctl = ln.W(net.wrow_ctl);
+        ln.err = CTL_ERR(ctl);
+        ln.npend = CTL_NPEND(ctl);
+        ln.absent = CTL_ABSENT(ctl);
+        ln.steps = ln.W(net.wrow_steps);
+        ln.events = ln.W(net.wrow_events);
+        ln.draw_idx = 0;
+        ln.pcg_lo = ln.pcg_hi = 0;
+        if (RNG == 1) {
+            ln.pcg_lo = (uint64_t)ln.W(net.wrow_rng) | ((uint64_t)ln.W(net.wrow_rng + 1) << 32);
+            ln.pcg_hi = (uint64_t)ln.W(net.wrow_rng + 2) | ((uint64_t)ln.W(net.wrow_rng + 3) << 32);
+        } else {
+            ln.draw_idx = ln.W(net.wrow_rng);
+        }
+        ln.phase_lo = ln.W(net.wrow_phase);
+        ln.phase_hi = net.n_phase_words > 1 ? ln.W(net.wrow_phase + 1) : 0u;
+        ln.hash = 0;
+        if (instr) ln.hash = (uint64_t)ln.W(net.wrow_hash) | ((uint64_t)ln.W(net.wrow_hash + 1) << 32);
+        ln.c0 = ln.c1 = ln.c2 = ln.c3 = 0;
+        ln.ccount = 0;
+        const uint64_t g = st.rep_offset + ln.rep_local;
+        ln.key0 = (uint32_t)g;
+        ln.key1 = (uint32_t)st.seed + (uint32_t)(g >> 32);
+        ln.traced = instr && ln.rep_local < st.trace_reps;
+        const bool has_stat = net.drow_wait != 0;
+        ln.wait_sum = has_stat ? ln.D(net.drow_wait) : 0.0;
+        ln.wait_n = has_stat ? ln.W(net.wrow_waitn) : 0u;
+        ln.dm_int = ln.W(net.wrow_dmask);
+        ln.dm_ext = 0;
+        ln.tmask = 0;
+        for (uint32_t j = 0; j < ln.npend; j++) {
+            const uint32_t t = ROUTE_TGT(ln.W(net.wrow_pend + 2 * j + 1));
+            if (t < SIMB_MAX_MODELS) ln.tmask |= 1u << t;
+        }
+        return ctl;
+    }
+    SIMB_HD void lane_store(Lane& ln, bool instr, uint32_t done_epoch) {
+        ln.D(net.drow_time) = ln.time;
+        ln.W(net.wrow_ctl) = CTL_MAKE(ln.err, done_epoch, ln.npend, ln.absent);
+        ln.W(net.wrow_steps) = ln.steps;
+        ln.W(net.wrow_events) = ln.events;
+        if (RNG == 1) {
+            ln.W(net.wrow_rng) = (uint32_t)ln.pcg_lo;
+            ln.W(net.wrow_rng + 1) = (uint32_t)(ln.pcg_lo >> 32);
+            ln.W(net.wrow_rng + 2) = (uint32_t)ln.pcg_hi;
+            ln.W(net.wrow_rng + 3) = (uint32_t)(ln.pcg_hi >> 32);
+        } else {
+            ln.W(net.wrow_rng) = ln.draw_idx;
+        }
+        ln.W(net.wrow_phase) = ln.phase_lo;
+        if (net.n_phase_words > 1) ln.W(net.wrow_phase + 1) = ln.phase_hi;
+        if (instr) {
+            ln.W(net.wrow_hash) = (uint32_t)ln.hash;
+            ln.W(net.wrow_hash + 1) = (uint32_t)(ln.hash >> 32);
+        }
+        if (net.drow_wait != 0) {
+            ln.D(net.drow_wait) = ln.wait_sum;
+            ln.W(net.wrow_waitn) = ln.wait_n;
+        }
+        ln.W(net.wrow_dmask) = ln.dm_int;
+    }
+
     // ================================================================================================
     // events_ext per model type
     // ================================================================================================
@@ -414,9 +548,7 @@ struct Engine {
                 if (md.flags & MF_STAT) ln.RD(md.ring_d + slot) = ln.time;
                 if (empty) {  // activate :128-150
                     ln.set_phase(m, 1);
-                    double dv = sample_continuous(ln, md);
-                    if (ln.err) break;
-                    ln.D(urow) = dv;
+                    if (!defer_draw(ln, m, md, true)) break;  // until_next_event = service time draw
                     record<INSTR>(ln, m, ACT_ARRIVAL, content);
                     record<INSTR>(ln, m, ACT_PROCESSING_START, content);
                     if (md.flags & MF_STAT) {
@@ -499,6 +631,7 @@ struct Engine {
             case MT_STOCHASTIC_GATE: {  // stochastic_gate.rs:163-172, receive_job :101-122
                 if (port != 0) { ln.err = 7; break; }
                 ln.D(urow) = 0.0;
+                if (ln.dm_int | ln.dm_ext) flush_draws(ln);  // earlier draws of the stream come first
                 bool pass = sample_bernoulli(ln, md);  // Bernoulli draw AT ARRIVAL
                 if (ln.err) break;
                 uint32_t slot;
@@ -612,10 +745,8 @@ struct Engine {
         const uint32_t urow = net.drow_until + m;
         switch (md.type) {
             case MT_GENERATOR: {  // generator.rs:169-177
-                double dv = sample_continuous(ln, md);  // the draw comes first (:102-109, :129-136)
-                if (ln.err) break;
+                if (!defer_draw(ln, m, md, false)) break;  // the draw comes first (:102-109, :129-136)
                 if (ln.phase(m) == 1) {  // release_job :98-123
-                    ln.D(urow) = dv;
                     uint32_t last = ln.W(md.wrow) + 1u;
                     if (last >= SIMB_NUM_LITERAL) { ln.err = 32; break; }  // content code space exhausted
                     ln.W(md.wrow) = last;
@@ -624,7 +755,6 @@ struct Engine {
                     emit<INSTR>(ln, md, 0, c);
                 } else {  // initialize_generation :125-146
                     ln.set_phase(m, 1);
-                    ln.D(urow) = dv;
                     record<INSTR>(ln, m, ACT_INITIALIZATION, SIMB_CONTENT_NONE);
                 }
                 break;
@@ -638,9 +768,7 @@ struct Engine {
                         break;
                     }
                     ln.set_phase(m, 1);  // process_next :160-175
-                    double dv = sample_continuous(ln, md);
-                    if (ln.err) break;
-                    ln.D(urow) = dv;
+                    if (!defer_draw(ln, m, md, false)) break;
                     record<INSTR>(ln, m, ACT_PROCESSING_START, ln.RW(md.ring_w0 + head));
                     if (md.flags & MF_STAT) {
                         ln.wait_sum += ln.time - ln.RD(md.ring_d + head);
@@ -692,6 +820,7 @@ struct Engine {
                 ln.D(urow) = SIMB_INF;
                 if (ln.phase(m) == 1) {  // send_jobs :110-134: one draw per firing
                     ln.set_phase(m, 0);
+                    if (ln.dm_int | ln.dm_ext) flush_draws(ln);  // earlier draws of the stream come first
                     uint32_t idx = sample_index(ln, md);
                     if (ln.err) break;
                     if (idx >= md.n_out) { ln.err = 34; break; }  // flow_paths[idx] out of bounds panics
@@ -782,12 +911,8 @@ struct Engine {
         uint32_t nev = 0;
         // ---- external events: model order, then message order (:202-223) ----
         if (warp_any(had)) {
-            uint32_t tmask = 0;
+            const uint32_t tmask = had ? ln.tmask : 0u;  // a target id matching no model has no bit: dropped
             const uint32_t np = had ? ln.npend : 0u;
-            for (uint32_t j = 0; j < np; j++) {
-                uint32_t t = ROUTE_TGT(ln.W(net.wrow_pend + 2 * j + 1));
-                if (t < M) tmask |= 1u << t;  // a target id matching no model is silently dropped
-            }
             uint32_t wm = warp_or(tmask);
             while (wm) {
                 const int m = lowest_bit(wm);
@@ -802,6 +927,11 @@ struct Engine {
                     }
                 }
             }
+        }
+        // ---- pay the deferred draws (and top up the Philox prefetch) at this converged point ----
+        if (live) {
+            if (RNG == 0 && ln.ccount <= 2u) philox_refill(ln);
+            flush_draws(ln);
         }
         // A failed events_ext aborts the step (`?` at :222); the replication freezes.
         const bool go = live && !ln.err;
@@ -823,6 +953,7 @@ struct Engine {
             }
             ln.time = ln.time + dt;
             ln.npend = 0;  // the mailbox is consumed; events_int refills it from slot 0
+            ln.tmask = 0;
         }
         // ---- internal events in model order (:237-268) ----
         uint32_t wm = warp_or(zmask);

@@ -18,8 +18,9 @@
 
 #include "core.cuh"
 
-#define SIMB_TABLE_QUAL __device__ const
+#define SIMB_TABLE_QUAL __device__ __align__(16) const
 #include "zig_tables.inc"
+#define ZIG_BYTES 2064u  /* 258 doubles: 257 table entries + 1 pad, a multiple of 16 B for the bulk copy */
 
 namespace simb {
 
@@ -85,8 +86,11 @@ __host__ __device__ inline SmemPlan smem_plan(const SimbNetDesc& net, uint32_t t
     return p;
 }
 
+#ifndef SIMB_MIN_BLOCKS
+#define SIMB_MIN_BLOCKS 4 /* <= 64 registers: 32 resident warps per SM measured +15% over 3 (24 warps) */
+#endif
 template <int RNG, bool INSTR>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, SIMB_MIN_BLOCKS)
 simb_step_kernel(const __grid_constant__ SimbNetDesc net, const __grid_constant__ SimbDevState st,
                  const __grid_constant__ SimbLaunch la, const uint32_t count_active) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -113,7 +117,13 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net, const __grid_constant_
     __syncthreads();
     // ---- 1. tile load: one bulk copy per state row, spread over the lanes of warp 0 ----
     if (tid < 32) {
-        if (tid == 0) mbar_expect_tx(bar, net.n_drows * tile * 8u + net.n_wrows * tile * 4u);
+        if (tid == 0) {
+            mbar_expect_tx(bar, net.n_drows * tile * 8u + net.n_wrows * tile * 4u +
+                                    (net.uses_exp ? ZIG_BYTES : 0u) + (net.uses_normal ? ZIG_BYTES : 0u));
+            // ziggurat x tables ride on the same barrier (random per-lane index -> shared memory, not constant)
+            if (net.uses_exp) bulk_g2s(s_expx, ZIG_EXP_X, ZIG_BYTES, bar);
+            if (net.uses_normal) bulk_g2s(s_normx, ZIG_NORM_X, ZIG_BYTES, bar);
+        }
         __syncwarp();
         for (uint32_t r = tid; r < n_rows; r += 32) {
             if (r < net.n_drows) bulk_g2s(s_d + (size_t)r * tile, st.d + (uint64_t)r * st.stride + base, tile * 8u, bar);
@@ -123,12 +133,6 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net, const __grid_constant_
             }
         }
     }
-    // meanwhile: ziggurat x tables into shared memory (random per-lane index -> shared, not constant)
-    if (net.uses_exp)
-        for (uint32_t i = tid; i < 257; i += tile) s_expx[i] = ZIG_EXP_X[i];
-    if (net.uses_normal)
-        for (uint32_t i = tid; i < 257; i += tile) s_normx[i] = ZIG_NORM_X[i];
-    __syncthreads();
     while (!mbar_try_wait(bar, 0)) {
     }
 
@@ -147,36 +151,8 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net, const __grid_constant_
     ln.ring_w = st.ring_w + ln.rep_local;
     ln.ring_d = st.ring_d + ln.rep_local;
     ln.ring_stride = st.stride;
-    ln.time = ln.D(net.drow_time);
-    const uint32_t ctl = ln.W(net.wrow_ctl);
-    ln.err = CTL_ERR(ctl);
-    ln.npend = CTL_NPEND(ctl);
-    const bool absent = CTL_ABSENT(ctl) != 0;
-    ln.steps = ln.W(net.wrow_steps);
-    ln.events = ln.W(net.wrow_events);
-    ln.draw_idx = 0;
-    ln.pcg_lo = ln.pcg_hi = 0;
-    if (RNG == 1) {
-        ln.pcg_lo = (uint64_t)ln.W(net.wrow_rng) | ((uint64_t)ln.W(net.wrow_rng + 1) << 32);
-        ln.pcg_hi = (uint64_t)ln.W(net.wrow_rng + 2) | ((uint64_t)ln.W(net.wrow_rng + 3) << 32);
-    } else {
-        ln.draw_idx = ln.W(net.wrow_rng);
-    }
-    ln.phase_lo = ln.W(net.wrow_phase);
-    ln.phase_hi = net.n_phase_words > 1 ? ln.W(net.wrow_phase + 1) : 0u;
-    ln.hash = 0;
-    if (INSTR) ln.hash = (uint64_t)ln.W(net.wrow_hash) | ((uint64_t)ln.W(net.wrow_hash + 1) << 32);
-    ln.cache = 0;
-    ln.cache_block = 0;
-    {
-        const uint64_t g = st.rep_offset + ln.rep_local;
-        ln.key0 = (uint32_t)g;
-        ln.key1 = (uint32_t)st.seed + (uint32_t)(g >> 32);
-    }
-    ln.traced = INSTR && ln.rep_local < st.trace_reps;
-    const bool has_stat = net.drow_wait != 0;
-    ln.wait_sum = has_stat ? ln.D(net.drow_wait) : 0.0;
-    ln.wait_n = has_stat ? ln.W(net.wrow_waitn) : 0u;
+    const uint32_t ctl = eng.lane_load(ln, INSTR);
+    const bool absent = ln.absent != 0;
 
     // ---- 3. up to K lockstep steps (each warp runs on its own; no block barrier per step) ----
     bool done = absent || (la.mode == 1 && CTL_EPOCH(ctl) == la.epoch);
@@ -188,31 +164,15 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net, const __grid_constant_
         eng.template step<INSTR>(ln, live);
         if (live && la.mode == 1 && !(ln.time < la.until)) done = true;  // step_until: mod.rs:281-285
     }
+    // last launch of an API call: pay the deferred draws so the stored state is observable as is
+    if (la.settle && !absent && (ln.dm_int | ln.dm_ext)) {
+        eng.flush_draws(ln);
+        stepped = true;
+    }
 
     // ---- 4. write back ----
     if (stepped) {
-        ln.D(net.drow_time) = ln.time;
-        ln.W(net.wrow_ctl) = CTL_MAKE(ln.err, (la.mode == 1 && done) ? la.epoch : 0u, ln.npend, absent ? 1u : 0u);
-        ln.W(net.wrow_steps) = ln.steps;
-        ln.W(net.wrow_events) = ln.events;
-        if (RNG == 1) {
-            ln.W(net.wrow_rng) = (uint32_t)ln.pcg_lo;
-            ln.W(net.wrow_rng + 1) = (uint32_t)(ln.pcg_lo >> 32);
-            ln.W(net.wrow_rng + 2) = (uint32_t)ln.pcg_hi;
-            ln.W(net.wrow_rng + 3) = (uint32_t)(ln.pcg_hi >> 32);
-        } else {
-            ln.W(net.wrow_rng) = ln.draw_idx;
-        }
-        ln.W(net.wrow_phase) = ln.phase_lo;
-        if (net.n_phase_words > 1) ln.W(net.wrow_phase + 1) = ln.phase_hi;
-        if (INSTR) {
-            ln.W(net.wrow_hash) = (uint32_t)ln.hash;
-            ln.W(net.wrow_hash + 1) = (uint32_t)(ln.hash >> 32);
-        }
-        if (has_stat) {
-            ln.D(net.drow_wait) = ln.wait_sum;
-            ln.W(net.wrow_waitn) = ln.wait_n;
-        }
+        eng.lane_store(ln, INSTR, (la.mode == 1 && done) ? la.epoch : 0u);
         fence_proxy_async();  // generic-proxy writes -> visible to the bulk (async proxy) stores
     }
     if (count_active) {

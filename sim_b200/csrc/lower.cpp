@@ -579,6 +579,7 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
         net.wrow_hash = wr;
         wr += 2;
     }
+    net.wrow_dmask = wr++;
     net.wrow_phase = wr;
     net.n_phase_words = (uint16_t)((net.n_models + 15) / 16);
     wr += net.n_phase_words;

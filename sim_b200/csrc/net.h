@@ -84,7 +84,7 @@ struct SimbNetDesc {
     uint16_t wrow_pend;     // max_pending x (content, route)
     uint16_t wrow_waitn;    // number of jobs that started service on the MF_STAT processor
     uint16_t uses_exp, uses_normal;
-    uint16_t pad0;
+    uint16_t wrow_dmask;    // models whose until_next_event still owes a deferred draw (core.cuh)
     SimbModelDesc models[SIMB_MAX_MODELS];
     uint16_t route_begin[SIMB_MAX_OUT_PORTS + 1];
     SimbRoute routes[SIMB_MAX_ROUTES];
@@ -151,6 +151,6 @@ struct SimbLaunch {
     uint32_t mode;        // 0 = step_n: run `k` steps; 1 = step_until: run up to `k` steps while clock < until
     uint32_t k;
     uint32_t epoch;       // step_until call epoch (ctl epoch == epoch => finished in this call)
-    uint32_t pad;
+    uint32_t settle;      // 1 = pay every deferred draw before the state is stored (last launch of an API call)
     double until;
 };

@@ -22,7 +22,7 @@ from .coupling import Connector, Message
 from .models import Model
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libsimb200.so")
+_LIB_PATH = os.environ.get("SIMB_LIBRARY", os.path.join(_HERE, "libsimb200.so"))  # override: kernel experiments
 
 RNG_PHILOX, RNG_PCG64MCG, RNG_EXTERNAL = 0, 1, 2
 FLAG_INSTRUMENT = 1

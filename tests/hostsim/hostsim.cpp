@@ -28,71 +28,8 @@ struct HS {
     std::vector<unsigned long long> conn_count, record_count, totals;
     std::vector<uint64_t> ext;
     uint32_t epoch = 0;
+    uint64_t settle_every = 0;
 };
-
-void load_lane(HS* h, Lane& ln, uint64_t r) {
-    const SimbNetDesc& net = h->hn.desc;
-    ln.d = h->d.data() + r;
-    ln.w = h->w.data() + r;
-    ln.stride = (uint32_t)h->n;
-    ln.ring_w = h->ring_w.data() + r;
-    ln.ring_d = h->ring_d.data() + r;
-    ln.ring_stride = h->n;
-    ln.time = ln.D(net.drow_time);
-    uint32_t ctl = ln.W(net.wrow_ctl);
-    ln.err = CTL_ERR(ctl);
-    ln.npend = CTL_NPEND(ctl);
-    ln.steps = ln.W(net.wrow_steps);
-    ln.events = ln.W(net.wrow_events);
-    ln.draw_idx = ln.W(net.wrow_rng);
-    if (h->rng_kind == 1) {
-        ln.pcg_lo = (uint64_t)ln.W(net.wrow_rng) | ((uint64_t)ln.W(net.wrow_rng + 1) << 32);
-        ln.pcg_hi = (uint64_t)ln.W(net.wrow_rng + 2) | ((uint64_t)ln.W(net.wrow_rng + 3) << 32);
-        ln.draw_idx = 0;
-    }
-    ln.phase_lo = ln.W(net.wrow_phase);
-    ln.phase_hi = net.n_phase_words > 1 ? ln.W(net.wrow_phase + 1) : 0;
-    ln.hash = h->instr ? ((uint64_t)ln.W(net.wrow_hash) | ((uint64_t)ln.W(net.wrow_hash + 1) << 32)) : 0;
-    ln.cache = 0;
-    ln.cache_block = 0;
-    uint64_t g = h->st.rep_offset + r;
-    ln.key0 = (uint32_t)g;
-    ln.key1 = (uint32_t)h->st.seed + (uint32_t)(g >> 32);
-    ln.rep_local = r;
-    ln.traced = h->instr && r < h->st.trace_reps;
-    if (h->hn.stat_model >= 0) {
-        ln.wait_sum = ln.D(net.drow_wait);
-        ln.wait_n = ln.W(net.wrow_waitn);
-    } else {
-        ln.wait_sum = 0;
-        ln.wait_n = 0;
-    }
-}
-void store_lane(HS* h, Lane& ln, bool done) {
-    const SimbNetDesc& net = h->hn.desc;
-    ln.D(net.drow_time) = ln.time;
-    ln.W(net.wrow_ctl) = CTL_MAKE(ln.err, done ? h->epoch : 0, ln.npend, 0);
-    ln.W(net.wrow_steps) = ln.steps;
-    ln.W(net.wrow_events) = ln.events;
-    if (h->rng_kind == 1) {
-        ln.W(net.wrow_rng) = (uint32_t)ln.pcg_lo;
-        ln.W(net.wrow_rng + 1) = (uint32_t)(ln.pcg_lo >> 32);
-        ln.W(net.wrow_rng + 2) = (uint32_t)ln.pcg_hi;
-        ln.W(net.wrow_rng + 3) = (uint32_t)(ln.pcg_hi >> 32);
-    } else {
-        ln.W(net.wrow_rng) = ln.draw_idx;
-    }
-    ln.W(net.wrow_phase) = ln.phase_lo;
-    if (net.n_phase_words > 1) ln.W(net.wrow_phase + 1) = ln.phase_hi;
-    if (h->instr) {
-        ln.W(net.wrow_hash) = (uint32_t)ln.hash;
-        ln.W(net.wrow_hash + 1) = (uint32_t)(ln.hash >> 32);
-    }
-    if (h->hn.stat_model >= 0) {
-        ln.D(net.drow_wait) = ln.wait_sum;
-        ln.W(net.wrow_waitn) = ln.wait_n;
-    }
-}
 
 template <int RNG, bool INSTR>
 void run(HS* h, int mode, uint64_t k, double until) {
@@ -100,15 +37,29 @@ void run(HS* h, int mode, uint64_t k, double until) {
     Engine<RNG> eng(h->hn.desc, h->st, tab);
     for (uint64_t r = 0; r < h->n; r++) {
         Lane ln;
-        load_lane(h, ln, r);
+        ln.d = h->d.data() + r;
+        ln.w = h->w.data() + r;
+        ln.stride = (uint32_t)h->n;
+        ln.ring_w = h->ring_w.data() + r;
+        ln.ring_d = h->ring_d.data() + r;
+        ln.ring_stride = h->n;
+        ln.rep_local = r;
+        eng.lane_load(ln, INSTR);
         bool done = false;
         for (uint64_t i = 0; mode == 1 || i < k; i++) {
             bool live = !ln.err && !done;
             if (!live) break;
             eng.template step<INSTR>(ln, true);
             if (mode == 1 && !(ln.time < until)) done = true;
+            // h->settle_every > 0: store + reload the lane every few steps, as consecutive kernel
+            // launches do (exercises the persisted deferred-draw mask and the Philox prefetch restart)
+            if (h->settle_every && (i + 1) % h->settle_every == 0) {
+                eng.lane_store(ln, INSTR, 0);
+                eng.lane_load(ln, INSTR);
+            }
         }
-        store_lane(h, ln, done);
+        eng.flush_draws(ln);  // "settle": what the last launch of an API call does
+        eng.lane_store(ln, INSTR, done ? h->epoch : 0);
     }
 }
 void dispatch(HS* h, int mode, uint64_t k, double until) {
@@ -196,6 +147,7 @@ void* hs_new(const char* models, const char* connectors, uint64_t n, uint64_t re
     return h;
 }
 void hs_free(void* h) { delete (HS*)h; }
+void hs_set_reload_every(void* h, uint64_t n) { ((HS*)h)->settle_every = n; }
 void hs_set_stream(void* hv, const uint64_t* draws, uint64_t per_rep) {
     HS* h = (HS*)hv;
     h->ext.assign(draws, draws + per_rep * h->n);

@@ -50,6 +50,10 @@ class HostSim:
         except Exception:
             pass
 
+    def set_reload_every(self, n):
+        """store + reload the lane state every n steps, like consecutive kernel launches of K = n"""
+        self.L.hs_set_reload_every(self.h, C.c_uint64(n))
+
     def set_stream(self, draws):  # draws[i, r]
         a = np.ascontiguousarray(draws, dtype=np.uint64)
         self.L.hs_set_stream(self.h, a.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_uint64(a.shape[0]))

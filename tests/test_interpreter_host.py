@@ -33,6 +33,20 @@ def test_step_n_hash_counts_time(name):
         assert o.get_global_time() == hs.time()[r]  # same libm on both sides here: bit-equal
 
 
+@pytest.mark.parametrize("k", [1, 2, 5])
+def test_results_do_not_depend_on_steps_per_launch(k):
+    """Reloading the lane state every k steps (what consecutive kernel launches do) must not change
+    anything: deferred draws persist through the state, the Philox prefetch restarts cleanly."""
+    for name in ("mm1", "gateway_network", "stochastic_gate"):
+        models, conns = networks.ALL[name]()
+        a = H.HostSim(models, conns, n=3, seed=11)
+        b = H.HostSim(models, conns, n=3, seed=11)
+        b.set_reload_every(k)
+        a.step_n(1200)
+        b.step_n(1200)
+        assert (a.hash() == b.hash()).all() and (a.time() == b.time()).all() and (a.draws() == b.draws()).all()
+
+
 def test_full_trace_and_counts_gateway_network():
     models, conns = networks.gateway_network()
     hs = H.HostSim(models, conns, n=2, seed=3, trace_reps=2, trace_cap=100000)

@@ -13,13 +13,13 @@ def _lower(models_json, connectors_json="[]", **kw):
 
 
 def test_mm1_layout_is_frozen():
-    """DESIGN.md "state layout": M/M/1 = 4 f64 rows + 14 u32 rows = 88 B per replication
-    (92 B with the waiting-time accumulators)."""
+    """DESIGN.md "state layout": M/M/1 = 4 f64 rows + 13 u32 rows = 84 B per replication
+    (96 B with the waiting-time accumulators)."""
     models, conns = networks.mm1()
     lay = H.HostSim(models, conns, n=1, instrument=False).layout()
-    assert (lay["n_drows"], lay["n_wrows"], lay["max_pending"], lay["ring_w_slots"]) == (4, 12, 2, 14)
+    assert (lay["n_drows"], lay["n_wrows"], lay["max_pending"], lay["ring_w_slots"]) == (4, 13, 2, 14)
     lay = H.HostSim(models, conns, n=1, instrument=False, stat_model_id="processor-01").layout()
-    assert (lay["n_drows"], lay["n_wrows"], lay["ring_d_slots"]) == (5, 13, 14)
+    assert (lay["n_drows"], lay["n_wrows"], lay["ring_d_slots"]) == (5, 14, 14)
 
 
 def test_field_order_is_irrelevant_and_unknown_fields_are_ignored():
