@@ -164,13 +164,38 @@ static inline U64Pair philox_pair_cold(uint32_t key0, uint32_t key1, uint32_t ct
     return r;
 }
 
-template <int RNG>
+// Literal-index repetition: X(0) X(1) ... (a `#pragma unroll` over the model loop is silently ignored
+// once the handlers are inlined into it, and only literal indices let the compiler fold the reads of a
+// baked network shape).
+#define SIMB_REP4(X) X(0) X(1) X(2) X(3)
+#define SIMB_REP8(X) SIMB_REP4(X) X(4) X(5) X(6) X(7)
+#define SIMB_REP16(X) SIMB_REP8(X) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15)
+#define SIMB_REP32(X) SIMB_REP16(X) X(16) X(17) X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26) X(27) X(28) X(29) X(30) X(31)
+// run X(m) for every literal m below the tier SM (4, 8, 16 or 32)
+#define SIMB_FOR_MODELS(SM, X)                          \
+    do {                                                \
+        if (SM <= 4) { SIMB_REP4(X) }                   \
+        else if (SM <= 8) { SIMB_REP8(X) }              \
+        else if (SM <= 16) { SIMB_REP16(X) }            \
+        else { SIMB_REP32(X) }                          \
+    } while (0)
+
+// RNG: 0 Philox, 1 Pcg64Mcg, 2 external stream.
+// SM > 0: `net` refers to a compile-time-constant descriptor (a baked network shape, shapes.inc) of at
+// most SM models: the model loops are expanded with literal indices so every structural read (types,
+// rows, routes) folds to an immediate and the handlers of absent model types disappear; the
+// distribution parameters still come from the launch's descriptor `par`.  SM == 0: generic interpreter.
+template <int RNG, int SM = 0>
 struct Engine {
-    const SimbNetDesc& net;
+    static constexpr bool STATIC = SM > 0;
+    const SimbNetDesc& net;  // structure
+    const SimbNetDesc& par;  // values: p0..p2, q0..q2, dist_err, wcum
     const SimbDevState& st;
     Tables tab;
 
-    SIMB_HD Engine(const SimbNetDesc& n, const SimbDevState& s, const Tables& t) : net(n), st(s), tab(t) {}
+    SIMB_HD Engine(const SimbNetDesc& n, const SimbDevState& s, const Tables& t) : net(n), par(n), st(s), tab(t) {}
+    SIMB_HD Engine(const SimbNetDesc& structure, const SimbNetDesc& values, const SimbDevState& s, const Tables& t)
+        : net(structure), par(values), st(s), tab(t) {}
 
     // Append the next Philox block to the per-lane draw cache (call only with ccount <= 2).  Draw
     // number i is word pair (i & 1) of block i >> 1, so the cache is a pure prefetch of the stream.
@@ -273,20 +298,20 @@ struct Engine {
         }
     }
     // Continuous::random_variate (random_variable.rs:69-89); parameter errors surface per draw
-    SIMB_HD double sample_continuous(Lane& ln, const SimbModelDesc& md) {
-        if (md.dist_err) {
-            if (!ln.err) ln.err = md.dist_err;
+    SIMB_HD double sample_continuous(Lane& ln, const SimbModelDesc& md, const SimbModelDesc& pd) {
+        if (pd.dist_err) {
+            if (!ln.err) ln.err = pd.dist_err;
             return 0.0;
         }
         switch (md.dist_kind) {
             case DK_EXP:
-                return sample_exp1(ln) * md.p0;  // Exp1 * lambda_inverse
+                return sample_exp1(ln) * pd.p0;  // Exp1 * lambda_inverse
             case DK_NORMAL: {
                 double n = sample_standard_normal(ln);
-                return md.p0 + md.p1 * n;
+                return pd.p0 + pd.p1 * n;
             }
             case DK_TRIANGULAR: {
-                double mn = md.p0, mx = md.p1, mode = md.p2;
+                double mn = pd.p0, mx = pd.p1, mode = pd.p2;
                 double f = standard_f64(ln);
                 double diff_mode_min = mode - mn;
                 double range = mx - mn;
@@ -297,7 +322,7 @@ struct Engine {
             default: {  // DK_UNIFORM: p0 = low, p1 = scale
                 double value1_2 = bits_f64((next_u64(ln) >> 12) | 0x3FF0000000000000ull);
                 double value0_1 = value1_2 - 1.0;
-                return value0_1 * md.p1 + md.p0;
+                return value0_1 * pd.p1 + pd.p0;
             }
         }
     }
@@ -311,25 +336,25 @@ struct Engine {
         }
     }
     // Index::random_variate (random_variable.rs:122-130)
-    SIMB_HD uint32_t sample_index(Lane& ln, const SimbModelDesc& md) {
-        if (md.dist_err) {
-            if (!ln.err) ln.err = md.dist_err;
+    SIMB_HD uint32_t sample_index(Lane& ln, const SimbModelDesc& md, const SimbModelDesc& pd) {
+        if (pd.dist_err) {
+            if (!ln.err) ln.err = pd.dist_err;
             return 0;
         }
-        uint64_t c = sample_uniform_int(ln, md.q0, md.q1, md.q2);
+        uint64_t c = sample_uniform_int(ln, pd.q0, pd.q1, pd.q2);
         if (!(md.flags & MF_INDEX_WEIGHTED)) return (uint32_t)(c > 0xFFFFFFFFull ? 0xFFFFFFFFull : c);
         uint32_t idx = 0;  // first cumulative weight strictly greater than the chosen weight
-        while (idx < md.n_w && net.wcum[md.wtab + idx] <= c) idx++;
+        while (idx < md.n_w && par.wcum[md.wtab + idx] <= c) idx++;
         return idx;
     }
     // Boolean::random_variate (random_variable.rs:96-101)
-    SIMB_HD bool sample_bernoulli(Lane& ln, const SimbModelDesc& md) {
-        if (md.dist_err) {
-            if (!ln.err) ln.err = md.dist_err;
+    SIMB_HD bool sample_bernoulli(Lane& ln, const SimbModelDesc& md, const SimbModelDesc& pd) {
+        if (pd.dist_err) {
+            if (!ln.err) ln.err = pd.dist_err;
             return false;
         }
         if (md.flags & MF_BERNOULLI_ALWAYS) return true;  // p == 1.0 consumes no draw
-        return next_u64(ln) < md.q0;
+        return next_u64(ln) < pd.q0;
     }
 
     // ---- deferred continuous draws ------------------------------------------------------------------
@@ -340,8 +365,10 @@ struct Engine {
     // internal phase in model order, then this external phase in model order) and any draw that must
     // happen inline (Bernoulli at arrival, gateway index) first pays the debts that precede it.
     SIMB_HD bool defer_draw(Lane& ln, uint32_t m, const SimbModelDesc& md, bool ext_phase) {
-        if (md.dist_err) {  // parameter errors surface at draw time (random_variable.rs:72-87)
-            if (!ln.err) ln.err = md.dist_err;
+        (void)md;
+        const uint32_t de = par.models[m].dist_err;
+        if (de) {  // parameter errors surface at draw time (random_variable.rs:72-87)
+            if (!ln.err) ln.err = de;
             return false;
         }
         if (ext_phase) ln.dm_ext |= 1u << m;
@@ -349,6 +376,24 @@ struct Engine {
         return true;
     }
     SIMB_HD void flush_draws(Lane& ln) {
+        if (STATIC) {
+            // literal model list: one (foldable) sampling site per model that can draw
+#define SIMB_FLUSH_INT(m)                                                                            \
+    if ((m) < net.n_models && net.models[m].dist_kind != DK_NONE && (ln.dm_int & (1u << (m)))) {     \
+        ln.dm_int &= ~(1u << (m));                                                                   \
+        ln.D(net.drow_until + (m)) = sample_continuous(ln, net.models[m], par.models[m]);            \
+    }
+#define SIMB_FLUSH_EXT(m)                                                                            \
+    if ((m) < net.n_models && net.models[m].dist_kind != DK_NONE && (ln.dm_ext & (1u << (m)))) {     \
+        ln.dm_ext &= ~(1u << (m));                                                                   \
+        ln.D(net.drow_until + (m)) = sample_continuous(ln, net.models[m], par.models[m]);            \
+    }
+            if (ln.dm_int) SIMB_FOR_MODELS(SM, SIMB_FLUSH_INT);
+            if (ln.dm_ext) SIMB_FOR_MODELS(SM, SIMB_FLUSH_EXT);
+#undef SIMB_FLUSH_INT
+#undef SIMB_FLUSH_EXT
+            return;
+        }
         while (ln.dm_int | ln.dm_ext) {
             uint32_t m;
             if (ln.dm_int) {
@@ -358,7 +403,7 @@ struct Engine {
                 m = (uint32_t)lowest_bit(ln.dm_ext);
                 ln.dm_ext &= ln.dm_ext - 1u;
             }
-            const double dv = sample_continuous(ln, net.models[m]);
+            const double dv = sample_continuous(ln, net.models[m], par.models[m]);
             ln.D(net.drow_until + m) = dv;
         }
     }
@@ -632,7 +677,7 @@ struct Engine {
                 if (port != 0) { ln.err = 7; break; }
                 ln.D(urow) = 0.0;
                 if (ln.dm_int | ln.dm_ext) flush_draws(ln);  // earlier draws of the stream come first
-                bool pass = sample_bernoulli(ln, md);  // Bernoulli draw AT ARRIVAL
+                bool pass = sample_bernoulli(ln, md, par.models[m]);  // Bernoulli draw AT ARRIVAL
                 if (ln.err) break;
                 uint32_t slot;
                 if (!ring_push(ln, md, content, &slot)) break;
@@ -705,7 +750,7 @@ struct Engine {
                 if (room) {
                     if (ph == 0) {  // start_batch :103-112
                         ln.set_phase(m, 1);
-                        ln.D(urow) = md.p0;
+                        ln.D(urow) = par.models[m].p0;
                     }  // add_to_batch :93-101 leaves the timer alone
                 } else {  // fill_batch :114-123
                     ln.set_phase(m, 2);
@@ -821,7 +866,7 @@ struct Engine {
                 if (ln.phase(m) == 1) {  // send_jobs :110-134: one draw per firing
                     ln.set_phase(m, 0);
                     if (ln.dm_int | ln.dm_ext) flush_draws(ln);  // earlier draws of the stream come first
-                    uint32_t idx = sample_index(ln, md);
+                    uint32_t idx = sample_index(ln, md, par.models[m]);
                     if (ln.err) break;
                     if (idx >= md.n_out) { ln.err = 34; break; }  // flow_paths[idx] out of bounds panics
                     release_n<INSTR>(ln, m, md, ln.W(md.wrow) & 0xFFFFu, idx, idx + 1u);
@@ -890,7 +935,7 @@ struct Engine {
                     release_n<INSTR>(ln, m, md, md.cap, 0, 0);
                 } else {  // release_partial_queue :143-159
                     ln.set_phase(m, 1);
-                    ln.D(urow) = md.p0;
+                    ln.D(urow) = par.models[m].p0;
                     release_n<INSTR>(ln, m, md, md.cap, 0, 0);
                 }
                 break;
@@ -905,6 +950,17 @@ struct Engine {
     // the others only take part in the warp-level votes.
     // ================================================================================================
     template <bool INSTR>
+    SIMB_HD void ext_model(Lane& ln, uint32_t m, uint32_t np, uint32_t& nev) {
+        const SimbModelDesc& md = net.models[m];
+        for (uint32_t j = 0; j < np && !ln.err; j++) {
+            const uint32_t rw = ln.W(net.wrow_pend + 2 * j + 1);
+            if (ROUTE_TGT(rw) != m) continue;
+            nev++;
+            events_ext<INSTR>(ln, m, md, ROUTE_PORT(rw), ln.W(net.wrow_pend + 2 * j));
+        }
+    }
+
+    template <bool INSTR>
     SIMB_HD void step(Lane& ln, bool live) {
         const uint32_t M = net.n_models;
         const bool had = live && ln.npend > 0;
@@ -914,17 +970,18 @@ struct Engine {
             const uint32_t tmask = had ? ln.tmask : 0u;  // a target id matching no model has no bit: dropped
             const uint32_t np = had ? ln.npend : 0u;
             uint32_t wm = warp_or(tmask);
-            while (wm) {
-                const int m = lowest_bit(wm);
-                wm &= wm - 1u;
-                if (((tmask >> m) & 1u) && !ln.err) {
-                    const SimbModelDesc& md = net.models[m];
-                    for (uint32_t j = 0; j < np && !ln.err; j++) {
-                        uint32_t rw = ln.W(net.wrow_pend + 2 * j + 1);
-                        if (ROUTE_TGT(rw) != (uint32_t)m) continue;
-                        nev++;
-                        events_ext<INSTR>(ln, (uint32_t)m, md, ROUTE_PORT(rw), ln.W(net.wrow_pend + 2 * j));
-                    }
+            if (STATIC) {
+#define SIMB_EXT_ONE(m)                                                                \
+    if ((m) < M && ((wm >> (m)) & 1u)) { /* warp-uniform */                            \
+        if (((tmask >> (m)) & 1u) && !ln.err) ext_model<INSTR>(ln, (m), np, nev);      \
+    }
+                SIMB_FOR_MODELS(SM, SIMB_EXT_ONE);
+#undef SIMB_EXT_ONE
+            } else {
+                while (wm) {
+                    const uint32_t m = (uint32_t)lowest_bit(wm);
+                    wm &= wm - 1u;
+                    if (((tmask >> m) & 1u) && !ln.err) ext_model<INSTR>(ln, m, np, nev);
                 }
             }
         }
@@ -937,32 +994,68 @@ struct Engine {
         const bool go = live && !ln.err;
         // ---- time advance (:225-236) ----
         double dt = 0.0;
-        if (go && !had) {
-            dt = SIMB_INF;
-            for (uint32_t m = 0; m < M; m++) dt = fmin(dt, ln.D(net.drow_until + m));
-        }
         uint32_t zmask = 0;
-        if (go) {
-            for (uint32_t m = 0; m < M; m++) {
-                double u = ln.D(net.drow_until + m);
-                if (!had && net.models[m].type != MT_PASSIVE) {
-                    u = u - dt;
-                    ln.D(net.drow_until + m) = u;
-                }
-                if (u == 0.0) zmask |= 1u << m;
+        if (STATIC) {
+            if (go && !had) {
+                dt = SIMB_INF;
+#define SIMB_MIN_ONE(m) if ((m) < M) dt = fmin(dt, ln.D(net.drow_until + (m)));
+                SIMB_FOR_MODELS(SM, SIMB_MIN_ONE);
+#undef SIMB_MIN_ONE
             }
+            if (go) {
+#define SIMB_ADV_ONE(m)                                          \
+    if ((m) < M) {                                               \
+        double u = ln.D(net.drow_until + (m));                   \
+        if (!had && net.models[m].type != MT_PASSIVE) {          \
+            u = u - dt;                                          \
+            ln.D(net.drow_until + (m)) = u;                      \
+        }                                                        \
+        if (u == 0.0) zmask |= 1u << (m);                        \
+    }
+                SIMB_FOR_MODELS(SM, SIMB_ADV_ONE);
+#undef SIMB_ADV_ONE
+            }
+        } else {
+            if (go && !had) {
+                dt = SIMB_INF;
+                for (uint32_t m = 0; m < M; m++) dt = fmin(dt, ln.D(net.drow_until + m));
+            }
+            if (go) {
+                for (uint32_t m = 0; m < M; m++) {
+                    double u = ln.D(net.drow_until + m);
+                    if (!had && net.models[m].type != MT_PASSIVE) {
+                        u = u - dt;
+                        ln.D(net.drow_until + m) = u;
+                    }
+                    if (u == 0.0) zmask |= 1u << m;
+                }
+            }
+        }
+        if (go) {
             ln.time = ln.time + dt;
             ln.npend = 0;  // the mailbox is consumed; events_int refills it from slot 0
             ln.tmask = 0;
         }
         // ---- internal events in model order (:237-268) ----
         uint32_t wm = warp_or(zmask);
-        while (wm) {
-            const int m = lowest_bit(wm);
-            wm &= wm - 1u;
-            if (((zmask >> m) & 1u) && !ln.err) {
-                nev++;
-                events_int<INSTR>(ln, (uint32_t)m, net.models[m]);
+        if (STATIC) {
+#define SIMB_INT_ONE(m)                                                                 \
+    if ((m) < M && net.models[m].type != MT_PASSIVE && ((wm >> (m)) & 1u)) {            \
+        if (((zmask >> (m)) & 1u) && !ln.err) {                                         \
+            nev++;                                                                      \
+            events_int<INSTR>(ln, (m), net.models[m]);                                  \
+        }                                                                               \
+    }
+            SIMB_FOR_MODELS(SM, SIMB_INT_ONE);
+#undef SIMB_INT_ONE
+        } else {
+            while (wm) {
+                const uint32_t m = (uint32_t)lowest_bit(wm);
+                wm &= wm - 1u;
+                if (((zmask >> m) & 1u) && !ln.err) {
+                    nev++;
+                    events_int<INSTR>(ln, m, net.models[m]);
+                }
             }
         }
         if (go) {

@@ -11,7 +11,10 @@ struct EngineDims {
     uint32_t tile;        // replications per CTA (= threads per CTA)
     uint32_t smem_bytes;  // dynamic shared memory per CTA
     uint32_t grid;        // CTAs per launch
+    int shape;            // baked shape id whose specialised kernel is used, or -1 (generic interpreter)
 };
+int engine_match_shape(const SimbNetDesc& net, int rng_kind, bool instrument);
+const char* engine_shape_name(int shape);
 
 // chooses the tile width for a layout and sets the kernel attributes; returns cudaError_t
 int engine_configure(const SimbNetDesc& net, uint64_t stride_hint, int rng_kind, bool instrument, EngineDims* dims);

@@ -10,7 +10,7 @@
 namespace simb {
 
 struct LowerOptions {
-    uint32_t queue_capacity = 64;
+    uint32_t queue_capacity = 0;  // 0 = defaults (64 for unbounded Processor queues, 16 for transient queues)
     uint32_t max_pending = 0;
     bool instrument = false;
     int rng_kind = 0;

@@ -12,6 +12,7 @@
 
 #define SIMB_TABLE_QUAL const
 #include "../../sim_b200/csrc/zig_tables.inc"
+#include "../../sim_b200/csrc/shapes.inc"
 
 using namespace simb;
 
@@ -29,12 +30,15 @@ struct HS {
     std::vector<uint64_t> ext;
     uint32_t epoch = 0;
     uint64_t settle_every = 0;
+    int shape = -1;
 };
 
-template <int RNG, bool INSTR>
+template <int RNG, bool INSTR, int SM>
 void run(HS* h, int mode, uint64_t k, double until) {
     Tables tab{ZIG_EXP_X, ZIG_EXP_F, ZIG_NORM_X, ZIG_NORM_F};
-    Engine<RNG> eng(h->hn.desc, h->st, tab);
+    // SM > 0: the literal-index ("baked shape") code path of the interpreter, structure from the host
+    // copy of the baked descriptor, values from the lowered network -- as the specialised kernels do
+    Engine<RNG, SM> eng(SM > 0 ? *kShapeHost[h->shape] : h->hn.desc, h->hn.desc, h->st, tab);
     for (uint64_t r = 0; r < h->n; r++) {
         Lane ln;
         ln.d = h->d.data() + r;
@@ -64,9 +68,18 @@ void run(HS* h, int mode, uint64_t k, double until) {
 }
 void dispatch(HS* h, int mode, uint64_t k, double until) {
     h->epoch = (h->epoch % 255) + 1;
-#define RUN(R)                                         \
-    if (h->instr) run<R, true>(h, mode, k, until);     \
-    else run<R, false>(h, mode, k, until);
+#define RUN(R)                                            \
+    if (h->instr) run<R, true, 0>(h, mode, k, until);     \
+    else run<R, false, 0>(h, mode, k, until);
+    if (h->shape >= 0 && h->rng_kind == 0 && !h->instr) {
+        static const int tiers[] = SIMB_SHAPE_TIERS;
+        switch (tiers[h->shape]) {
+            case 4: run<0, false, 4>(h, mode, k, until); return;
+            case 8: run<0, false, 8>(h, mode, k, until); return;
+            case 16: run<0, false, 16>(h, mode, k, until); return;
+            default: run<0, false, 32>(h, mode, k, until); return;
+        }
+    }
     if (h->rng_kind == 0) { RUN(0) }
     else if (h->rng_kind == 1) { RUN(1) }
     else { RUN(2) }
@@ -148,6 +161,28 @@ void* hs_new(const char* models, const char* connectors, uint64_t n, uint64_t re
 }
 void hs_free(void* h) { delete (HS*)h; }
 void hs_set_reload_every(void* h, uint64_t n) { ((HS*)h)->settle_every = n; }
+// select the baked-shape code path when the lowered network matches shape `k` structurally; returns 1 on match
+int hs_use_shape(void* hv, int k) {
+    HS* h = (HS*)hv;
+    if (k < 0 || k >= SIMB_N_SHAPES) return 0;
+    auto strip = [](SimbNetDesc* d) {
+        for (int i = 0; i < SIMB_MAX_MODELS; i++) {
+            SimbModelDesc& m = d->models[i];
+            m.p0 = m.p1 = m.p2 = 0.0;
+            m.q0 = m.q1 = m.q2 = 0;
+            m.dist_err = 0;
+        }
+        std::memset(d->wcum, 0, sizeof d->wcum);
+    };
+    SimbNetDesc a, b;
+    std::memcpy(&a, &h->hn.desc, sizeof a);
+    std::memcpy(&b, kShapeHost[k], sizeof b);
+    strip(&a);
+    strip(&b);
+    if (std::memcmp(&a, &b, sizeof a) != 0) return 0;
+    h->shape = k;
+    return 1;
+}
 void hs_set_stream(void* hv, const uint64_t* draws, uint64_t per_rep) {
     HS* h = (HS*)hv;
     h->ext.assign(draws, draws + per_rep * h->n);

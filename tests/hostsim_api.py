@@ -26,7 +26,7 @@ def to_json(models, connectors):
 
 class HostSim:
     def __init__(self, models, connectors, n=1, rep_offset=0, seed=42, rng_kind=0, instrument=True, stat_model_id=None,
-                 queue_capacity=64, max_pending=0, trace_reps=0, trace_cap=0, raw_json=None):
+                 queue_capacity=0, max_pending=0, trace_reps=0, trace_cap=0, raw_json=None):
         self.L = lib()
         mj, cj = raw_json if raw_json else to_json(models, connectors)
         err = C.create_string_buffer(512)
@@ -53,6 +53,10 @@ class HostSim:
     def set_reload_every(self, n):
         """store + reload the lane state every n steps, like consecutive kernel launches of K = n"""
         self.L.hs_set_reload_every(self.h, C.c_uint64(n))
+
+    def use_shape(self, k):
+        """run through the literal-index (baked shape) code path; False if the network does not match shape k"""
+        return bool(self.L.hs_use_shape(self.h, k))
 
     def set_stream(self, draws):  # draws[i, r]
         a = np.ascontiguousarray(draws, dtype=np.uint64)

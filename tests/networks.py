@@ -296,7 +296,7 @@ def gateway_network():
 def large_mixed():
     """config 5 (32 models): two gateway sub-networks and the tandem share one generator through a split."""
     models, connectors = [], []
-    models.append(Model.new("source", Generator.new(Exp(3.0), None, "job", False, None)))
+    models.append(Model.new("source", Generator.new(Exp(2.0), None, "job", False, None)))
     models.append(Model.new("fanout", ParallelGateway.new(["in"], ["g1", "g2", "t"], False)))
     connectors.append(Connector.new("s0", "source", "fanout", "job", "in"))
 

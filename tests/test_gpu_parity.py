@@ -212,3 +212,51 @@ def test_status_strings():
     sim = _sim(models, conns, 2)
     assert sim.get_status("generator-01") == "Generating jobs"
     assert sim.get_status("load-balancer-01") == "Listening for requests"
+
+
+@pytest.mark.parametrize("name,stat,shape", [("mm1", "processor-01", "mm1"), ("tandem", None, "generic"),
+                                             ("gateway_network", None, "generic"), ("large_mixed", None, "generic")])
+@pytest.mark.parametrize("k", [1, 16])
+def test_production_kernels_match_oracle(name, stat, shape, k):
+    """The production configuration (Philox, not instrumented): M/M/1 runs on the step kernel
+    specialised for its baked shape (sim_b200/csrc/shapes.inc), the other BASELINE networks on the
+    generic interpreter.  Both must agree with the oracle in everything observable without
+    instrumentation: steps, events, draws, clocks, every model's until_next_event, the waiting-time
+    accumulators -- and with the instrumented kernel's trace hash taken on the same replications."""
+    models, conns = networks.ALL[name]()
+    n, until = 300, 150.0
+    sim = _sim(models, conns, n, seed=5, instrument=False, stat_model_id=stat, steps_per_launch=k)
+    assert sim.describe()["kernel_shape"] == shape
+    sim.step_until(until)
+    ref_models = networks.mm1(store_records=True)[0] if name == "mm1" else models
+    ref = oracle_api.OracleSimulation(ref_models, conns).run_batch(5, 0, n, threads=8, until=until, stat_model_id=stat)
+    assert ref["err"] == 0 and (sim.get_errors() == 0).all()
+    assert (sim.get_steps() == ref["steps"]).all()
+    assert (sim.get_events() == ref["events"]).all()
+    assert _close(sim.get_global_time(), ref["time"])
+    if stat:
+        s, cnt = sim.get_wait_stats()
+        assert (cnt == ref["wait_n"]).all() and _close(s, ref["wait_sum"])
+    gen = _sim(models, conns, n, seed=5, instrument=True, stat_model_id=stat, steps_per_launch=k)
+    assert gen.describe()["kernel_shape"] == "generic"
+    gen.step_until(until)
+    assert (gen.get_trace_hash() == ref["hash"]).all()
+    assert (gen.get_draws() == sim.get_draws()).all()
+    for m in models:
+        assert _close(gen.get_until_next_event(m.id), sim.get_until_next_event(m.id)), m.id
+    # a second call continues both the same way
+    sim.step_n(77)
+    gen.step_n(77)
+    assert (gen.get_steps() == sim.get_steps()).all() and _close(gen.get_global_time(), sim.get_global_time())
+
+
+def test_shape_match_ignores_distribution_values():
+    """A baked shape is the network STRUCTURE; rates are launch parameters."""
+    models, conns = networks.mm1(lam_gen=0.7, lam_proc=1.1)
+    sim = _sim(models, conns, 64, seed=2, instrument=False, stat_model_id="processor-01")
+    assert sim.describe()["kernel_shape"] == "mm1"
+    sim.step_n(500)
+    ref = oracle_api.OracleSimulation(models, conns).run_batch(2, 0, 64, threads=4, nsteps=500)
+    assert (sim.get_events() == ref["events"]).all() and _close(sim.get_global_time(), ref["time"])
+    other, conns2 = networks.mm1(capacity=9)
+    assert _sim(other, conns2, 8, instrument=False, stat_model_id="processor-01").describe()["kernel_shape"] == "generic"

@@ -179,3 +179,51 @@ def test_all_passive_network():
     hs = H.HostSim(models, conns, n=1)
     hs.step_n(1)
     assert hs.time()[0] == float("inf") and np.isnan(hs.until(0)[0])
+
+
+BAKED = [("mm1", "processor-01")]  # tools/gen_shapes.py BASELINE
+
+
+@pytest.mark.parametrize("shape,name,stat", [(i, n, s) for i, (n, s) in enumerate(BAKED)])
+def test_baked_shape_code_path_equals_generic_and_oracle(shape, name, stat):
+    """The literal-index ("baked shape") expansion of the interpreter -- what the specialised CUDA
+    kernels compile -- must behave exactly like the generic interpreter and the oracle."""
+    models, conns = networks.ALL[name]()
+    a = H.HostSim(models, conns, n=12, seed=5, instrument=False, stat_model_id=stat)
+    b = H.HostSim(models, conns, n=12, seed=5, instrument=False, stat_model_id=stat)
+    assert b.use_shape(shape)
+    assert not b.use_shape(shape + 7)  # no such baked shape
+    assert b.use_shape(shape)
+    b.set_reload_every(3)
+    a.step_until(200.0)
+    b.step_until(200.0)
+    assert (a.steps() == b.steps()).all() and (a.events() == b.events()).all() and (a.draws() == b.draws()).all()
+    assert (a.time() == b.time()).all() and (b.errors() == 0).all()
+    for m in range(len(models)):
+        assert np.array_equal(a.until(m), b.until(m), equal_nan=True)
+    for r in (0, 11):
+        e, o = _oracle(models, conns, 5, r, until=200.0)
+        c = o.counters()
+        assert (c["steps"], c["events"], o.rng_draws(), o.get_global_time()) == \
+               (int(b.steps()[r]), int(b.events()[r]), int(b.draws()[r]), b.time()[r])
+
+
+def test_shape_match_is_structural():
+    models, conns = networks.mm1(lam_gen=0.9, lam_proc=2.0)       # other rates: same shape
+    assert H.HostSim(models, conns, n=1, instrument=False, stat_model_id="processor-01").use_shape(0)
+    models, conns = networks.mm1(capacity=9)                       # other capacity: another structure
+    assert not H.HostSim(models, conns, n=1, instrument=False, stat_model_id="processor-01").use_shape(0)
+    models, conns = networks.mm1()
+    assert not H.HostSim(models, conns, n=1, instrument=False).use_shape(0)  # no statistic rows: another layout
+
+
+def test_baked_shapes_are_up_to_date():
+    """sim_b200/csrc/shapes.inc must be what tools/gen_shapes.py produces from sim_b200/shapes/*.json."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "sim_b200", "csrc", "shapes.inc")
+    before = open(path).read()
+    subprocess.check_call([sys.executable, os.path.join(root, "tools", "gen_shapes.py")], stdout=subprocess.DEVNULL)
+    assert open(path).read() == before
