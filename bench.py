@@ -45,6 +45,7 @@ def parse():
     p.add_argument("--cpu-replications", type=int, default=0, help="replications of the CPU baseline sample (0 = auto)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-k1", action="store_true", help="skip the one-step-per-launch (HBM streaming) section")
     return p.parse_args()
 
 
@@ -135,8 +136,8 @@ def run_reference(args):
     import __graft_entry__ as ge
     ge._run(["make", "-s"], os.path.join(ROOT, "oracle"))
     cores = os.cpu_count() or 1
-    nreps = args.cpu_replications or max(cores * 8, 64)
-    for _ in range(args.warmup):
+    nreps = args.cpu_replications or cores * 512  # ~2 s of CPU work per step at ~5e6 events/s per core
+    for _ in range(min(args.warmup, 1)):
         cpu_sample(args, cores, max(cores, 8))
     tot_ev, tot_dt = 0, 0.0
     for _ in range(args.steps):
@@ -243,19 +244,54 @@ def main():
 
     # roofline of the dominant kernel (simb_step_kernel): algorithmic bytes per launch / mean launch time
     peak, peak_src = peaks()
+    ncu = {}
+    ncu_path = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(ncu_path):
+        with open(ncu_path) as f:
+            ncu = json.load(f)
+
+    def roofline_of(desc_, ctr_, rsteps_local, wall_s, tag):
+        state_b = desc_["state_bytes_per_replication"]
+        launches_ = max(1, ctr_["launches"])
+        # ring touches per replication-step for this network: ~0.4 slots of 4 B (+8 B arrival time)
+        ring_b = 0.4 * (4 + (8 if stat else 0)) if desc_["ring_u32_slots"] else 0.0
+        alg = desc_["stride"] * (2.0 * state_b) + (rsteps_local / launches_) * ring_b
+        launch_ms_ = ctr_["kernel_ms"] / launches_
+        ach = alg / (launch_ms_ * 1e-3) / 1e9 if launch_ms_ > 0 else 0.0
+        cap = ncu.get(tag, {})
+        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": cap.get("dram_bytes_per_launch"), "kernel": "simb_step_kernel<%s>" % desc_["kernel_shape"],
+                "launches": ctr_["launches"], "launch_ms": launch_ms_, "algorithmic_bytes_per_launch": alg,
+                "steps_per_launch": desc_["steps_per_launch"], "state_bytes_per_replication": state_b,
+                "peak_source": peak_src, "kernel_share_of_step": ctr_["kernel_ms"] * 1e-3 / wall_s if wall_s > 0 else None,
+                "ncu": cap or None}
+
     k_eff = desc["steps_per_launch"]
-    state_b = desc["state_bytes_per_replication"]
     launches = ctr["launches"]
-    # ring touches per replication-step for this network: ~0.4 slots of 4 B (+8 B arrival time)
-    ring_b = 0.4 * (4 + (8 if stat else 0)) if desc["ring_u32_slots"] else 0.0
-    alg_bytes_per_launch = desc["stride"] * (2.0 * state_b) + (rsteps_total / world / max(1, launches)) * ring_b
-    launch_ms = ctr["kernel_ms"] / max(1, launches)
-    achieved = alg_bytes_per_launch / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "simb_step_kernel", "launches": launches, "launch_ms": launch_ms,
-                "algorithmic_bytes_per_launch": alg_bytes_per_launch, "steps_per_launch": k_eff,
-                "state_bytes_per_replication": state_b, "peak_source": peak_src,
-                "kernel_share_of_step": ctr["kernel_ms"] * 1e-3 / dt if dt > 0 else None}
+    roofline = roofline_of(desc, ctr, rsteps_total / world, dt, "fused")
+    roofline["note"] = ("fused steps: the state is loaded once per %d steps, so the kernel sits far below the HBM roof "
+                        "and is bound by instruction issue (ncu issue-active in roofline.ncu); the HBM-streaming "
+                        "formulation (one step per launch, Simulation::step granularity) is reported in hbm_streaming_k1" % k_eff)
+
+    # the same workload with ONE step per launch (API-faithful Simulation::step granularity): every launch
+    # streams the whole state through HBM; bounded to a quarter of the horizon to keep the run short
+    k1 = None
+    if rank == 0 and world == 1 and not args.no_k1:
+        s1 = Simulation.post_json(mj, cj, n, seed=42, device=local_rank, steps_per_launch=1, stat_model_id=stat)
+        s1.step_until(args.until / 16.0)
+        s1.reset_counters()
+        c0 = s1.get_counters()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        s1.step_until(args.until / 4.0)
+        torch.cuda.synchronize()
+        w1 = time.perf_counter() - t1
+        c1 = s1.get_counters()
+        r1 = roofline_of(s1.describe(), c1, c1["steps"] - c0["steps"], w1, "k1")
+        k1 = {"value": (c1["events"] - c0["events"]) / w1, "unit": UNIT,
+              "replication_steps_per_s": (c1["steps"] - c0["steps"]) / w1, "roofline": r1,
+              "sample": "step_until(%g) -> step_until(%g), steps_per_launch=1" % (args.until / 16.0, args.until / 4.0)}
+        s1.close()
 
     # end to end through the public API with host buffers: post (JSON in), run, waits read back to the host
     e2e = None
@@ -287,7 +323,7 @@ def main():
         import __graft_entry__ as ge
         ge._run(["make", "-s"], os.path.join(ROOT, "oracle"))
         cores = os.cpu_count() or 1
-        nreps = args.cpu_replications or max(cores * 16, 64)
+        nreps = args.cpu_replications or cores * 2560  # ~10 s of CPU work at ~5e6 events/s per core
         ev, cdt, _ = cpu_sample(args, cores, nreps)
         cpu = {"value": ev / cdt, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d replications x step_until(%g), one replication per thread, %d threads, %.1f s" % (nreps, args.until, cores, cdt)}
@@ -301,11 +337,14 @@ def main():
                        if args.network == "mm1" else args.network,
                        "replications_per_gpu": n, "until": args.until, "steps_per_launch": k_eff,
                        "rng": "philox4x32-10 per replication", "tile": desc["tile"],
-                       "l2": "state tile %.0f MB + rings per GPU vs 126 MB L2; see roofline.traffic / DESIGN.md" % (desc["stride"] * state_b / 1e6),
+                       "l2": "state %.0f MB + rings %.0f MB per GPU vs 126 MB L2 (inputs larger than L2; no flush)" % (
+                           desc["stride"] * desc["state_bytes_per_replication"] / 1e6,
+                           desc["stride"] * (desc["ring_u32_slots"] * 4 + desc["ring_f64_slots"] * 8) / 1e6),
                        "parallelism": "replications sharded, %d per GPU" % n},
             "replication_steps_per_s": rsteps_total / dt_max,
             "gpu_launches": int(launches * world + 2 * args.steps * world),
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "statistic": ci,
+            "clocks": clocks, "roofline": roofline, "hbm_streaming_k1": k1, "cpu_baseline": cpu, "e2e": e2e,
+            "statistic": ci,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -231,29 +231,52 @@ const char* engine_shape_name(int shape) { return (shape >= 0 && shape < SIMB_N_
 
 int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool instrument, EngineDims* dims) {
     dims->shape = engine_match_shape(net, rng_kind, instrument);
-    // widest tile that leaves room for at least two CTAs per SM (227 KB usable shared memory)
+    // widest tile that leaves room for SIMB_MIN_BLOCKS CTAs per SM (227 KB usable shared memory) with
+    // half of the SM's unified storage left to L1 (the ring slots live there between steps)
+    const uint32_t budget = (114u * 1024u) / SIMB_MIN_BLOCKS;
     uint32_t tile = 256;
-    while (tile > 32 && smem_plan(net, tile).total > 100u * 1024u) tile >>= 1;
+    while (tile > 32 && smem_plan(net, tile, 1).total > budget) tile >>= 1;
+    const uint32_t stages = 1;
     if (n && n < tile) {
         uint32_t t = 32;
         while (t < n) t <<= 1;
         if (t < tile) tile = t;
     }
-    SmemPlan sp = smem_plan(net, tile);
+    SmemPlan sp = smem_plan(net, tile, stages);
     if (sp.total > 227u * 1024u) return (int)cudaErrorInvalidConfiguration;
     dims->tile = tile;
+    dims->stages = stages;
     dims->smem_bytes = sp.total;
-    dims->grid = 0;
     cudaError_t e = cudaFuncSetAttribute((const void*)pick_kernel(rng_kind, instrument, dims->shape),
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
-    return (int)e;
+    if (e != cudaSuccess) return (int)e;
+    // One CTA per tile.  Measured (profiles/r01_pipeline_experiments.txt): a persistent grid of
+    // SMs x resident CTAs with static tile assignment is 8 % slower at K = 64 (no dynamic load balance)
+    // and double buffering inside a CTA gains nothing at K = 1, where the 4 co-resident CTAs per SM already
+    // overlap each other's load / compute / store phases; the kernel keeps its grid-stride tile loop.
+    dims->grid = 0xFFFFFFFFu;
+    return (int)cudaSuccess;
 }
 
-int engine_launch_step(const SimbNetDesc& net, const SimbDevState& st, const SimbLaunch& la, const EngineDims& dims,
+int engine_launch_step(const SimbNetDesc& net, const SimbDevState& st, const SimbLaunch& la_in, const EngineDims& dims,
                        int rng_kind, bool instrument, bool count_active, cudaStream_t stream) {
-    const uint32_t grid = (uint32_t)(st.stride / dims.tile);
-    pick_kernel(rng_kind, instrument, dims.shape)<<<grid, dims.tile, dims.smem_bytes, stream>>>(net, st, la, count_active ? 1u : 0u);
-    return (int)cudaGetLastError();
+    const uint32_t n_tiles = (uint32_t)(st.stride / dims.tile);
+    const uint32_t grid = n_tiles < dims.grid ? n_tiles : dims.grid;
+    SimbLaunch la = la_in;
+    la.stages = dims.stages;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(dims.tile);
+    cfg.dynamicSmemBytes = dims.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // pairs with griddepcontrol.* in the kernel
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const uint32_t ca = count_active ? 1u : 0u;
+    return (int)cudaLaunchKernelEx(&cfg, pick_kernel(rng_kind, instrument, dims.shape), net, st, la, ca);
 }
 
 static inline uint32_t blocks_for(uint64_t n, uint32_t t) { return (uint32_t)((n + t - 1) / t); }

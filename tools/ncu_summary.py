@@ -1,0 +1,61 @@
+#!/usr/bin/env python3
+"""Summarise ncu captures into profiles/ncu_summary.json (read by bench.py for roofline.traffic / .ncu).
+
+usage: ncu_summary.py tag=path.ncu-rep [tag=path ...]      (tags used by bench.py: fused, k1)
+For each capture the LAST profiled launch of simb_step_kernel is summarised (steady state)."""
+import csv
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WANT = {
+    "gpu__time_duration.sum": "duration_us",
+    "dram__bytes_read.sum": "dram_read_mb",
+    "dram__bytes_write.sum": "dram_write_mb",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct_of_peak",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
+    "smsp__inst_executed.sum": "warp_instructions",
+    "smsp__thread_inst_executed_per_inst_executed.ratio": "active_threads_per_instruction",
+    "sm__warps_active.avg.pct_of_peak_sustained_active": "achieved_occupancy_pct",
+    "launch__registers_per_thread": "registers_per_thread",
+    "launch__grid_size": "grid",
+    "lts__t_sector_hit_rate.pct": "l2_hit_pct",
+    "l1tex__t_sector_hit_rate.pct": "l1_hit_pct",
+}
+
+
+def summarise(path):
+    out = subprocess.check_output(["ncu", "-i", path, "--page", "raw", "--csv"], text=True, stderr=subprocess.DEVNULL)
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    data = [r for r in rows[2:] if "simb_step_kernel" in r[hdr.index("Kernel Name")]]
+    r = data[-1]
+    res = {"kernel": r[hdr.index("Kernel Name")].split("(")[0], "launches_profiled": len(data), "source": os.path.basename(path)}
+    for k, name in WANT.items():
+        if k in hdr:
+            v = float(r[hdr.index(k)])
+            u = units[hdr.index(k)]
+            if name == "duration_us" and u == "ms":
+                v *= 1e3
+            if name.endswith("_mb") and u == "Gbyte":
+                v *= 1e3
+            res[name] = v
+    res["dram_bytes_per_launch"] = (res.get("dram_read_mb", 0) + res.get("dram_write_mb", 0)) * 1e6
+    return res
+
+
+def main():
+    path = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    summary = json.load(open(path)) if os.path.exists(path) else {}
+    for arg in sys.argv[1:]:
+        tag, rep = arg.split("=", 1)
+        summary[tag] = summarise(rep)
+    with open(path, "w") as f:
+        json.dump(summary, f, indent=1, sort_keys=True)
+    print(json.dumps(summary, indent=1, sort_keys=True))
+
+
+if __name__ == "__main__":
+    main()
