@@ -260,3 +260,112 @@ def test_shape_match_ignores_distribution_values():
     assert (sim.get_events() == ref["events"]).all() and _close(sim.get_global_time(), ref["time"])
     other, conns2 = networks.mm1(capacity=9)
     assert _sim(other, conns2, 8, instrument=False, stat_model_id="processor-01").describe()["kernel_shape"] == "generic"
+
+
+# ---- BASELINE.json full size: 2^20 replications x step_until(10 000) ---------------------------------------
+FULL_N = 1 << 20
+FULL_UNTIL = 10000.0
+
+
+@pytest.fixture(scope="module")
+def full_mm1():
+    models, conns = networks.mm1()
+    sim = _sim(models, conns, FULL_N, seed=42, instrument=False, stat_model_id="processor-01")
+    assert sim.describe()["kernel_shape"] == "mm1"
+    sim.step_until(FULL_UNTIL)
+    return sim
+
+
+def test_full_size_properties(full_mm1):
+    sim = full_mm1
+    t = sim.get_global_time()
+    steps, events, draws = sim.get_steps(), sim.get_events(), sim.get_draws()
+    s, cnt = sim.get_wait_stats()
+    assert (sim.get_errors() == 0).all()
+    assert np.isfinite(t).all() and (t >= FULL_UNTIL).all() and (t < FULL_UNTIL + 60.0).all()
+    # M/M/1 cadence: every step runs at least one event, at most three
+    assert (events >= steps).all() and (events <= 3 * steps.astype(np.uint64)).all()
+    # one draw per generator firing / service start, plus rare ziggurat retries: draws ~ events / 2.4
+    assert (draws > events // 3).all() and (draws < events).all()
+    assert (cnt > 0).all() and np.isfinite(s).all() and (s >= 0).all()
+    # replication-to-replication variability is real (not one replication copied 2^20 times)
+    assert np.unique(steps).size > 200 and np.unique(t).size > FULL_N * 0.999
+    # expected number of arrivals 5000 +- a few hundred; steps ~ 3.33 per arrival
+    assert 15000 < steps.mean() < 18500
+    c = sim.get_counters()
+    assert c["steps"] == int(steps.astype(np.uint64).sum()) and c["events"] == int(events.astype(np.uint64).sum())
+
+
+def test_full_size_sampled_replications_match_oracle(full_mm1):
+    """Replications picked across the whole 2^20 batch, each compared with the oracle over the full horizon."""
+    sim = full_mm1
+    t, steps, events = sim.get_global_time(), sim.get_steps(), sim.get_events()
+    s, cnt = sim.get_wait_stats()
+    rec_models, conns = networks.mm1(store_records=True)
+    o = oracle_api.OracleSimulation(rec_models, conns)
+    for r0 in (0, 255, 256, 65535, 300001, 524288, 777777, FULL_N - 4):
+        ref = o.run_batch(42, r0, 4, threads=4, until=FULL_UNTIL, stat_model_id="processor-01", trace_hash=False)
+        sl = slice(r0, r0 + 4)
+        assert (steps[sl] == ref["steps"]).all() and (events[sl] == ref["events"]).all()
+        assert (cnt[sl] == ref["wait_n"]).all()
+        assert _close(t[sl], ref["time"]) and _close(s[sl], ref["wait_sum"])
+
+
+def test_full_size_statistic_and_sharding_invariance(full_mm1):
+    """IID mean waiting time CI over 2^20 replications (BASELINE config 2) equals IndependentSample on the
+    host, brackets the stationary M/M/1/14 waiting time up to the warm-up bias, and a shard posted with a
+    replication offset reproduces the same replications bit for bit."""
+    sim = full_mm1
+    s, cnt = sim.get_wait_stats()
+    means = s / cnt
+    from sim_b200 import output_analysis as oa
+    host = oa.IndependentSample.post(means)
+    ci = sim.independent_sample_ci(0.05)
+    hci = host.confidence_interval_mean(0.05)
+    assert ci["n"] == FULL_N
+    assert abs(ci["mean"] - host.point_estimate_mean()) <= 1e-10 * ci["mean"]
+    assert abs(ci["lower"] - hci.lower()) <= 1e-9 and abs(ci["upper"] - hci.upper()) <= 1e-9
+    # stationary M/M/1/14 (lambda .5, mu .333333): W = L / lambda_eff - 1/mu, closed form of simulations.rs:105-108
+    w_q = (172285188.0 / 14316139.0) / (4766600.0 / 14316169.0) - 1.0 / 0.333333
+    assert abs(ci["mean"] - w_q) / w_q < 0.02
+    models, conns = networks.mm1()
+    shard = _sim(models, conns, 512, seed=42, instrument=False, stat_model_id="processor-01", replication_offset=700000)
+    shard.step_until(FULL_UNTIL)
+    assert np.array_equal(shard.get_global_time(), sim.get_global_time()[700000:700512])
+    assert np.array_equal(shard.get_steps(), sim.get_steps()[700000:700512])
+    s2, c2 = shard.get_wait_stats()
+    assert np.array_equal(s2, s[700000:700512]) and np.array_equal(c2, cnt[700000:700512])
+
+
+def test_steady_state_output_on_device_records():
+    """BASELINE config 3 statistic: per-replication response-time series of the last tandem stage from the
+    captured device records -> SteadyStateOutput (MSER-style deletion, <= 30 batch means).  The series and the
+    interval must equal what the oracle's records give."""
+    models, conns = networks.tandem()
+    for m in models:
+        m.inner.store_records = True
+    sim = _sim(models, conns, 16, seed=8, instrument=True, trace_replications=4, trace_capacity=200000, steps_per_launch=32)
+    sim.step_until(800.0)
+    from sim_b200 import output_analysis as oa
+
+    def series(records):
+        arrival, out = {}, []
+        for time, action, subject in records:
+            if action == "Arrival":
+                arrival[subject] = time
+            elif action == "Departure" and subject in arrival:
+                out.append(time - arrival.pop(subject))
+        return out
+
+    for r in range(4):
+        o = oracle_api.OracleSimulation(models, conns)
+        o.set_rng_philox(8, r)
+        assert o.step_until(800.0, collect=False)[0] == 0
+        want = series(o.get_records("processor-3")[1])
+        got = series(sim.get_records("processor-3", r))
+        assert len(want) == len(got) > 100 and _close(want, got)
+        e, ref = oracle_api.steady_state(want, 0.05)
+        ss = oa.SteadyStateOutput.post(got)
+        ci = ss.confidence_interval_mean(0.05)
+        assert (ss.deletion_point, ss.batch_size, ss.batch_count) == (ref["deletion_point"], ref["batch_size"], ref["batch_count"])
+        assert abs(ci.lower() - ref["lower"]) < 1e-9 and abs(ci.upper() - ref["upper"]) < 1e-9
