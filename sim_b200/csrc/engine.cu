@@ -231,12 +231,27 @@ const char* engine_shape_name(int shape) { return (shape >= 0 && shape < SIMB_N_
 
 int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool instrument, EngineDims* dims) {
     dims->shape = engine_match_shape(net, rng_kind, instrument);
-    // widest tile that leaves room for SIMB_MIN_BLOCKS CTAs per SM (227 KB usable shared memory) with
-    // half of the SM's unified storage left to L1 (the ring slots live there between steps)
-    const uint32_t budget = (114u * 1024u) / SIMB_MIN_BLOCKS;
-    uint32_t tile = 256;
-    while (tile > 32 && smem_plan(net, tile, 1).total > budget) tile >>= 1;
+    // Tile width = replications per CTA.  Pick the width that keeps the most warps resident per SM
+    // (shared memory 227 KB, 64 registers per thread -> at most 32 warps, at most 32 CTAs); among equals
+    // prefer the wider tile (fewer, larger bulk copies), and keep half of the SM's unified storage for L1
+    // when that costs no occupancy (the ring slots live in L1 between steps).
     const uint32_t stages = 1;
+    uint32_t tile = 256, best_warps = 0;
+    for (uint32_t cand = 256; cand >= 32; cand >>= 1) {
+        const uint32_t smem = smem_plan(net, cand, stages).total;
+        if (smem > 227u * 1024u) continue;
+        uint32_t ctas = (227u * 1024u) / smem;
+        const uint32_t by_regs = 65536u / (64u * cand), by_threads = 2048u / cand;
+        if (ctas > by_regs) ctas = by_regs;
+        if (ctas > by_threads) ctas = by_threads;
+        if (ctas > 32u) ctas = 32u;
+        const uint32_t warps = ctas * cand / 32u;
+        if (warps > best_warps) {
+            best_warps = warps;
+            tile = cand;
+        }
+    }
+    if (best_warps == 0) return (int)cudaErrorInvalidConfiguration;
     if (n && n < tile) {
         uint32_t t = 32;
         while (t < n) t <<= 1;
