@@ -68,6 +68,7 @@ void free_device(simb_sim* s) {
     F(s->st.w);
     F(s->st.ring_w);
     F(s->st.ring_d);
+    F(s->st.mail);
     F(s->st.trace);
     F(s->st.trace_count);
     F(s->st.conn_count);
@@ -118,6 +119,7 @@ int build_device(simb_sim* s, uint32_t keep_mask, const simb_sim* old) {
     if ((r = dev_alloc(&st.w, (size_t)net.n_wrows * stride, false))) return r;
     if ((r = dev_alloc(&st.ring_w, (size_t)(s->hn.ring_w_slots + 1) * stride, true))) return r;
     if ((r = dev_alloc(&st.ring_d, (size_t)(s->hn.ring_d_slots + 1) * stride, true))) return r;
+    if ((r = dev_alloc(&st.mail, (size_t)(2u * (net.max_pending - net.pend_tile) + 1) * stride, true))) return r;
     st.trace_reps = 0;
     st.trace_cap = 0;
     if (s->instrument) {
@@ -521,7 +523,15 @@ int simb_get_messages(simb_sim* s, uint64_t rep, simb_message* out, uint64_t cap
     const uint32_t np = CTL_NPEND(w[net.wrow_ctl]);
     *count = np;
     for (uint32_t j = 0; j < np && j < capacity && out; j++) {
-        const uint32_t content = w[net.wrow_pend + 2 * j], rw = w[net.wrow_pend + 2 * j + 1];
+        uint32_t content, rw;
+        if (j < net.pend_tile) {
+            content = w[net.wrow_pend + 2 * j];
+            rw = w[net.wrow_pend + 2 * j + 1];
+        } else {
+            const uint32_t* base = s->st.mail + (uint64_t)(2u * (j - net.pend_tile)) * s->st.stride + rep;
+            CUDA_TRY(cudaMemcpy(&content, base, 4, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(&rw, base + s->st.stride, 4, cudaMemcpyDeviceToHost));
+        }
         simb_message& m = out[j];
         std::memset(&m, 0, sizeof m);
         const uint32_t conn = ROUTE_CONN(rw);

@@ -96,32 +96,22 @@ struct Lane {
     double* d;
     uint32_t* w;
     uint32_t stride;
-    // global ring storage, already offset to this replication's column
-    uint32_t* ring_w;
-    double* ring_d;
-    uint64_t ring_stride;
+    uint32_t rep;  // local replication index (column of the global arrays; rings are addressed through it)
     // registers
     double time;
     uint32_t err, npend, steps, events, draw_idx;
     uint32_t phase_lo, phase_hi;
     uint64_t hash;
     uint64_t pcg_lo, pcg_hi;
-    uint64_t c0, c1, c2, c3;  // next draws of the Philox stream: c0 is draw number draw_idx
-    uint32_t ccount;          // valid entries in c0..c3
-    uint32_t key0, key1;
-    uint32_t tmask;           // bit m: the mailbox holds a message for model m
+    uint64_t c0, c1, c2;  // next draws of the Philox stream: c0 is draw number draw_idx
+    uint32_t ccount;      // valid entries in c0..c2
+    uint32_t tmask;       // bit m: the mailbox holds a message for model m
     uint32_t dm_int, dm_ext;  // deferred continuous draws: "until_next_event[m] = sample(dist[m])" still
                               // owed from the previous internal phase / this external phase
-    uint32_t absent;
-    uint64_t rep_local;
     uint32_t traced;
-    uint32_t wait_n;
-    double wait_sum;
 
     SIMB_HD double& D(uint32_t row) { return d[(size_t)row * stride]; }
     SIMB_HD uint32_t& W(uint32_t row) { return w[(size_t)row * stride]; }
-    SIMB_HD uint32_t& RW(uint32_t slot) { return ring_w[(uint64_t)slot * ring_stride]; }
-    SIMB_HD double& RD(uint32_t slot) { return ring_d[(uint64_t)slot * ring_stride]; }
     SIMB_HD uint32_t phase(uint32_t m) const {
         return m < 16 ? (phase_lo >> (2 * m)) & 3u : (phase_hi >> (2 * (m - 16))) & 3u;
     }
@@ -199,24 +189,43 @@ struct Engine {
 
     // Append the next Philox block to the per-lane draw cache (call only with ccount <= 2).  Draw
     // number i is word pair (i & 1) of block i >> 1, so the cache is a pure prefetch of the stream.
+    // Philox key of this replication: (global replication index, seed) -- derived on demand, not kept in registers
+    SIMB_HD uint32_t key0(const Lane& ln) const { return (uint32_t)(st.rep_offset + ln.rep); }
+    SIMB_HD uint32_t key1(const Lane& ln) const { return (uint32_t)st.seed + (uint32_t)((st.rep_offset + ln.rep) >> 32); }
+    // Append the next Philox block to the three-entry draw cache (call only with ccount <= 1).  Draw
+    // number i is word pair (i & 1) of block i >> 1, so the cache is a pure prefetch of the stream.
     SIMB_HD void cache_push(Lane& ln, uint32_t nxt, uint64_t a, uint64_t b) {
-        if (nxt & 1u) a = b;  // only right after a state load that left an odd draw index
-        const uint32_t n = ln.ccount;
-        if (n == 0) { ln.c0 = a; ln.c1 = b; }
-        else if (n == 1) { ln.c1 = a; ln.c2 = b; }
-        else { ln.c2 = a; ln.c3 = b; }
-        ln.ccount = n + ((nxt & 1u) ? 1u : 2u);
+        if (nxt & 1u) a = b;  // odd position (only right after a state load): the block's second half
+        if (ln.ccount == 0) {
+            ln.c0 = a;
+            ln.c1 = b;
+        } else {
+            ln.c1 = a;
+            ln.c2 = b;
+        }
+        ln.ccount += (nxt & 1u) ? 1u : 2u;
     }
     SIMB_HD void philox_refill(Lane& ln) {
         const uint32_t nxt = ln.draw_idx + ln.ccount;
         uint64_t a, b;
-        philox_block(ln.key0, ln.key1, nxt >> 1, &a, &b);
+        philox_block(key0(ln), key1(ln), nxt >> 1, &a, &b);
         cache_push(ln, nxt, a, b);
     }
     SIMB_HD void philox_refill_cold(Lane& ln) {
         const uint32_t nxt = ln.draw_idx + ln.ccount;
-        const U64Pair p = philox_pair_cold(ln.key0, ln.key1, nxt >> 1);
+        const U64Pair p = philox_pair_cold(key0(ln), key1(ln), nxt >> 1);
         cache_push(ln, nxt, p.a, p.b);
+    }
+
+    // queue / table storage in global memory, [slot][replication]
+    SIMB_HD uint32_t& RW(Lane& ln, uint32_t slot) { return st.ring_w[(uint64_t)slot * st.stride + ln.rep]; }
+    SIMB_HD double& RD(Lane& ln, uint32_t slot) { return st.ring_d[(uint64_t)slot * st.stride + ln.rep]; }
+
+    // mailbox slot j: word 0 = content, word 1 = route.  The first net.pend_tile slots are rows of the
+    // state tile (shared memory); deeper slots -- reached only by rare bursts -- stay in global memory.
+    SIMB_HD uint32_t& mail_word(Lane& ln, uint32_t j, uint32_t which) {
+        if (j < net.pend_tile) return ln.W(net.wrow_pend + 2u * j + which);
+        return st.mail[(uint64_t)(2u * (j - net.pend_tile) + which) * st.stride + ln.rep];
     }
 
     // ---- uniform u64 source (RngCore::next_u64 on the shared DynRng, services.rs:25-27) ----------
@@ -226,7 +235,6 @@ struct Engine {
             const uint64_t v = ln.c0;
             ln.c0 = ln.c1;
             ln.c1 = ln.c2;
-            ln.c2 = ln.c3;
             ln.ccount--;
             ln.draw_idx++;
             return v;
@@ -247,7 +255,7 @@ struct Engine {
                 if (!ln.err) ln.err = 37;  // SIMB_ERR_STREAM_EXHAUSTED
                 return 0;
             }
-            return st.ext[(uint64_t)idx * st.stride + ln.rep_local];
+            return st.ext[(uint64_t)idx * st.stride + ln.rep];
         }
     }
 
@@ -419,7 +427,7 @@ struct Engine {
             st.record_count[m * ACT_COUNT + action] += 1ull;
 #endif
             if (ln.traced) {
-                uint32_t k = st.trace_count[ln.rep_local];
+                uint32_t k = st.trace_count[ln.rep];
                 if (k < st.trace_cap) {
                     SimbTraceRec r;
                     r.step = ln.steps + 1u;
@@ -427,9 +435,9 @@ struct Engine {
                     r.content = content;
                     r.aux = action | (aux << 8);
                     r.time = ln.time;
-                    st.trace[(uint64_t)ln.rep_local * st.trace_cap + k] = r;
+                    st.trace[(uint64_t)ln.rep * st.trace_cap + k] = r;
                 }
-                st.trace_count[ln.rep_local] = k + 1u;
+                st.trace_count[ln.rep] = k + 1u;
             }
         }
     }
@@ -445,8 +453,8 @@ struct Engine {
                 return;
             }
             SimbRoute rt = net.routes[r];
-            ln.W(net.wrow_pend + 2 * ln.npend) = content;
-            ln.W(net.wrow_pend + 2 * ln.npend + 1) = ROUTE_WORD(rt.tgt_model, rt.tgt_port, rt.connector);
+            mail_word(ln, ln.npend, 0) = content;
+            mail_word(ln, ln.npend, 1) = ROUTE_WORD(rt.tgt_model, rt.tgt_port, rt.connector);
             ln.npend++;
             if (rt.tgt_model < SIMB_MAX_MODELS) ln.tmask |= 1u << rt.tgt_model;
             if (INSTR) {
@@ -457,7 +465,7 @@ struct Engine {
                 st.conn_count[rt.connector] += 1ull;
 #endif
                 if (ln.traced) {
-                    uint32_t k = st.trace_count[ln.rep_local];
+                    uint32_t k = st.trace_count[ln.rep];
                     if (k < st.trace_cap) {
                         SimbTraceRec t;
                         t.step = ln.steps + 1u;
@@ -465,9 +473,9 @@ struct Engine {
                         t.content = content;
                         t.aux = 0;
                         t.time = ln.time;
-                        st.trace[(uint64_t)ln.rep_local * st.trace_cap + k] = t;
+                        st.trace[(uint64_t)ln.rep * st.trace_cap + k] = t;
                     }
-                    st.trace_count[ln.rep_local] = k + 1u;
+                    st.trace_count[ln.rep] = k + 1u;
                 }
             }
         }
@@ -486,7 +494,7 @@ struct Engine {
             return false;
         }
         uint32_t s = ring_slot(md, head, len);
-        ln.RW(md.ring_w0 + s) = content;
+        RW(ln, md.ring_w0 + s) = content;
         ln.W(md.wrow) = (head << 16) | (len + 1u);
         *slot_out = s;
         return true;
@@ -494,7 +502,7 @@ struct Engine {
     SIMB_HD uint32_t ring_pop(Lane& ln, const SimbModelDesc& md, uint32_t* slot_out) {
         uint32_t q = ln.W(md.wrow);
         uint32_t head = q >> 16, len = q & 0xFFFFu;
-        uint32_t c = ln.RW(md.ring_w0 + head);
+        uint32_t c = RW(ln, md.ring_w0 + head);
         *slot_out = head;
         uint32_t nh = head + 1u;
         if (nh >= md.ring_cap) nh = 0;
@@ -503,13 +511,12 @@ struct Engine {
     }
 
     // ---- per-lane context <-> state tile -----------------------------------------------------------
-    // Before: ln.d / ln.w / ln.stride / ln.ring_* / ln.rep_local are set.  Returns the ctl word.
+    // Before: ln.d / ln.w / ln.stride / ln.ring_* / ln.rep are set.  Returns the ctl word.
     SIMB_HD uint32_t lane_load(Lane& ln, bool instr) {
         ln.time = ln.D(net.drow_time);
         const uint32_t ctl = ln.W(net.wrow_ctl);
         ln.err = CTL_ERR(ctl);
         ln.npend = CTL_NPEND(ctl);
-        ln.absent = CTL_ABSENT(ctl);
         ln.steps = ln.W(net.wrow_steps);
         ln.events = ln.W(net.wrow_events);
         ln.draw_idx = 0;
@@ -524,27 +531,21 @@ struct Engine {
         ln.phase_hi = net.n_phase_words > 1 ? ln.W(net.wrow_phase + 1) : 0u;
         ln.hash = 0;
         if (instr) ln.hash = (uint64_t)ln.W(net.wrow_hash) | ((uint64_t)ln.W(net.wrow_hash + 1) << 32);
-        ln.c0 = ln.c1 = ln.c2 = ln.c3 = 0;
+        ln.c0 = ln.c1 = ln.c2 = 0;
         ln.ccount = 0;
-        const uint64_t g = st.rep_offset + ln.rep_local;
-        ln.key0 = (uint32_t)g;
-        ln.key1 = (uint32_t)st.seed + (uint32_t)(g >> 32);
-        ln.traced = instr && ln.rep_local < st.trace_reps;
-        const bool has_stat = net.drow_wait != 0;
-        ln.wait_sum = has_stat ? ln.D(net.drow_wait) : 0.0;
-        ln.wait_n = has_stat ? ln.W(net.wrow_waitn) : 0u;
+        ln.traced = instr && ln.rep < st.trace_reps;
         ln.dm_int = ln.W(net.wrow_dmask);
         ln.dm_ext = 0;
         ln.tmask = 0;
         for (uint32_t j = 0; j < ln.npend; j++) {
-            const uint32_t t = ROUTE_TGT(ln.W(net.wrow_pend + 2 * j + 1));
+            const uint32_t t = ROUTE_TGT(mail_word(ln, j, 1));
             if (t < SIMB_MAX_MODELS) ln.tmask |= 1u << t;
         }
         return ctl;
     }
-    SIMB_HD void lane_store(Lane& ln, bool instr, uint32_t done_epoch) {
+    SIMB_HD void lane_store(Lane& ln, bool instr, uint32_t done_epoch, uint32_t absent) {
         ln.D(net.drow_time) = ln.time;
-        ln.W(net.wrow_ctl) = CTL_MAKE(ln.err, done_epoch, ln.npend, ln.absent);
+        ln.W(net.wrow_ctl) = CTL_MAKE(ln.err, done_epoch, ln.npend, absent);
         ln.W(net.wrow_steps) = ln.steps;
         ln.W(net.wrow_events) = ln.events;
         if (RNG == 1) {
@@ -560,10 +561,6 @@ struct Engine {
         if (instr) {
             ln.W(net.wrow_hash) = (uint32_t)ln.hash;
             ln.W(net.wrow_hash + 1) = (uint32_t)(ln.hash >> 32);
-        }
-        if (net.drow_wait != 0) {
-            ln.D(net.drow_wait) = ln.wait_sum;
-            ln.W(net.wrow_waitn) = ln.wait_n;
         }
         ln.W(net.wrow_dmask) = ln.dm_int;
     }
@@ -590,15 +587,15 @@ struct Engine {
                 }
                 uint32_t slot;
                 if (!ring_push(ln, md, content, &slot)) break;
-                if (md.flags & MF_STAT) ln.RD(md.ring_d + slot) = ln.time;
+                if (md.flags & MF_STAT) RD(ln, md.ring_d + slot) = ln.time;
                 if (empty) {  // activate :128-150
                     ln.set_phase(m, 1);
                     if (!defer_draw(ln, m, md, true)) break;  // until_next_event = service time draw
                     record<INSTR>(ln, m, ACT_ARRIVAL, content);
                     record<INSTR>(ln, m, ACT_PROCESSING_START, content);
                     if (md.flags & MF_STAT) {
-                        ln.wait_sum += ln.time - ln.time;  // Processing Start - Arrival = 0 here
-                        ln.wait_n++;
+                        ln.D(net.drow_wait) += ln.time - ln.time;  // Processing Start - Arrival = 0 here
+                        ln.W(net.wrow_waitn) += 1u;
                     }
                 } else {  // add_job :119-126
                     record<INSTR>(ln, m, ACT_ARRIVAL, content);
@@ -660,13 +657,13 @@ struct Engine {
                 uint32_t cnt = ln.W(md.wrow);
                 uint32_t i = 0;
                 for (; i < cnt; i++)
-                    if (ln.RW(md.ring_w0 + i) == content) break;
+                    if (RW(ln, md.ring_w0 + i) == content) break;
                 if (i < cnt) {
-                    ln.RW(md.ring_w1 + i) += 1u;
+                    RW(ln, md.ring_w1 + i) += 1u;
                 } else {
                     if (cnt >= md.ring_cap) { ln.err = 32; break; }
-                    ln.RW(md.ring_w0 + cnt) = content;
-                    ln.RW(md.ring_w1 + cnt) = 1u;
+                    RW(ln, md.ring_w0 + cnt) = content;
+                    RW(ln, md.ring_w1 + cnt) = 1u;
                     ln.W(md.wrow) = cnt + 1u;
                 }
                 record<INSTR>(ln, m, ACT_ARRIVAL, content, port + 1u);
@@ -681,7 +678,7 @@ struct Engine {
                 if (ln.err) break;
                 uint32_t slot;
                 if (!ring_push(ln, md, content, &slot)) break;
-                ln.RW(md.ring_w1 + slot) = pass ? 1u : 0u;
+                RW(ln, md.ring_w1 + slot) = pass ? 1u : 0u;
                 record<INSTR>(ln, m, ACT_ARRIVAL, content);
                 break;
             }
@@ -699,25 +696,25 @@ struct Engine {
                 uint32_t cnt = ln.W(md.wrow);
                 uint32_t i = 0;
                 for (; i < cnt; i++)
-                    if (ln.RW(md.ring_w0 + i) == content) break;
+                    if (RW(ln, md.ring_w0 + i) == content) break;
                 uint32_t mine = port == 0 ? 1u : 2u, other = port == 0 ? 2u : 1u;
                 if (i == cnt) {
                     if (cnt >= md.ring_cap) { ln.err = 32; break; }
                     uint32_t seq = ln.W(md.wrow + 2);
                     ln.W(md.wrow + 2) = seq + 1u;
-                    ln.RW(md.ring_w0 + cnt) = content;
-                    ln.RW(md.ring_w1 + cnt) = (seq << 2) | mine;
-                    ln.RD(md.ring_d + cnt) = ln.time;
+                    RW(ln, md.ring_w0 + cnt) = content;
+                    RW(ln, md.ring_w1 + cnt) = (seq << 2) | mine;
+                    RD(ln, md.ring_d + cnt) = ln.time;
                     ln.W(md.wrow) = cnt + 1u;
                     break;
                 }
-                uint32_t fl = ln.RW(md.ring_w1 + i);
+                uint32_t fl = RW(ln, md.ring_w1 + i);
                 if (!(fl & other)) {  // same side again: overwrite the time
-                    ln.RD(md.ring_d + i) = ln.time;
+                    RD(ln, md.ring_d + i) = ln.time;
                     break;
                 }
                 // both sides now known: duration = stop - start (some_duration :95-100)
-                double t_other = ln.RD(md.ring_d + i);
+                double t_other = RD(ln, md.ring_d + i);
                 double dur = port == 0 ? t_other - ln.time : ln.time - t_other;
                 uint32_t seq = fl >> 2;
                 uint32_t best_c = ln.W(md.wrow + 1), best_seq = ln.W(md.wrow + 3);
@@ -734,9 +731,9 @@ struct Engine {
                 // drop the completed entry (swap with last; lookup is by name, order by seq)
                 uint32_t last = cnt - 1u;
                 if (i != last) {
-                    ln.RW(md.ring_w0 + i) = ln.RW(md.ring_w0 + last);
-                    ln.RW(md.ring_w1 + i) = ln.RW(md.ring_w1 + last);
-                    ln.RD(md.ring_d + i) = ln.RD(md.ring_d + last);
+                    RW(ln, md.ring_w0 + i) = RW(ln, md.ring_w0 + last);
+                    RW(ln, md.ring_w1 + i) = RW(ln, md.ring_w1 + last);
+                    RD(ln, md.ring_d + i) = RD(ln, md.ring_d + last);
                 }
                 ln.W(md.wrow) = last;
                 break;
@@ -776,7 +773,7 @@ struct Engine {
     SIMB_HD void release_n(Lane& ln, uint32_t m, const SimbModelDesc& md, uint32_t n, uint32_t out_port, uint32_t aux) {
         if (INSTR) {
             uint32_t head = ln.W(md.wrow) >> 16;
-            for (uint32_t i = 0; i < n; i++) record<INSTR>(ln, m, ACT_DEPARTURE, ln.RW(md.ring_w0 + ring_slot(md, head, i)), aux);
+            for (uint32_t i = 0; i < n; i++) record<INSTR>(ln, m, ACT_DEPARTURE, RW(ln, md.ring_w0 + ring_slot(md, head, i)), aux);
         }
         for (uint32_t i = 0; i < n && !ln.err; i++) {
             uint32_t slot;
@@ -814,10 +811,10 @@ struct Engine {
                     }
                     ln.set_phase(m, 1);  // process_next :160-175
                     if (!defer_draw(ln, m, md, false)) break;
-                    record<INSTR>(ln, m, ACT_PROCESSING_START, ln.RW(md.ring_w0 + head));
+                    record<INSTR>(ln, m, ACT_PROCESSING_START, RW(ln, md.ring_w0 + head));
                     if (md.flags & MF_STAT) {
-                        ln.wait_sum += ln.time - ln.RD(md.ring_d + head);
-                        ln.wait_n++;
+                        ln.D(net.drow_wait) += ln.time - RD(ln, md.ring_d + head);
+                        ln.W(net.wrow_waitn) += 1u;
                     }
                     break;
                 }
@@ -877,16 +874,16 @@ struct Engine {
                 uint32_t cnt = ln.W(md.wrow);
                 uint32_t i = 0;
                 for (; i < cnt; i++)  // canonical choice: earliest-inserted full collection
-                    if (ln.RW(md.ring_w1 + i) == md.n_in) break;
+                    if (RW(ln, md.ring_w1 + i) == md.n_in) break;
                 if (i == cnt) {  // passivate
                     ln.D(urow) = SIMB_INF;
                     break;
                 }
                 ln.D(urow) = 0.0;  // send_job :118-143
-                uint32_t c = ln.RW(md.ring_w0 + i);
+                uint32_t c = RW(ln, md.ring_w0 + i);
                 for (uint32_t j = i; j + 1u < cnt; j++) {  // remove, keeping insertion order
-                    ln.RW(md.ring_w0 + j) = ln.RW(md.ring_w0 + j + 1u);
-                    ln.RW(md.ring_w1 + j) = ln.RW(md.ring_w1 + j + 1u);
+                    RW(ln, md.ring_w0 + j) = RW(ln, md.ring_w0 + j + 1u);
+                    RW(ln, md.ring_w1 + j) = RW(ln, md.ring_w1 + j + 1u);
                 }
                 ln.W(md.wrow) = cnt - 1u;
                 if (INSTR)
@@ -903,7 +900,7 @@ struct Engine {
                 ln.D(urow) = 0.0;
                 uint32_t slot;
                 uint32_t c = ring_pop(ln, md, &slot);
-                if (ln.RW(md.ring_w1 + slot)) {  // pass_job :129-141
+                if (RW(ln, md.ring_w1 + slot)) {  // pass_job :129-141
                     record<INSTR>(ln, m, ACT_PASS, c);
                     emit<INSTR>(ln, md, 0, c);
                 } else {  // block_job :143-148
@@ -953,10 +950,10 @@ struct Engine {
     SIMB_HD void ext_model(Lane& ln, uint32_t m, uint32_t np, uint32_t& nev) {
         const SimbModelDesc& md = net.models[m];
         for (uint32_t j = 0; j < np && !ln.err; j++) {
-            const uint32_t rw = ln.W(net.wrow_pend + 2 * j + 1);
+            const uint32_t rw = mail_word(ln, j, 1);
             if (ROUTE_TGT(rw) != m) continue;
             nev++;
-            events_ext<INSTR>(ln, m, md, ROUTE_PORT(rw), ln.W(net.wrow_pend + 2 * j));
+            events_ext<INSTR>(ln, m, md, ROUTE_PORT(rw), mail_word(ln, j, 0));
         }
     }
 
@@ -987,7 +984,7 @@ struct Engine {
         }
         // ---- pay the deferred draws (and top up the Philox prefetch) at this converged point ----
         if (live) {
-            if (RNG == 0 && ln.ccount <= 2u) philox_refill(ln);
+            if (RNG == 0 && ln.ccount <= 1u) philox_refill(ln);
             flush_draws(ln);
         }
         // A failed events_ext aborts the step (`?` at :222); the replication freezes.

@@ -38,7 +38,7 @@ __global__ void simb_init_kernel(const __grid_constant__ SimbNetDesc net, const 
     }
     const uint32_t rng_rows = rng_kind == 1 ? 4u : 1u;
     for (uint32_t k = 0; k < net.n_wrows; k++) {
-        if (keep_mail && k >= net.wrow_pend && k < net.wrow_pend + 2u * net.max_pending) continue;
+        if (keep_mail && k >= net.wrow_pend && k < net.wrow_pend + 2u * net.pend_tile) continue;
         if (keep_rng && k >= net.wrow_rng && k < net.wrow_rng + rng_rows) continue;
         st.w[(uint64_t)k * st.stride + r] = w_init[k];
     }
@@ -84,8 +84,13 @@ __global__ void simb_inject_kernel(const __grid_constant__ SimbNetDesc net, cons
         atomicAdd(overflow, 1ull);
         return;
     }
-    st.w[(uint64_t)(net.wrow_pend + 2u * np) * st.stride + r] = content;
-    st.w[(uint64_t)(net.wrow_pend + 2u * np + 1u) * st.stride + r] = route_word;
+    if (np < net.pend_tile) {
+        st.w[(uint64_t)(net.wrow_pend + 2u * np) * st.stride + r] = content;
+        st.w[(uint64_t)(net.wrow_pend + 2u * np + 1u) * st.stride + r] = route_word;
+    } else {
+        st.mail[(uint64_t)(2u * (np - net.pend_tile)) * st.stride + r] = content;
+        st.mail[(uint64_t)(2u * (np - net.pend_tile) + 1u) * st.stride + r] = route_word;
+    }
     st.w[(uint64_t)net.wrow_ctl * st.stride + r] = CTL_MAKE(CTL_ERR(c), CTL_EPOCH(c), np + 1u, CTL_ABSENT(c));
 }
 
@@ -268,17 +273,16 @@ int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool inst
     // One CTA per tile.  Measured (profiles/r01_pipeline_experiments.txt): a persistent grid of
     // SMs x resident CTAs with static tile assignment is 8 % slower at K = 64 (no dynamic load balance)
     // and double buffering inside a CTA gains nothing at K = 1, where the 4 co-resident CTAs per SM already
-    // overlap each other's load / compute / store phases; the kernel keeps its grid-stride tile loop.
-    dims->grid = 0xFFFFFFFFu;
+    // overlap each other's load / compute / store phases.
+    dims->grid = 0;
     return (int)cudaSuccess;
 }
 
 int engine_launch_step(const SimbNetDesc& net, const SimbDevState& st, const SimbLaunch& la_in, const EngineDims& dims,
                        int rng_kind, bool instrument, bool count_active, cudaStream_t stream) {
-    const uint32_t n_tiles = (uint32_t)(st.stride / dims.tile);
-    const uint32_t grid = n_tiles < dims.grid ? n_tiles : dims.grid;
+    const uint32_t grid = (uint32_t)(st.stride / dims.tile);
     SimbLaunch la = la_in;
-    la.stages = dims.stages;
+    la.stages = 1;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(grid);

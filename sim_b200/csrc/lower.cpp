@@ -593,7 +593,8 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
         }
     }
     net.wrow_pend = wr;
-    wr += (uint16_t)(2 * net.max_pending);
+    net.pend_tile = (uint16_t)(net.max_pending < SIMB_MAIL_TILE_SLOTS ? net.max_pending : SIMB_MAIL_TILE_SLOTS);
+    wr += (uint16_t)(2 * net.pend_tile);
     net.n_drows = dr;
     net.n_wrows = wr;
 

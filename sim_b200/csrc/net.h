@@ -11,6 +11,9 @@
 #define SIMB_MAX_OUT_PORTS 96   /* total out-ports over all models */
 #define SIMB_MAX_WEIGHTS 64     /* total cumulative-weight entries over all ExclusiveGateways */
 #define SIMB_MAX_NAMES 255      /* content prefix / literal intern table */
+#ifndef SIMB_MAIL_TILE_SLOTS
+#define SIMB_MAIL_TILE_SLOTS 8  /* mailbox slots staged in shared memory; deeper slots (rare bursts) stay in HBM */
+#endif
 
 enum SimbModelType : uint8_t {
     MT_GENERATOR = 0,        // sim/src/models/generator.rs
@@ -81,10 +84,12 @@ struct SimbNetDesc {
     uint16_t wrow_hash;     // 2 words (instrumented handles only; else 0)
     uint16_t wrow_phase;    // 2 bits per model
     uint16_t n_phase_words;
-    uint16_t wrow_pend;     // max_pending x (content, route)
+    uint16_t wrow_pend;     // pend_tile x (content, route)
     uint16_t wrow_waitn;    // number of jobs that started service on the MF_STAT processor
     uint16_t uses_exp, uses_normal;
     uint16_t wrow_dmask;    // models whose until_next_event still owes a deferred draw (core.cuh)
+    uint16_t pend_tile;     // mailbox slots kept in the state tile (min(max_pending, SIMB_MAIL_TILE_SLOTS));
+                            // the rest live in the global overflow array SimbDevState.mail
     SimbModelDesc models[SIMB_MAX_MODELS];
     uint16_t route_begin[SIMB_MAX_OUT_PORTS + 1];
     SimbRoute routes[SIMB_MAX_ROUTES];
@@ -133,6 +138,7 @@ struct SimbDevState {
     uint32_t* w;          // [n_wrows][stride]
     uint32_t* ring_w;     // [ring_w_slots][stride]
     double* ring_d;       // [ring_d_slots][stride]
+    uint32_t* mail;       // mailbox overflow: [(max_pending - pend_tile) x (content, route)][stride]
     uint64_t stride;      // padded replication count (multiple of the tile width)
     uint64_t n;           // real replication count
     uint64_t rep_offset;  // global index of local replication 0

@@ -108,11 +108,7 @@ __host__ __device__ constexpr int shape_tier() {  // model-count tier of a baked
     return SHAPE < 0 ? 0 : tiers[SHAPE < 0 ? 0 : SHAPE];
 }
 
-// Persistent tile pipeline.  The grid is a multiple of the SM count (host: resident CTAs per SM x
-// 148); CTA c processes tiles c, c + grid, c + 2 grid, ...  With la.stages == 2 the bulk loads of the
-// NEXT tile are issued (by warp 0) before the current tile is computed, and the bulk stores of the
-// current tile drain while the next one is computed: HBM traffic and instruction issue overlap inside
-// one CTA instead of relying on co-resident CTAs alone.
+// One CTA = one tile of blockDim.x consecutive replications.
 template <int RNG, bool INSTR, int SHAPE>
 __global__ void __launch_bounds__(256, SIMB_MIN_BLOCKS)
 simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_constant__ SimbDevState st,
@@ -121,37 +117,18 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t tile = blockDim.x;
     const uint32_t tid = threadIdx.x;
-    const uint32_t stages = la.stages;
-    const SmemPlan sp = smem_plan(net, tile, stages);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.off_bar);  // [0], [1]: tile stages; [2]: tables
+    const SmemPlan sp = smem_plan(net, tile, 1);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + sp.off_bar);
     unsigned long long* s_red = reinterpret_cast<unsigned long long*>(smem + sp.off_red);
     double* s_expx = reinterpret_cast<double*>(smem + sp.off_expx);
     double* s_normx = reinterpret_cast<double*>(smem + sp.off_normx);
+    double* s_d = reinterpret_cast<double*>(smem + sp.off_tiles);
+    uint32_t* s_w = reinterpret_cast<uint32_t*>(smem + sp.off_tiles + sp.d_bytes);
     const uint32_t n_rows = net.n_drows + net.n_wrows;
-    const uint32_t tile_bytes = net.n_drows * tile * 8u + net.n_wrows * tile * 4u;
-    const uint32_t n_tiles = (uint32_t)(st.stride / tile);
-
-    // issue the bulk loads of tile `t` into stage `sg` (warp 0 only; one copy per state row)
-    auto issue_load = [&](uint32_t t, uint32_t sg) {
-        unsigned char* stage = smem + sp.off_tiles + sg * sp.stage_bytes;
-        double* s_d = reinterpret_cast<double*>(stage);
-        uint32_t* s_w = reinterpret_cast<uint32_t*>(stage + sp.d_bytes);
-        const uint64_t base = (uint64_t)t * tile;
-        if (tid == 0) mbar_expect_tx(&bars[sg], tile_bytes);
-        __syncwarp();
-        for (uint32_t r = tid; r < n_rows; r += 32) {
-            if (r < net.n_drows) bulk_g2s(s_d + (size_t)r * tile, st.d + (uint64_t)r * st.stride + base, tile * 8u, &bars[sg]);
-            else {
-                const uint32_t rr = r - net.n_drows;
-                bulk_g2s(s_w + (size_t)rr * tile, st.w + (uint64_t)rr * st.stride + base, tile * 4u, &bars[sg]);
-            }
-        }
-    };
+    const uint64_t base = (uint64_t)blockIdx.x * tile;  // first replication (padded index) of this tile
 
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        mbar_init(&bars[2], 1);
+        mbar_init(bar, 1);
         s_red[0] = 0ull;
         s_red[1] = 0ull;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -163,16 +140,24 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
     // global memory before the PREVIOUS launch has completed and flushed.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    uint32_t t = blockIdx.x;
-    if (t >= n_tiles) return;
+
+    // ---- 1. tile load: one bulk copy (TMA) per state row, spread over the lanes of warp 0 ----
     if (tid < 32) {
         if (tid == 0) {
-            // ziggurat x tables, once per CTA (random per-lane index -> shared memory, not constant)
-            mbar_expect_tx(&bars[2], (net.uses_exp ? ZIG_BYTES : 0u) + (net.uses_normal ? ZIG_BYTES : 0u));
-            if (net.uses_exp) bulk_g2s(s_expx, ZIG_EXP_X, ZIG_BYTES, &bars[2]);
-            if (net.uses_normal) bulk_g2s(s_normx, ZIG_NORM_X, ZIG_BYTES, &bars[2]);
+            mbar_expect_tx(bar, net.n_drows * tile * 8u + net.n_wrows * tile * 4u +
+                                    (net.uses_exp ? ZIG_BYTES : 0u) + (net.uses_normal ? ZIG_BYTES : 0u));
+            // ziggurat x tables ride on the same barrier (random per-lane index -> shared memory, not constant)
+            if (net.uses_exp) bulk_g2s(s_expx, ZIG_EXP_X, ZIG_BYTES, bar);
+            if (net.uses_normal) bulk_g2s(s_normx, ZIG_NORM_X, ZIG_BYTES, bar);
         }
-        issue_load(t, 0);
+        __syncwarp();
+        for (uint32_t r = tid; r < n_rows; r += 32) {
+            if (r < net.n_drows) bulk_g2s(s_d + (size_t)r * tile, st.d + (uint64_t)r * st.stride + base, tile * 8u, bar);
+            else {
+                const uint32_t rr = r - net.n_drows;
+                bulk_g2s(s_w + (size_t)rr * tile, st.w + (uint64_t)rr * st.stride + base, tile * 4u, bar);
+            }
+        }
     }
     Tables tab;
     tab.exp_x = s_expx;
@@ -180,91 +165,62 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
     tab.norm_x = s_normx;
     tab.norm_f = ZIG_NORM_F;
     Engine<RNG, shape_tier<SHAPE>()> eng(net, net_param, st, tab);
-    while (!mbar_try_wait(&bars[2], 0)) {
+    while (!mbar_try_wait(bar, 0)) {
     }
 
-    for (uint32_t it = 0; t < n_tiles; t += gridDim.x, it++) {
-        const uint32_t sg = stages == 2 ? (it & 1u) : 0u;
-        const uint32_t parity = stages == 2 ? ((it >> 1) & 1u) : (it & 1u);
-        const uint32_t t_next = t + gridDim.x;
-        // ---- 1. prefetch the next tile into the other stage (its previous stores have left it) ----
-        if (stages == 2 && t_next < n_tiles && tid < 32) {
-            bulk_wait_read_all();
-            issue_load(t_next, sg ^ 1u);
-        }
-        while (!mbar_try_wait(&bars[sg], parity)) {
-        }
-        unsigned char* stage = smem + sp.off_tiles + sg * sp.stage_bytes;
-        double* s_d = reinterpret_cast<double*>(stage);
-        uint32_t* s_w = reinterpret_cast<uint32_t*>(stage + sp.d_bytes);
-        const uint64_t base = (uint64_t)t * tile;  // first replication (padded index) of this tile
+    // ---- 2. per-lane context ----
+    Lane ln;
+    ln.d = s_d + tid;
+    ln.w = s_w + tid;
+    ln.stride = tile;
+    ln.rep = (uint32_t)(base + tid);
+    const uint32_t ctl = eng.lane_load(ln, INSTR);
+    const bool absent = CTL_ABSENT(ctl) != 0;
 
-        // ---- 2. per-lane context ----
-        Lane ln;
-        ln.d = s_d + tid;
-        ln.w = s_w + tid;
-        ln.stride = tile;
-        ln.rep_local = base + tid;
-        ln.ring_w = st.ring_w + ln.rep_local;
-        ln.ring_d = st.ring_d + ln.rep_local;
-        ln.ring_stride = st.stride;
-        const uint32_t ctl = eng.lane_load(ln, INSTR);
-        const bool absent = ln.absent != 0;
-
-        // ---- 3. up to K lockstep steps (each warp runs on its own; no block barrier per step) ----
-        bool done = absent || (la.mode == 1 && CTL_EPOCH(ctl) == la.epoch);
-        bool stepped = false;
-        for (uint32_t k = 0; k < la.k; k++) {
-            const bool live = !done && ln.err == 0;
-            if (__ballot_sync(0xFFFFFFFFu, live) == 0u) break;  // every replication of this warp is finished
-            stepped = true;
-            eng.template step<INSTR>(ln, live);
-            if (live && la.mode == 1 && !(ln.time < la.until)) done = true;  // step_until: mod.rs:281-285
-        }
-        // last launch of an API call: pay the deferred draws so the stored state is observable as is
-        if (la.settle && !absent && (ln.dm_int | ln.dm_ext)) {
-            eng.flush_draws(ln);
-            stepped = true;
-        }
-
-        // ---- 4. write back ----
-        if (stepped) {
-            eng.lane_store(ln, INSTR, (la.mode == 1 && done) ? la.epoch : 0u);
-            fence_proxy_async();  // generic-proxy writes -> visible to the bulk (async proxy) stores
-        }
-        if (count_active) {
-            const uint32_t act = __popc(__ballot_sync(0xFFFFFFFFu, !done && ln.err == 0));
-            const uint32_t bad = __popc(__ballot_sync(0xFFFFFFFFu, !absent && ln.err != 0));
-            if ((tid & 31u) == 0) {
-                if (act) atomicAdd(&s_red[0], (unsigned long long)act);
-                if (bad) atomicAdd(&s_red[1], (unsigned long long)bad);
-            }
-        }
-        const bool any_stepped = __syncthreads_or(stepped) != 0;
-        if (tid < 32) {
-            if (any_stepped) {
-                for (uint32_t r = tid; r < n_rows; r += 32) {
-                    if (r < net.n_drows) bulk_s2g(st.d + (uint64_t)r * st.stride + base, s_d + (size_t)r * tile, tile * 8u);
-                    else {
-                        const uint32_t rr = r - net.n_drows;
-                        bulk_s2g(st.w + (uint64_t)rr * st.stride + base, s_w + (size_t)rr * tile, tile * 4u);
-                    }
-                }
-                bulk_commit();
-            }
-            if (stages != 2 && t_next < n_tiles) {  // single buffer: drain the stores, then refill the same stage
-                bulk_wait_read_all();
-                issue_load(t_next, 0);
-            }
-        }
+    // ---- 3. up to K lockstep steps (each warp runs on its own; no block barrier per step) ----
+    bool done = absent || (la.mode == 1 && CTL_EPOCH(ctl) == la.epoch);
+    bool stepped = false;
+    for (uint32_t k = 0; k < la.k; k++) {
+        const bool live = !done && ln.err == 0;
+        if (__ballot_sync(0xFFFFFFFFu, live) == 0u) break;  // every replication of this warp is finished
+        stepped = true;
+        eng.template step<INSTR>(ln, live);
+        if (live && la.mode == 1 && !(ln.time < la.until)) done = true;  // step_until: mod.rs:281-285
     }
-    if (tid < 32) bulk_wait_read_all();  // the stores must have read shared memory before the CTA exits
+    // last launch of an API call: pay the deferred draws so the stored state is observable as is
+    if (la.settle && !absent && (ln.dm_int | ln.dm_ext)) {
+        eng.flush_draws(ln);
+        stepped = true;
+    }
+
+    // ---- 4. write back ----
+    if (stepped) {
+        eng.lane_store(ln, INSTR, (la.mode == 1 && done) ? la.epoch : 0u, absent ? 1u : 0u);
+        fence_proxy_async();  // generic-proxy writes -> visible to the bulk (async proxy) stores
+    }
     if (count_active) {
-        __syncthreads();
-        if (tid == 0) {
-            if (s_red[0]) atomicAdd(&st.totals[2], s_red[0]);
-            if (s_red[1]) atomicAdd(&st.totals[3], s_red[1]);
+        const uint32_t act = __popc(__ballot_sync(0xFFFFFFFFu, !done && ln.err == 0));
+        const uint32_t bad = __popc(__ballot_sync(0xFFFFFFFFu, !absent && ln.err != 0));
+        if ((tid & 31u) == 0) {
+            if (act) atomicAdd(&s_red[0], (unsigned long long)act);
+            if (bad) atomicAdd(&s_red[1], (unsigned long long)bad);
         }
+    }
+    const bool any_stepped = __syncthreads_or(stepped) != 0;
+    if (any_stepped && tid < 32) {
+        for (uint32_t r = tid; r < n_rows; r += 32) {
+            if (r < net.n_drows) bulk_s2g(st.d + (uint64_t)r * st.stride + base, s_d + (size_t)r * tile, tile * 8u);
+            else {
+                const uint32_t rr = r - net.n_drows;
+                bulk_s2g(st.w + (uint64_t)rr * st.stride + base, s_w + (size_t)rr * tile, tile * 4u);
+            }
+        }
+        bulk_commit();
+        bulk_wait_read_all();  // the stores must have read shared memory before the CTA exits
+    }
+    if (count_active && tid == 0) {
+        if (s_red[0]) atomicAdd(&st.totals[2], s_red[0]);
+        if (s_red[1]) atomicAdd(&st.totals[3], s_red[1]);
     }
 }
 

@@ -24,7 +24,7 @@ struct HS {
     int rng_kind = 0;
     bool instr = false;
     std::vector<double> d, ring_d;
-    std::vector<uint32_t> w, ring_w, trace_count;
+    std::vector<uint32_t> w, ring_w, trace_count, mail;
     std::vector<SimbTraceRec> trace;
     std::vector<unsigned long long> conn_count, record_count, totals;
     std::vector<uint64_t> ext;
@@ -44,10 +44,7 @@ void run(HS* h, int mode, uint64_t k, double until) {
         ln.d = h->d.data() + r;
         ln.w = h->w.data() + r;
         ln.stride = (uint32_t)h->n;
-        ln.ring_w = h->ring_w.data() + r;
-        ln.ring_d = h->ring_d.data() + r;
-        ln.ring_stride = h->n;
-        ln.rep_local = r;
+        ln.rep = (uint32_t)r;
         eng.lane_load(ln, INSTR);
         bool done = false;
         for (uint64_t i = 0; mode == 1 || i < k; i++) {
@@ -58,12 +55,12 @@ void run(HS* h, int mode, uint64_t k, double until) {
             // h->settle_every > 0: store + reload the lane every few steps, as consecutive kernel
             // launches do (exercises the persisted deferred-draw mask and the Philox prefetch restart)
             if (h->settle_every && (i + 1) % h->settle_every == 0) {
-                eng.lane_store(ln, INSTR, 0);
+                eng.lane_store(ln, INSTR, 0, 0);
                 eng.lane_load(ln, INSTR);
             }
         }
         eng.flush_draws(ln);  // "settle": what the last launch of an API call does
-        eng.lane_store(ln, INSTR, done ? h->epoch : 0);
+        eng.lane_store(ln, INSTR, done ? h->epoch : 0, 0);
     }
 }
 void dispatch(HS* h, int mode, uint64_t k, double until) {
@@ -117,6 +114,7 @@ void* hs_new(const char* models, const char* connectors, uint64_t n, uint64_t re
     h->w.assign((size_t)net.n_wrows * n, 0u);
     h->ring_w.assign((size_t)(h->hn.ring_w_slots + 1) * n, 0u);
     h->ring_d.assign((size_t)(h->hn.ring_d_slots + 1) * n, 0.0);
+    h->mail.assign((size_t)(2u * (net.max_pending - net.pend_tile) + 1) * n, 0u);
     if (!trace_cap) trace_cap = 4096;
     if (trace_reps > n) trace_reps = (uint32_t)n;
     h->trace.assign((size_t)trace_reps * trace_cap + 1, SimbTraceRec());
@@ -146,6 +144,7 @@ void* hs_new(const char* models, const char* connectors, uint64_t n, uint64_t re
     st.w = h->w.data();
     st.ring_w = h->ring_w.data();
     st.ring_d = h->ring_d.data();
+    st.mail = h->mail.data();
     st.stride = n;
     st.n = n;
     st.rep_offset = rep_offset;
@@ -203,8 +202,13 @@ int hs_inject(void* hv, const char* tgt, const char* port, const char* content) 
         uint32_t& ctl = h->w[(size_t)net.wrow_ctl * h->n + r];
         uint32_t np = CTL_NPEND(ctl);
         if (np >= net.max_pending) return 32;
-        h->w[(size_t)(net.wrow_pend + 2 * np) * h->n + r] = code;
-        h->w[(size_t)(net.wrow_pend + 2 * np + 1) * h->n + r] = rw;
+        if (np < net.pend_tile) {
+            h->w[(size_t)(net.wrow_pend + 2 * np) * h->n + r] = code;
+            h->w[(size_t)(net.wrow_pend + 2 * np + 1) * h->n + r] = rw;
+        } else {
+            h->mail[(size_t)(2 * (np - net.pend_tile)) * h->n + r] = code;
+            h->mail[(size_t)(2 * (np - net.pend_tile) + 1) * h->n + r] = rw;
+        }
         ctl = CTL_MAKE(CTL_ERR(ctl), CTL_EPOCH(ctl), np + 1, 0);
     }
     return 0;
@@ -286,7 +290,12 @@ void hs_layout(void* hv, uint32_t out[8]) {
 void hs_pending_get(void* hv, uint64_t rep, uint32_t i, uint32_t out[2]) {
     HS* h = (HS*)hv;
     const SimbNetDesc& net = h->hn.desc;
-    out[0] = h->w[(size_t)(net.wrow_pend + 2 * i) * h->n + rep];
-    out[1] = h->w[(size_t)(net.wrow_pend + 2 * i + 1) * h->n + rep];
+    if (i < net.pend_tile) {
+        out[0] = h->w[(size_t)(net.wrow_pend + 2 * i) * h->n + rep];
+        out[1] = h->w[(size_t)(net.wrow_pend + 2 * i + 1) * h->n + rep];
+    } else {
+        out[0] = h->mail[(size_t)(2 * (i - net.pend_tile)) * h->n + rep];
+        out[1] = h->mail[(size_t)(2 * (i - net.pend_tile) + 1) * h->n + rep];
+    }
 }
 }
