@@ -224,7 +224,8 @@ struct Engine {
     // mailbox slot j: word 0 = content, word 1 = route.  The first net.pend_tile slots are rows of the
     // state tile (shared memory); deeper slots -- reached only by rare bursts -- stay in global memory.
     SIMB_HD uint32_t& mail_word(Lane& ln, uint32_t j, uint32_t which) {
-        if (j < net.pend_tile) return ln.W(net.wrow_pend + 2u * j + which);
+        // no overflow area when the whole mailbox fits the tile (folds away for baked shapes)
+        if (net.pend_tile == net.max_pending || j < net.pend_tile) return ln.W(net.wrow_pend + 2u * j + which);
         return st.mail[(uint64_t)(2u * (j - net.pend_tile) + which) * st.stride + ln.rep];
     }
 

@@ -262,6 +262,7 @@ int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool inst
         while (t < n) t <<= 1;
         if (t < tile) tile = t;
     }
+    if (dims->shape >= 0 && tile != SIMB_SHAPE_TILE) dims->shape = -1;  // baked-shape kernels assume the full tile width
     SmemPlan sp = smem_plan(net, tile, stages);
     if (sp.total > 227u * 1024u) return (int)cudaErrorInvalidConfiguration;
     dims->tile = tile;

@@ -108,14 +108,16 @@ __host__ __device__ constexpr int shape_tier() {  // model-count tier of a baked
     return SHAPE < 0 ? 0 : tiers[SHAPE < 0 ? 0 : SHAPE];
 }
 
-// One CTA = one tile of blockDim.x consecutive replications.
+// One CTA = one tile of blockDim.x consecutive replications.  Kernels of baked shapes are only launched
+// with SIMB_SHAPE_TILE threads, so their shared-memory row offsets are immediates.
+#define SIMB_SHAPE_TILE 256u
 template <int RNG, bool INSTR, int SHAPE>
 __global__ void __launch_bounds__(256, SIMB_MIN_BLOCKS)
 simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_constant__ SimbDevState st,
                  const __grid_constant__ SimbLaunch la, const uint32_t count_active) {
     const SimbNetDesc& net = shape_desc<SHAPE>(net_param);
     extern __shared__ __align__(128) unsigned char smem[];
-    const uint32_t tile = blockDim.x;
+    const uint32_t tile = SHAPE >= 0 ? SIMB_SHAPE_TILE : blockDim.x;
     const uint32_t tid = threadIdx.x;
     const SmemPlan sp = smem_plan(net, tile, 1);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + sp.off_bar);

@@ -253,13 +253,19 @@ def test_production_kernels_match_oracle(name, stat, shape, k):
 def test_shape_match_ignores_distribution_values():
     """A baked shape is the network STRUCTURE; rates are launch parameters."""
     models, conns = networks.mm1(lam_gen=0.7, lam_proc=1.1)
-    sim = _sim(models, conns, 64, seed=2, instrument=False, stat_model_id="processor-01")
+    sim = _sim(models, conns, 256, seed=2, instrument=False, stat_model_id="processor-01")
     assert sim.describe()["kernel_shape"] == "mm1"
     sim.step_n(500)
-    ref = oracle_api.OracleSimulation(models, conns).run_batch(2, 0, 64, threads=4, nsteps=500)
+    ref = oracle_api.OracleSimulation(models, conns).run_batch(2, 0, 256, threads=4, nsteps=500)
     assert (sim.get_events() == ref["events"]).all() and _close(sim.get_global_time(), ref["time"])
     other, conns2 = networks.mm1(capacity=9)
-    assert _sim(other, conns2, 8, instrument=False, stat_model_id="processor-01").describe()["kernel_shape"] == "generic"
+    assert _sim(other, conns2, 256, instrument=False, stat_model_id="processor-01").describe()["kernel_shape"] == "generic"
+    # baked-shape kernels assume the full 256-wide tile: small batches run on the generic interpreter
+    small = _sim(*networks.mm1(), 64, seed=2, instrument=False, stat_model_id="processor-01")
+    assert small.describe()["kernel_shape"] == "generic"
+    small.step_n(500)
+    ref = oracle_api.OracleSimulation(*networks.mm1()).run_batch(2, 0, 64, threads=4, nsteps=500)
+    assert (small.get_events() == ref["events"]).all() and _close(small.get_global_time(), ref["time"])
 
 
 # ---- BASELINE.json full size: 2^20 replications x step_until(10 000) ---------------------------------------
