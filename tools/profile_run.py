@@ -16,6 +16,8 @@ p.add_argument("--k", type=int, default=1)
 p.add_argument("--warm-until", type=float, default=300.0)
 p.add_argument("--launches", type=int, default=3)
 p.add_argument("--instrument", action="store_true")
+p.add_argument("--until-window", type=float, default=0.0,
+               help="profile a step_until(warm_until + window) call instead of step_n (use ncu -s to skip launches)")
 a = p.parse_args()
 
 import torch
@@ -29,7 +31,10 @@ sim = Simulation.post(models, conns, replications=a.replications, seed=42, steps
 sim.step_until(a.warm_until)
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
-sim.step_n(a.k * a.launches)
+if a.until_window > 0:
+    sim.step_until(a.warm_until + a.until_window)
+else:
+    sim.step_n(a.k * a.launches)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 c = sim.get_counters()
