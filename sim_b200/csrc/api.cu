@@ -60,9 +60,24 @@ int fail(int code, const std::string& msg) {
             return fail(SIMB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                \
     } while (0)
 
+// Device memory comes from the stream-ordered pool of the device (cudaMallocAsync) with the release
+// threshold raised once, so that re-posting a simulation (the replication idiom: post, run, read, destroy)
+// reuses the pool instead of going back to the driver for hundreds of MB every time.
+void ensure_pool(int device) {
+    static bool done[64] = {false};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done[device] = true;
+}
+
 void free_device(simb_sim* s) {
-    auto F = [](void* p) {
-        if (p) cudaFree(p);
+    cudaStream_t stream = s->stream;
+    auto F = [stream](void* p) {
+        if (p) cudaFreeAsync(p, stream);
     };
     F(s->st.d);
     F(s->st.w);
@@ -93,10 +108,10 @@ void free_device(simb_sim* s) {
 }
 
 template <class T>
-int dev_alloc(T** p, size_t count, bool zero) {
+int dev_alloc(cudaStream_t stream, T** p, size_t count, bool zero) {
     size_t bytes = (count ? count : 1) * sizeof(T);
-    CUDA_TRY(cudaMalloc((void**)p, bytes));
-    if (zero) CUDA_TRY(cudaMemset(*p, 0, bytes));
+    CUDA_TRY(cudaMallocAsync((void**)p, bytes, stream));
+    if (zero) CUDA_TRY(cudaMemsetAsync(*p, 0, bytes, stream));
     return 0;
 }
 
@@ -115,24 +130,24 @@ int build_device(simb_sim* s, uint32_t keep_mask, const simb_sim* old) {
     st.rep_offset = s->cfg.replication_offset;
     st.seed = s->cfg.seed;
     int r;
-    if ((r = dev_alloc(&st.d, (size_t)net.n_drows * stride, false))) return r;
-    if ((r = dev_alloc(&st.w, (size_t)net.n_wrows * stride, false))) return r;
-    if ((r = dev_alloc(&st.ring_w, (size_t)(s->hn.ring_w_slots + 1) * stride, true))) return r;
-    if ((r = dev_alloc(&st.ring_d, (size_t)(s->hn.ring_d_slots + 1) * stride, true))) return r;
-    if ((r = dev_alloc(&st.mail, (size_t)(2u * (net.max_pending - net.pend_tile) + 1) * stride, true))) return r;
+    if ((r = dev_alloc(s->stream, &st.d, (size_t)net.n_drows * stride, false))) return r;
+    if ((r = dev_alloc(s->stream, &st.w, (size_t)net.n_wrows * stride, false))) return r;
+    if ((r = dev_alloc(s->stream, &st.ring_w, (size_t)(s->hn.ring_w_slots + 1) * stride, true))) return r;
+    if ((r = dev_alloc(s->stream, &st.ring_d, (size_t)(s->hn.ring_d_slots + 1) * stride, true))) return r;
+    if ((r = dev_alloc(s->stream, &st.mail, (size_t)(2u * (net.max_pending - net.pend_tile) + 1) * stride, true))) return r;
     st.trace_reps = 0;
     st.trace_cap = 0;
     if (s->instrument) {
         st.trace_reps = (uint32_t)std::min<uint64_t>(s->cfg.trace_replications, n);
         st.trace_cap = s->cfg.trace_capacity ? s->cfg.trace_capacity : 4096;
-        if ((r = dev_alloc(&st.trace, (size_t)st.trace_reps * st.trace_cap, true))) return r;
-        if ((r = dev_alloc(&st.trace_count, (size_t)stride, true))) return r;
-        if ((r = dev_alloc(&st.conn_count, (size_t)net.n_connectors + 1, true))) return r;
-        if ((r = dev_alloc(&st.record_count, (size_t)net.n_models * ACT_COUNT, true))) return r;
+        if ((r = dev_alloc(s->stream, &st.trace, (size_t)st.trace_reps * st.trace_cap, true))) return r;
+        if ((r = dev_alloc(s->stream, &st.trace_count, (size_t)stride, true))) return r;
+        if ((r = dev_alloc(s->stream, &st.conn_count, (size_t)net.n_connectors + 1, true))) return r;
+        if ((r = dev_alloc(s->stream, &st.record_count, (size_t)net.n_models * ACT_COUNT, true))) return r;
     }
-    if ((r = dev_alloc(&st.totals, 4, true))) return r;
-    if ((r = dev_alloc(&s->d_dinit, net.n_drows, false))) return r;
-    if ((r = dev_alloc(&s->d_winit, net.n_wrows, false))) return r;
+    if ((r = dev_alloc(s->stream, &st.totals, 4, true))) return r;
+    if ((r = dev_alloc(s->stream, &s->d_dinit, net.n_drows, false))) return r;
+    if ((r = dev_alloc(s->stream, &s->d_winit, net.n_wrows, false))) return r;
     CUDA_TRY(cudaMemcpy(s->d_dinit, s->hn.d_init.data(), net.n_drows * sizeof(double), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(s->d_winit, s->hn.w_init.data(), net.n_wrows * sizeof(uint32_t), cudaMemcpyHostToDevice));
     s->n_pre = (uint32_t)s->hn.ring_preload.size();
@@ -142,15 +157,15 @@ int build_device(simb_sim* s, uint32_t keep_mask, const simb_sim* old) {
             slots[i] = s->hn.ring_preload[i].slot;
             vals[i] = s->hn.ring_preload[i].value;
         }
-        if ((r = dev_alloc(&s->d_pre_slots, s->n_pre, false))) return r;
-        if ((r = dev_alloc(&s->d_pre_vals, s->n_pre, false))) return r;
+        if ((r = dev_alloc(s->stream, &s->d_pre_slots, s->n_pre, false))) return r;
+        if ((r = dev_alloc(s->stream, &s->d_pre_vals, s->n_pre, false))) return r;
         CUDA_TRY(cudaMemcpy(s->d_pre_slots, slots.data(), s->n_pre * 4, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(s->d_pre_vals, vals.data(), s->n_pre * 4, cudaMemcpyHostToDevice));
     }
     s->n_red_blocks = engine_reduce_blocks(n);
-    if ((r = dev_alloc(&s->d_psum, s->n_red_blocks, true))) return r;
-    if ((r = dev_alloc(&s->d_pcnt, s->n_red_blocks, true))) return r;
-    if ((r = dev_alloc(&s->d_overflow, 1, true))) return r;
+    if ((r = dev_alloc(s->stream, &s->d_psum, s->n_red_blocks, true))) return r;
+    if ((r = dev_alloc(s->stream, &s->d_pcnt, s->n_red_blocks, true))) return r;
+    if ((r = dev_alloc(s->stream, &s->d_overflow, 1, true))) return r;
     CUDA_TRY(engine_launch_init(net, st, s->d_dinit, s->d_winit, s->d_pre_slots, s->d_pre_vals, s->n_pre, s->rng_kind,
                                 s->instrument, keep_mask, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -329,6 +344,7 @@ int simb_post_json(const char* models_json, const char* connectors_json, const s
         return bail(fail(SIMB_ERR_CUDA, "cudaStreamCreate failed"));
     if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess)
         return bail(fail(SIMB_ERR_CUDA, "cudaEventCreate failed"));
+    ensure_pool(config->device);
     e = build_device(s, 0, nullptr);
     if (e) return bail(e);
     *out = s;
@@ -440,6 +456,7 @@ int simb_destroy(simb_sim* s) {
     if (!s) return 0;
     cudaSetDevice(s->cfg.device);
     free_device(s);
+    if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);

@@ -308,11 +308,14 @@ struct Engine {
     }
     // Continuous::random_variate (random_variable.rs:69-89); parameter errors surface per draw
     SIMB_HD double sample_continuous(Lane& ln, const SimbModelDesc& md, const SimbModelDesc& pd) {
+        return sample_continuous_kind(ln, md.dist_kind, pd);
+    }
+    SIMB_HD double sample_continuous_kind(Lane& ln, uint32_t dist_kind, const SimbModelDesc& pd) {
         if (pd.dist_err) {
             if (!ln.err) ln.err = pd.dist_err;
             return 0.0;
         }
-        switch (md.dist_kind) {
+        switch (dist_kind) {
             case DK_EXP:
                 return sample_exp1(ln) * pd.p0;  // Exp1 * lambda_inverse
             case DK_NORMAL: {
@@ -386,7 +389,32 @@ struct Engine {
     }
     SIMB_HD void flush_draws(Lane& ln) {
         if (STATIC) {
-            // literal model list: one (foldable) sampling site per model that can draw
+            // When every drawing model of the baked shape uses the same distribution family (folds to a
+            // constant), ONE sampling site serves all debts: the model index only selects the parameters.
+            uint32_t kind = DK_NONE;
+            bool same = true;
+#define SIMB_KIND_ONE(m)                                                                  \
+    if ((m) < net.n_models && net.models[m].dist_kind != DK_NONE) {                       \
+        if (kind == DK_NONE) kind = net.models[m].dist_kind;                              \
+        else if (kind != net.models[m].dist_kind) same = false;                           \
+    }
+            SIMB_FOR_MODELS(SM, SIMB_KIND_ONE);
+#undef SIMB_KIND_ONE
+            if (same && kind != DK_NONE) {
+                while (ln.dm_int | ln.dm_ext) {
+                    uint32_t m;
+                    if (ln.dm_int) {
+                        m = (uint32_t)lowest_bit(ln.dm_int);
+                        ln.dm_int &= ln.dm_int - 1u;
+                    } else {
+                        m = (uint32_t)lowest_bit(ln.dm_ext);
+                        ln.dm_ext &= ln.dm_ext - 1u;
+                    }
+                    ln.D(net.drow_until + m) = sample_continuous_kind(ln, kind, par.models[m]);
+                }
+                return;
+            }
+            // otherwise: literal model list, one (foldable) sampling site per model that can draw
 #define SIMB_FLUSH_INT(m)                                                                            \
     if ((m) < net.n_models && net.models[m].dist_kind != DK_NONE && (ln.dm_int & (1u << (m)))) {     \
         ln.dm_int &= ~(1u << (m));                                                                   \
