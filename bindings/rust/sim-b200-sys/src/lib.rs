@@ -24,6 +24,8 @@ pub struct simb_config {
     pub trace_capacity: u32,
     pub reserved0: u32,
     pub stat_model_id: *const c_char,
+    pub batch_warmup: u32,
+    pub batch_size: u32,
 }
 
 #[repr(C)]

@@ -89,6 +89,8 @@ typedef struct simb_config {
     uint32_t trace_capacity;     /* events kept per traced replication (0 -> 4096) */
     uint32_t reserved0;
     const char* stat_model_id;   /* Processor whose per-job waiting time is accumulated, or NULL */
+    uint32_t batch_warmup;       /* streaming batch means of that statistic: jobs deleted at the start ... */
+    uint32_t batch_size;         /* ... and jobs per batch (0 = off); at most 30 batches per replication */
 } simb_config;
 
 typedef struct simb_sim simb_sim; /* opaque handle: owns all device memory of one batched Simulation */
@@ -228,6 +230,13 @@ int simb_intern_content(simb_sim* sim, const char* content, uint32_t* out);
  * mod.rs:205-345, t_score t_scores.rs:9-30, usize_sqrt utils/mod.rs:84-92).
  */
 int simb_get_wait_stats(simb_sim* sim, double* sum, uint32_t* count, uint64_t capacity);
+/* per-replication streaming batch means (simb_config.batch_size > 0): mean and population variance of the
+ * completed batch means and their number (<= 30) -- the steady-state statistic of BASELINE config 3 with a
+ * fixed budget instead of SteadyStateOutput's series-dependent deletion point (mod.rs:224-260) */
+int simb_get_batch_means(simb_sim* sim, double* mean, double* variance, uint32_t* batches, uint64_t capacity);
+/* SteadyStateOutput::confidence_interval_mean given (batches_mean, batches_variance, batch_count): note the
+ * reference's asymmetric degrees of freedom (mod.rs:327 vs :330) */
+int simb_oa_batch_means_ci(double mean, double variance, uint64_t batch_count, double alpha, simb_ci* out);
 int simb_stat_partial(simb_sim* sim, double* sum_of_means, uint64_t* n);
 int simb_stat_partial_sqdev(simb_sim* sim, double mean, double* sum_sqdev);
 int simb_independent_sample_ci(simb_sim* sim, double alpha, simb_ci* out);

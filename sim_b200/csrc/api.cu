@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -302,11 +303,15 @@ int simb_device_count(int* count) {
 int simb_post_json(const char* models_json, const char* connectors_json, const simb_config* config, simb_sim** out) {
     if (!out || !config || !models_json || !connectors_json) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
-    if (config->struct_size != sizeof(simb_config)) return fail(SIMB_ERR_INVALID_ARGUMENT, "simb_config.struct_size mismatch");
+    // ABI evolution: version-1 callers pass the struct without the two trailing batch-means fields
+    const size_t v1_size = offsetof(simb_config, batch_warmup);
+    if (config->struct_size != sizeof(simb_config) && config->struct_size != v1_size)
+        return fail(SIMB_ERR_INVALID_ARGUMENT, "simb_config.struct_size mismatch");
     if (config->replications == 0) return fail(SIMB_ERR_INVALID_ARGUMENT, "replications must be > 0");
     if (config->rng_kind < 0 || config->rng_kind > 2) return fail(SIMB_ERR_INVALID_ARGUMENT, "unknown rng_kind");
     simb_sim* s = new simb_sim();
-    s->cfg = *config;
+    std::memset(&s->cfg, 0, sizeof s->cfg);
+    std::memcpy(&s->cfg, config, config->struct_size);
     if (config->stat_model_id) s->stat_model_id = config->stat_model_id;
     s->cfg.stat_model_id = nullptr;
     s->instrument = (config->flags & SIMB_FLAG_INSTRUMENT) != 0;
@@ -317,6 +322,8 @@ int simb_post_json(const char* models_json, const char* connectors_json, const s
     s->opt.instrument = s->instrument;
     s->opt.rng_kind = s->rng_kind;
     s->opt.stat_model_id = s->stat_model_id;
+    s->opt.batch_warmup = s->cfg.batch_warmup;
+    s->opt.batch_size = s->cfg.batch_size;
     std::string err;
     int e = lower_network(models_json, connectors_json, s->opt, &s->hn, &err);
     if (e) {
@@ -769,6 +776,40 @@ int simb_get_wait_stats(simb_sim* s, double* sum, uint32_t* count, uint64_t capa
     int e = 0;
     if (sum && (e = copy_row_d(s, s->hn.desc.drow_wait, sum, capacity))) return e;
     if (count && (e = copy_row_w(s, s->hn.desc.wrow_waitn, count, capacity))) return e;
+    return 0;
+}
+int simb_get_batch_means(simb_sim* s, double* mean, double* variance, uint32_t* batches, uint64_t capacity) {
+    if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");
+    const SimbNetDesc& net = s->hn.desc;
+    if (s->hn.stat_model < 0 || net.bm_size == 0) return fail(SIMB_ERR_INVALID_ARGUMENT, "batch means were not configured (simb_config.batch_size)");
+    if (capacity < s->st.n) return fail(SIMB_ERR_INVALID_ARGUMENT, "output buffer smaller than the replication count");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    std::vector<double> sm(s->st.n), sq(s->st.n);
+    std::vector<uint32_t> jobs(s->st.n);
+    int e;
+    if ((e = copy_row_d(s, net.drow_bm + 1, sm.data(), s->st.n))) return e;
+    if ((e = copy_row_d(s, net.drow_bm + 2, sq.data(), s->st.n))) return e;
+    if ((e = copy_row_w(s, net.wrow_waitn, jobs.data(), s->st.n))) return e;
+    for (uint64_t r = 0; r < s->st.n; r++) {
+        uint32_t b = jobs[r] > net.bm_warmup ? (jobs[r] - net.bm_warmup) / net.bm_size : 0u;
+        if (b > SIMB_MAX_BATCHES) b = SIMB_MAX_BATCHES;
+        const double m = b ? sm[r] / (double)b : std::nan("");
+        if (batches) batches[r] = b;
+        if (mean) mean[r] = m;
+        if (variance) variance[r] = b ? sq[r] / (double)b - m * m : std::nan("");  // population variance, one pass
+    }
+    return 0;
+}
+int simb_oa_batch_means_ci(double mean, double variance, uint64_t batch_count, double alpha, simb_ci* out) {
+    if (!out) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    double lo, hi;
+    int e = oa::batch_means_ci(mean, variance, batch_count, alpha, &lo, &hi);
+    if (e) return fail(e, "t_score: unsupported alpha or no completed batch");
+    out->mean = mean;
+    out->variance = variance;
+    out->lower = lo;
+    out->upper = hi;
+    out->n = batch_count;
     return 0;
 }
 static int stat_reduce(simb_sim* s, int which, double mean, double* sum, uint64_t* n) {

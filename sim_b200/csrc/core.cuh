@@ -510,6 +510,30 @@ struct Engine {
         }
     }
 
+    // ---- statistics of the MF_STAT processor (output_analysis on the device) --------------------------
+    // One waiting time (Processing Start - Arrival, the series of sim/tests/web.rs:571-597) in service-start
+    // order: running sum + count for the IID mean, and -- when configured -- streaming batch means with a
+    // fixed warm-up deletion and fixed batch size, at most 30 batches (a defined deviation from
+    // SteadyStateOutput, which needs the whole series for its deletion point).
+    SIMB_HD void wait_sample(Lane& ln, double wt) {
+        const uint32_t j = ln.W(net.wrow_waitn);
+        ln.W(net.wrow_waitn) = j + 1u;
+        ln.D(net.drow_wait) += wt;
+        if (net.bm_size != 0u && j >= net.bm_warmup) {
+            const uint32_t k = j - net.bm_warmup;
+            if (k / net.bm_size < SIMB_MAX_BATCHES) {
+                double acc = ln.D(net.drow_bm) + wt;
+                if ((k + 1u) % net.bm_size == 0u) {  // batch complete: fold its mean into the sums
+                    const double mean = acc / (double)net.bm_size;
+                    ln.D(net.drow_bm + 1) += mean;
+                    ln.D(net.drow_bm + 2) += mean * mean;
+                    acc = 0.0;
+                }
+                ln.D(net.drow_bm) = acc;
+            }
+        }
+    }
+
     // ---- FIFO ring helpers: queue word = head(16) | len(16) ----------------------------------------
     SIMB_HD uint32_t ring_slot(const SimbModelDesc& md, uint32_t head, uint32_t i) {
         uint32_t s = head + i;
@@ -622,10 +646,7 @@ struct Engine {
                     if (!defer_draw(ln, m, md, true)) break;  // until_next_event = service time draw
                     record<INSTR>(ln, m, ACT_ARRIVAL, content);
                     record<INSTR>(ln, m, ACT_PROCESSING_START, content);
-                    if (md.flags & MF_STAT) {
-                        ln.D(net.drow_wait) += ln.time - ln.time;  // Processing Start - Arrival = 0 here
-                        ln.W(net.wrow_waitn) += 1u;
-                    }
+                    if (md.flags & MF_STAT) wait_sample(ln, ln.time - ln.time);  // Processing Start - Arrival = 0 here
                 } else {  // add_job :119-126
                     record<INSTR>(ln, m, ACT_ARRIVAL, content);
                 }
@@ -841,10 +862,7 @@ struct Engine {
                     ln.set_phase(m, 1);  // process_next :160-175
                     if (!defer_draw(ln, m, md, false)) break;
                     record<INSTR>(ln, m, ACT_PROCESSING_START, RW(ln, md.ring_w0 + head));
-                    if (md.flags & MF_STAT) {
-                        ln.D(net.drow_wait) += ln.time - RD(ln, md.ring_d + head);
-                        ln.W(net.wrow_waitn) += 1u;
-                    }
+                    if (md.flags & MF_STAT) wait_sample(ln, ln.time - RD(ln, md.ring_d + head));
                     break;
                 }
                 if (len == 0) { ln.err = 34; break; }  // queue.remove(0) on an empty Vec panics

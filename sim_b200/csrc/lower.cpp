@@ -570,6 +570,12 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
     net.drow_until = dr;
     dr += (uint16_t)net.n_models;
     if (hn.stat_model >= 0) net.drow_wait = dr++;
+    if (hn.stat_model >= 0 && opt.batch_size > 0) {
+        net.drow_bm = dr;
+        dr += 3;
+        net.bm_warmup = opt.batch_warmup;
+        net.bm_size = opt.batch_size;
+    }
     net.wrow_ctl = wr++;
     net.wrow_rng = wr;
     wr += (opt.rng_kind == 1) ? 4 : 1;

@@ -15,6 +15,7 @@ struct LowerOptions {
     bool instrument = false;
     int rng_kind = 0;
     std::string stat_model_id;
+    uint32_t batch_warmup = 0, batch_size = 0;  // streaming batch means of the statistic (batch_size 0 = off)
 };
 
 struct HostModel {

@@ -12,6 +12,7 @@
 #define SIMB_MAX_WEIGHTS 64     /* total cumulative-weight entries over all ExclusiveGateways */
 #define SIMB_MAX_NAMES 255      /* content prefix / literal intern table */
 #ifndef SIMB_MAIL_TILE_SLOTS
+#define SIMB_MAX_BATCHES 30      /* Schmeiser's k = 30 (sim/src/output_analysis/mod.rs:246-253) */
 #define SIMB_MAIL_TILE_SLOTS 8  /* mailbox slots staged in shared memory; deeper slots (rare bursts) stay in HBM */
 #endif
 
@@ -73,11 +74,14 @@ struct SimbRoute {
 
 struct SimbNetDesc {
     uint32_t n_models, n_routes, n_connectors, max_pending;
+    uint32_t bm_warmup, bm_size;  // streaming batch means of the MF_STAT waiting times: jobs deleted at the
+                                  // start, jobs per batch (0 = off); at most SIMB_MAX_BATCHES batches
     // state tile layout (rows of N replications each)
     uint16_t n_drows, n_wrows;
     uint16_t drow_time;     // global_time
     uint16_t drow_until;    // until_next_event of model m = drow_until + m
     uint16_t drow_wait;     // waiting-time sum of the MF_STAT processor (0 if none)
+    uint16_t drow_bm;       // 3 rows: running sum of the open batch, sum of batch means, sum of squared batch means
     uint16_t wrow_ctl;      // err(8) | epoch(8) | npend(8) | absent(1)
     uint16_t wrow_rng;      // draw index (Philox/external) or 4 words of PCG state
     uint16_t wrow_steps, wrow_events;

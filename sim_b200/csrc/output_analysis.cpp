@@ -66,6 +66,21 @@ int independent_ci(double mean, double variance, uint64_t n, double alpha, doubl
     return 0;
 }
 
+int batch_means_ci(double mean, double variance, uint64_t batches, double alpha, double* lower, double* upper) {
+    if (batches == 0) return ERR_PREREQ;
+    if (batches == 1) {  // mod.rs:317-322
+        *lower = *upper = mean;
+        return 0;
+    }
+    double t_lo, t_hi;  // df = batch_count below, batch_count - 1 above (mod.rs:327 vs :330)
+    int e = t_score(alpha, batches, &t_lo);
+    if (e) return e;
+    if ((e = t_score(alpha, batches - 1, &t_hi))) return e;
+    *lower = mean - t_lo * std::sqrt(variance) / std::sqrt((double)batches);
+    *upper = mean + t_hi * std::sqrt(variance) / std::sqrt((double)batches);
+    return 0;
+}
+
 int steady_state(const double* x, uint64_t n, double alpha, SteadyState* out) {
     if (n < 2) return ERR_PANIC;  // `len() - 2` underflows (mod.rs:227)
     // set_to_fixed_budget, mod.rs:224-260: backward scan; note the operator precedence at :233

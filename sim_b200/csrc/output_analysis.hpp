@@ -15,6 +15,9 @@ void mean_variance(const double* points, uint64_t n, double* mean, double* varia
 // IndependentSample::confidence_interval_mean given (mean, variance, n)
 int independent_ci(double mean, double variance, uint64_t n, double alpha, double* lower, double* upper);
 
+// SteadyStateOutput::confidence_interval_mean from (batches_mean, batches_variance, batch_count)
+int batch_means_ci(double mean, double variance, uint64_t batch_count, double alpha, double* lower, double* upper);
+
 struct SteadyState {
     uint64_t deletion_point, batch_size, batch_count;
     double mean, variance, lower, upper;

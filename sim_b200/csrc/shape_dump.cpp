@@ -39,9 +39,9 @@ int main(int argc, char** argv) {
         return 1;
     }
     const SimbNetDesc& n = hn.desc;
-    std::printf("{%uu, %uu, %uu, %uu,\n", n.n_models, n.n_routes, n.n_connectors, n.max_pending);
-    std::printf(" %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u,\n", n.n_drows, n.n_wrows, n.drow_time,
-                n.drow_until, n.drow_wait, n.wrow_ctl, n.wrow_rng, n.wrow_steps, n.wrow_events, n.wrow_hash, n.wrow_phase,
+    std::printf("{%uu, %uu, %uu, %uu, %uu, %uu,\n", n.n_models, n.n_routes, n.n_connectors, n.max_pending, n.bm_warmup, n.bm_size);
+    std::printf(" %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u,\n", n.n_drows, n.n_wrows, n.drow_time,
+                n.drow_until, n.drow_wait, n.drow_bm, n.wrow_ctl, n.wrow_rng, n.wrow_steps, n.wrow_events, n.wrow_hash, n.wrow_phase,
                 n.n_phase_words, n.wrow_pend, n.wrow_waitn, n.uses_exp, n.uses_normal, n.wrow_dmask, n.pend_tile);
     std::printf(" {\n");
     for (int i = 0; i < SIMB_MAX_MODELS; i++) {

@@ -79,6 +79,13 @@ class SteadyStateOutput:
         return self._run(0.05).mean
 
 
+def batch_means_confidence_interval(mean: float, variance: float, batch_count: int, alpha: float) -> ConfidenceInterval:
+    """``SteadyStateOutput::confidence_interval_mean`` (mod.rs:302-333) from batch statistics."""
+    ci = _CI()
+    _check(load_library().simb_oa_batch_means_ci(float(mean), float(variance), int(batch_count), float(alpha), C.byref(ci)))
+    return ConfidenceInterval(ci.lower, ci.upper)
+
+
 def t_score(alpha: float, df: int) -> float:
     """t_scores.rs:9-30"""
     out = C.c_double()

@@ -38,7 +38,7 @@ class SimbConfig(C.Structure):
         ("replication_offset", C.c_uint64), ("seed", C.c_uint64), ("rng_kind", C.c_int32), ("device", C.c_int32),
         ("steps_per_launch", C.c_uint32), ("queue_capacity", C.c_uint32), ("max_pending", C.c_uint32),
         ("trace_replications", C.c_uint32), ("trace_capacity", C.c_uint32), ("reserved0", C.c_uint32),
-        ("stat_model_id", C.c_char_p),
+        ("stat_model_id", C.c_char_p), ("batch_warmup", C.c_uint32), ("batch_size", C.c_uint32),
     ]
 
 
@@ -116,6 +116,8 @@ def load_library() -> C.CDLL:
     L.simb_render_content.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint64]
     L.simb_intern_content.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint32)]
     L.simb_get_wait_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.simb_get_batch_means.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.simb_oa_batch_means_ci.argtypes = [C.c_double, C.c_double, C.c_uint64, C.c_double, C.POINTER(_CI)]
     L.simb_stat_partial.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.simb_stat_partial_sqdev.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double)]
     L.simb_independent_sample_ci.argtypes = [C.c_void_p, C.c_double, C.POINTER(_CI)]
@@ -172,7 +174,8 @@ class Simulation:
     def post_json(cls, models_json: str, connectors_json: str, replications: int = 1, *, seed: int = 42,
                   rng_kind: int = RNG_PHILOX, replication_offset: int = 0, device: int = 0, steps_per_launch: int = 0,
                   queue_capacity: int = 0, max_pending: int = 0, instrument: bool = False, trace_replications: int = 0,
-                  trace_capacity: int = 0, stat_model_id: Optional[str] = None) -> "Simulation":
+                  trace_capacity: int = 0, stat_model_id: Optional[str] = None, batch_warmup: int = 0,
+                  batch_size: int = 0) -> "Simulation":
         """``WebSimulation::post_json`` (web.rs:23-31) form of ``post``."""
         L = load_library()
         cfg = SimbConfig()
@@ -189,6 +192,8 @@ class Simulation:
         cfg.trace_replications = trace_replications
         cfg.trace_capacity = trace_capacity
         cfg.stat_model_id = stat_model_id.encode() if stat_model_id else None
+        cfg.batch_warmup = batch_warmup
+        cfg.batch_size = batch_size
         h = C.c_void_p()
         _check(L.simb_post_json(models_json.encode(), connectors_json.encode(), C.byref(cfg), C.byref(h)))
         return cls(h, replications, models_json, connectors_json)
@@ -346,6 +351,15 @@ class Simulation:
         n = np.zeros(self.replications, np.uint32)
         _check(load_library().simb_get_wait_stats(self._h, s.ctypes.data, n.ctypes.data, self.replications))
         return s, n
+
+    def get_batch_means(self):
+        """Per-replication streaming batch means of the waiting times (batch_size > 0): (mean of the batch
+        means, their population variance, number of completed batches <= 30)."""
+        m = np.zeros(self.replications, np.float64)
+        v = np.zeros(self.replications, np.float64)
+        b = np.zeros(self.replications, np.uint32)
+        _check(load_library().simb_get_batch_means(self._h, m.ctypes.data, v.ctypes.data, b.ctypes.data, self.replications))
+        return m, v, b
 
     def stat_partial(self):
         s = C.c_double()

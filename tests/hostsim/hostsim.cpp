@@ -87,7 +87,8 @@ void dispatch(HS* h, int mode, uint64_t k, double until) {
 extern "C" {
 void* hs_new(const char* models, const char* connectors, uint64_t n, uint64_t rep_offset, uint64_t seed, int rng_kind,
              int instrument, const char* stat_model_id, uint32_t queue_capacity, uint32_t max_pending,
-             uint32_t trace_reps, uint32_t trace_cap, char* errbuf, int errlen, int* status) {
+             uint32_t trace_reps, uint32_t trace_cap, uint32_t batch_warmup, uint32_t batch_size, char* errbuf, int errlen,
+             int* status) {
     HS* h = new HS();
     LowerOptions opt;
     opt.queue_capacity = queue_capacity;
@@ -95,6 +96,8 @@ void* hs_new(const char* models, const char* connectors, uint64_t n, uint64_t re
     opt.instrument = instrument != 0;
     opt.rng_kind = rng_kind;
     if (stat_model_id) opt.stat_model_id = stat_model_id;
+    opt.batch_warmup = batch_warmup;
+    opt.batch_size = batch_size;
     std::string err;
     int e = lower_network(models, connectors, opt, &h->hn, &err);
     if (status) *status = e;
@@ -247,6 +250,15 @@ void hs_get_wait(void* hv, double* sum, uint32_t* n) {
     for (uint64_t r = 0; r < h->n; r++) {
         sum[r] = h->d[(size_t)net.drow_wait * h->n + r];
         n[r] = h->w[(size_t)net.wrow_waitn * h->n + r];
+    }
+}
+void hs_get_batch(void* hv, double* sum_means, double* sum_sq, double* open_sum) {
+    HS* h = (HS*)hv;
+    const SimbNetDesc& net = h->hn.desc;
+    for (uint64_t r = 0; r < h->n; r++) {
+        open_sum[r] = h->d[(size_t)net.drow_bm * h->n + r];
+        sum_means[r] = h->d[(size_t)(net.drow_bm + 1) * h->n + r];
+        sum_sq[r] = h->d[(size_t)(net.drow_bm + 2) * h->n + r];
     }
 }
 void hs_get_conn_counts(void* hv, uint64_t* out) {

@@ -26,14 +26,14 @@ def to_json(models, connectors):
 
 class HostSim:
     def __init__(self, models, connectors, n=1, rep_offset=0, seed=42, rng_kind=0, instrument=True, stat_model_id=None,
-                 queue_capacity=0, max_pending=0, trace_reps=0, trace_cap=0, raw_json=None):
+                 queue_capacity=0, max_pending=0, trace_reps=0, trace_cap=0, raw_json=None, batch_warmup=0, batch_size=0):
         self.L = lib()
         mj, cj = raw_json if raw_json else to_json(models, connectors)
         err = C.create_string_buffer(512)
         status = C.c_int()
         h = self.L.hs_new(mj.encode(), cj.encode(), C.c_uint64(n), C.c_uint64(rep_offset), C.c_uint64(seed), rng_kind,
                           int(instrument), stat_model_id.encode() if stat_model_id else None, queue_capacity,
-                          max_pending, trace_reps, trace_cap, err, 512, C.byref(status))
+                          max_pending, trace_reps, trace_cap, batch_warmup, batch_size, err, 512, C.byref(status))
         self.status = status.value
         self.error = err.value.decode()
         self.h = C.c_void_p(h) if h else None
@@ -111,6 +111,13 @@ class HostSim:
         n = np.zeros(self.n, np.uint32)
         self.L.hs_get_wait(self.h, s.ctypes.data_as(C.POINTER(C.c_double)), n.ctypes.data_as(C.POINTER(C.c_uint32)))
         return s, n
+
+    def batch(self):
+        """(sum of batch means, sum of squared batch means, running sum of the open batch) per replication"""
+        a, b, c = (np.zeros(self.n, np.float64) for _ in range(3))
+        p = lambda x: x.ctypes.data_as(C.POINTER(C.c_double))
+        self.L.hs_get_batch(self.h, p(a), p(b), p(c))
+        return a, b, c
 
     def conn_counts(self):
         out = np.zeros(max(1, self.n_connectors), np.uint64)

@@ -375,3 +375,42 @@ def test_steady_state_output_on_device_records():
         ci = ss.confidence_interval_mean(0.05)
         assert (ss.deletion_point, ss.batch_size, ss.batch_count) == (ref["deletion_point"], ref["batch_size"], ref["batch_count"])
         assert abs(ci.lower() - ref["lower"]) < 1e-9 and abs(ci.upper() - ref["upper"]) < 1e-9
+
+
+def test_streaming_batch_means_on_device():
+    """BASELINE config 3: tandem network, steady-state batch means (fixed warm-up, fixed batch size, <= 30
+    batches) accumulated per replication on the device; checked against the oracle's record series and the
+    SteadyStateOutput-style interval of the host analysis."""
+    from sim_b200 import output_analysis as oa
+    models, conns = networks.tandem()
+    rec = networks.tandem()[0]
+    for m in rec:
+        m.inner.store_records = True
+    warm, size, n, until = 40, 25, 2048, 1500.0
+    sim = _sim(models, conns, n, seed=13, instrument=False, stat_model_id="processor-3", batch_warmup=warm,
+               batch_size=size)
+    sim.step_until(until)
+    mean, var, batches = sim.get_batch_means()
+    assert (batches == 30).mean() > 0.95 and (batches <= 30).all()
+    for r in (0, 7, 1000, 2047):
+        o = oracle_api.OracleSimulation(rec, conns)
+        o.set_rng_philox(13, r)
+        assert o.step_until(until, collect=False)[0] == 0
+        arrival, waits = {}, []
+        for t, action, subject in o.get_records("processor-3")[1]:
+            if action == "Arrival":
+                arrival[subject] = t
+            elif action == "Processing Start":
+                waits.append(t - arrival.pop(subject))
+        w = waits[warm:]
+        bm = [sum(w[b * size:(b + 1) * size]) / size for b in range(min(len(w) // size, 30))]
+        assert batches[r] == len(bm)
+        m = sum(bm) / len(bm)
+        v = sum((x - m) ** 2 for x in bm) / len(bm)
+        assert abs(mean[r] - m) <= 1e-9 * max(1.0, abs(m)) and abs(var[r] - v) <= 1e-7 * max(1.0, v)
+        ci = oa.batch_means_confidence_interval(mean[r], var[r], int(batches[r]), 0.05)
+        assert ci.lower() < mean[r] < ci.upper()
+    # replications are independent: the grand mean of the replication estimates has a tight IID interval
+    ok = batches == 30
+    grand = oa.IndependentSample.post(mean[ok]).confidence_interval_mean(0.05)
+    assert grand.half_width() < 0.05 * abs(mean[ok].mean())

@@ -227,3 +227,54 @@ def test_baked_shapes_are_up_to_date():
     before = open(path).read()
     subprocess.check_call([sys.executable, os.path.join(root, "tools", "gen_shapes.py")], stdout=subprocess.DEVNULL)
     assert open(path).read() == before
+
+
+def _batch_means_from_waits(waits, warmup, size, max_batches=30):
+    """streaming batch means exactly as the device accumulates them (sim_b200/csrc/core.cuh wait_sample)"""
+    means = []
+    w = waits[warmup:]
+    for b in range(min(len(w) // size, max_batches)):
+        acc = 0.0
+        for x in w[b * size:(b + 1) * size]:
+            acc += x
+        means.append(acc / size)
+    return means
+
+
+def _oracle_waits(models, conns, seed, rep, until, model_id):
+    o = O.OracleSimulation(models, conns)
+    o.set_rng_philox(seed, rep)
+    assert o.step_until(until, collect=False)[0] == 0
+    arrival, waits = {}, []
+    for t, action, subject in o.get_records(model_id)[1]:
+        if action == "Arrival":
+            arrival[subject] = t
+        elif action == "Processing Start":
+            waits.append(t - arrival.pop(subject))
+    return waits
+
+
+def test_streaming_batch_means_match_the_oracle_series():
+    """BASELINE config 3 statistic: per-replication batch means with a fixed warm-up and batch size,
+    accumulated on the fly, equal the batch means of the oracle's waiting-time series."""
+    models, conns = networks.tandem()
+    rec = networks.tandem()[0]
+    for m in rec:
+        m.inner.store_records = True
+    warm, size = 40, 25
+    hs = H.HostSim(models, conns, n=4, seed=13, stat_model_id="processor-3", batch_warmup=warm, batch_size=size)
+    hs.set_reload_every(7)
+    hs.step_until(1500.0)
+    sm, sq, open_sum = hs.batch()
+    _, cnt = hs.wait()
+    for r in range(4):
+        waits = _oracle_waits(rec, conns, 13, r, 1500.0, "processor-3")
+        assert len(waits) == cnt[r]
+        means = _batch_means_from_waits(waits, warm, size)
+        assert len(means) == 30  # the horizon is long enough to fill Schmeiser's 30 batches
+        assert abs(sm[r] - sum(means)) <= 1e-9 * abs(sum(means))
+        assert abs(sq[r] - sum(x * x for x in means)) <= 1e-9 * sum(x * x for x in means)
+    short = H.HostSim(models, conns, n=2, seed=13, stat_model_id="processor-3", batch_warmup=warm, batch_size=size)
+    short.step_until(60.0)  # fewer than warm-up + one batch
+    sm, sq, open_sum = short.batch()
+    assert (sm == 0).all() and (sq == 0).all()
