@@ -150,7 +150,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_dt / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: %s" % (args.network, sample), "until": args.until},
+        "config": {"workload": "M/M/1 batched (BASELINE configs[1]): Generator Exp(0.5) -> Processor Exp(0.333333) cap 14 -> Storage"
+                   if args.network == "mm1" else args.network,
+                   "replications_per_step": nreps, "until": args.until, "sample": sample,
+                   "implementation": "C++ oracle port of the reference engine (the Rust crate cannot be built in this image)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))

@@ -95,6 +95,9 @@ enum DistKind : int {
     D_NORMAL = 1,       // Continuous::Normal{mean,std_dev}
     D_TRIANGULAR = 2,   // Continuous::Triangular{min,max,mode}
     D_UNIFORM = 3,      // Continuous::Uniform{min,max}
+    D_GAMMA = 4,        // Continuous::Gamma{shape,scale}      a=shape, b=scale
+    D_LOGNORMAL = 5,    // Continuous::LogNormal{mu,sigma}     a=mu, b=sigma
+    D_WEIBULL = 6,      // Continuous::Weibull{shape,scale}    a=shape, b=scale (passed to rand_distr SWAPPED)
 };
 struct Continuous {
     int kind = D_EXP;

@@ -331,6 +331,37 @@ struct Engine {
                 if (f_range < diff_mode_min) return mn + sqrt(f_range * diff_mode_min);
                 return mx - sqrt((range - f_range) * (mx - mode));
             }
+            case DK_GAMMA: {  // rand_distr 0.4 Gamma (Marsaglia-Tsang); shape == 1 is lowered to DK_EXP
+                const double d = pd.p0, cc = pd.p1, scale = pd.p2;
+                double u_small = 0.0;
+                if (pd.q0) u_small = open01(ln);  // GammaSmallShape draws its Open01 first
+                double g = 0.0;
+                for (;;) {
+                    const double x = sample_standard_normal(ln);
+                    const double v_cbrt = 1.0 + cc * x;
+                    if (v_cbrt <= 0.0) {
+                        if (ln.err) break;
+                        continue;
+                    }
+                    const double v = v_cbrt * v_cbrt * v_cbrt;
+                    const double u = open01(ln);
+                    const double x_sqr = x * x;
+                    if (u < 1.0 - 0.0331 * x_sqr * x_sqr || log(u) < 0.5 * x_sqr + d * (1.0 - v + log(v))) {
+                        g = d * v * scale;
+                        break;
+                    }
+                    if (ln.err) break;
+                }
+                return pd.q0 ? g * pow(u_small, bits_f64(pd.q1)) : g;
+            }
+            case DK_LOGNORMAL: {
+                const double n = sample_standard_normal(ln);
+                return exp(pd.p0 + pd.p1 * n);
+            }
+            case DK_WEIBULL: {  // OpenClosed01, then scale * (-ln x)^(1/shape)
+                const double x = (double)((next_u64(ln) >> 11) + 1ull) * (1.0 / 9007199254740992.0);
+                return pd.p0 * pow(-log(x), pd.p1);
+            }
             default: {  // DK_UNIFORM: p0 = low, p1 = scale
                 double value1_2 = bits_f64((next_u64(ln) >> 12) | 0x3FF0000000000000ull);
                 double value0_1 = value1_2 - 1.0;

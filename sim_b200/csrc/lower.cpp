@@ -204,8 +204,54 @@ int lower_continuous(Ctx& c, const Value* v, SimbModelDesc* md) {
         md->p1 = scale;
         return 0;
     }
-    if (kind == "beta" || kind == "gamma" || kind == "logNormal" || kind == "weibull")
-        return c.fail(33, "random variable `" + kind + "` is outside the accelerated path (SURVEY.md 8f-3)");
+    if (kind == "gamma") {  // rand_distr 0.4 Gamma::new(shape, scale)
+        double shape, scale;
+        if (!get_num(p, "shape", &shape) || !get_num(p, "scale", &scale)) return c.fail(13, "gamma: missing field");
+        if (!(shape > 0.0) || !(scale > 0.0)) {
+            md->dist_kind = DK_GAMMA;
+            md->dist_err = 16;
+            return 0;
+        }
+        if (shape == 1.0) {  // GammaRepr::One(Exp::new(1 / scale))
+            const double lambda = 1.0 / scale;
+            md->dist_kind = DK_EXP;
+            if (!(lambda > 0.0)) md->dist_err = 16;
+            md->p0 = 1.0 / lambda;
+            return 0;
+        }
+        const bool small = shape < 1.0;
+        const double sh = small ? shape + 1.0 : shape;
+        const double d = sh - 1.0 / 3.0;
+        md->dist_kind = DK_GAMMA;
+        md->p0 = d;
+        md->p1 = 1.0 / std::sqrt(9.0 * d);
+        md->p2 = scale;
+        md->q0 = small ? 1 : 0;
+        const double inv_shape = 1.0 / shape;
+        std::memcpy(&md->q1, &inv_shape, 8);
+        return 0;
+    }
+    if (kind == "logNormal") {
+        double mu, sigma;
+        if (!get_num(p, "mu", &mu) || !get_num(p, "sigma", &sigma)) return c.fail(13, "logNormal: missing field");
+        md->dist_kind = DK_LOGNORMAL;
+        if (!std::isfinite(sigma)) md->dist_err = 17;
+        md->p0 = mu;
+        md->p1 = sigma;
+        return 0;
+    }
+    if (kind == "weibull") {
+        // the reference passes (shape, scale) to rand_distr's Weibull::new(scale, shape): swapped roles
+        double shape, scale;
+        if (!get_num(p, "shape", &shape) || !get_num(p, "scale", &scale)) return c.fail(13, "weibull: missing field");
+        md->dist_kind = DK_WEIBULL;
+        if (!(shape > 0.0) || !(scale > 0.0)) md->dist_err = 19;
+        md->p0 = shape;        // acts as rand_distr's scale
+        md->p1 = 1.0 / scale;  // acts as rand_distr's 1/shape
+        return 0;
+    }
+    if (kind == "beta")
+        return c.fail(33, "random variable `beta` is outside the accelerated path (SURVEY.md 8f-3)");
     return c.fail(13, "unknown variant `" + kind + "`");
 }
 
@@ -643,7 +689,9 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
             hn.w_init[md.wrow] = (uint32_t)pm[i].preload.size();  // head 0, len n
         }
         if (net.models[i].dist_kind == DK_EXP) net.uses_exp = 1;
-        if (net.models[i].dist_kind == DK_NORMAL) net.uses_normal = 1;
+        if (net.models[i].dist_kind == DK_NORMAL || net.models[i].dist_kind == DK_GAMMA ||
+            net.models[i].dist_kind == DK_LOGNORMAL)
+            net.uses_normal = 1;
     }
     for (uint32_t k = 0; k < net.n_phase_words; k++) hn.w_init[net.wrow_phase + k] = phase_words[k];
     if (overflow) return c.fail(32, "content intern table overflow (more than 255 distinct names)");

@@ -31,7 +31,13 @@ enum SimbModelType : uint8_t {
     MT_COUNT = 11
 };
 
-enum SimbDistKind : uint8_t { DK_EXP = 0, DK_NORMAL = 1, DK_TRIANGULAR = 2, DK_UNIFORM = 3, DK_NONE = 255 };
+enum SimbDistKind : uint8_t {
+    DK_EXP = 0, DK_NORMAL = 1, DK_TRIANGULAR = 2, DK_UNIFORM = 3,
+    DK_GAMMA = 4,      // p0 = d, p1 = c, p2 = scale; q0 = 0 large shape / 1 small shape (q1 = bits of 1/shape)
+    DK_LOGNORMAL = 5,  // p0 = mu, p1 = sigma
+    DK_WEIBULL = 6,    // p0 = scale, p1 = 1/shape (rand_distr's roles, i.e. the reference's swapped ones)
+    DK_NONE = 255
+};
 
 // ModelDesc.flags
 #define MF_STORE_RECORDS 1u

@@ -21,7 +21,8 @@ class _Variant:
 
 
 class ContinuousRandomVariable:
-    """``Continuous`` (random_variable.rs:17-28).  In scope: Exp, Normal, Triangular, Uniform."""
+    """``Continuous`` (random_variable.rs:17-28): Exp, Normal, Triangular, Uniform, Gamma, LogNormal, Weibull
+    (Beta is not on the accelerated path)."""
 
     @staticmethod
     def Exp(lambda_: float) -> _Variant:
@@ -38,6 +39,21 @@ class ContinuousRandomVariable:
     @staticmethod
     def Uniform(min: float, max: float) -> _Variant:  # noqa: A002
         return _Variant("uniform", {"min": float(min), "max": float(max)})
+
+
+    @staticmethod
+    def Gamma(shape: float, scale: float) -> _Variant:
+        return _Variant("gamma", {"shape": float(shape), "scale": float(scale)})
+
+    @staticmethod
+    def LogNormal(mu: float, sigma: float) -> _Variant:
+        return _Variant("logNormal", {"mu": float(mu), "sigma": float(sigma)})
+
+    @staticmethod
+    def Weibull(shape: float, scale: float) -> _Variant:
+        """NOTE: the reference hands (shape, scale) to rand_distr's ``Weibull::new(scale, shape)``
+        (random_variable.rs:85-87), so the two parameters act with swapped roles; reproduced."""
+        return _Variant("weibull", {"shape": float(shape), "scale": float(scale)})
 
 
 class BooleanRandomVariable:

@@ -215,6 +215,28 @@ def generator_passive():
     return models, connectors
 
 
+def more_variables():
+    """the remaining continuous variables of random_variable.rs:19-27 that the engine
+    accelerates -- Gamma (large and small shape, and shape == 1 which rand_distr turns into an Exp),
+    LogNormal and Weibull (with the reference's swapped-parameter quirk)."""
+    T = ContinuousRandomVariable
+    models = [
+        Model.new("gen", Generator.new(T.Gamma(2.5, 0.8), None, "job", False, None)),
+        Model.new("p-lognormal", Processor.new(T.LogNormal(-0.2, 0.5), 12, "job", "done", False, None)),
+        Model.new("p-weibull", Processor.new(T.Weibull(1.2, 2.0), 12, "job", "done", False, None)),
+        Model.new("p-gamma-small", Processor.new(T.Gamma(0.6, 1.5), 12, "job", "done", False, None)),
+        Model.new("p-gamma-one", Processor.new(T.Gamma(1.0, 0.7), 12, "job", "done", False, None)),
+        _storage("sink"),
+    ]
+    C = Connector.new
+    connectors = [
+        C("c1", "gen", "p-lognormal", "job", "job"), C("c2", "p-lognormal", "p-weibull", "done", "job"),
+        C("c3", "p-weibull", "p-gamma-small", "done", "job"), C("c4", "p-gamma-small", "p-gamma-one", "done", "job"),
+        C("c5", "p-gamma-one", "sink", "done", "store"),
+    ]
+    return models, connectors
+
+
 # ---- BASELINE.json configurations (shapes fixed in SURVEY.md 8(d)) -----------------------------------
 def tandem():
     """config 3: generator Exp(1.0) -> load balancer (3 paths) -> 3x stage-1 processor Exp(0.4) cap 8 ->
@@ -341,6 +363,6 @@ ALL = {
     "gate_blocking": gate_blocking, "load_balancer": load_balancer, "parallel_gateway": parallel_gateway,
     "stochastic_gate": stochastic_gate, "batcher": batcher, "stopwatch": stopwatch,
     "processor_from_queue": processor_from_queue, "processor_network": processor_network,
-    "generator_passive": generator_passive, "tandem": tandem, "gateway_network": gateway_network,
+    "generator_passive": generator_passive, "more_variables": more_variables, "tandem": tandem, "gateway_network": gateway_network,
     "large_mixed": large_mixed,
 }

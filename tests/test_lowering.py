@@ -37,7 +37,7 @@ def test_field_order_is_irrelevant_and_unknown_fields_are_ignored():
     ("[{\"id\": \"x\"}]", 13),                                   # missing field `type`
     ("[{\"id\": \"g\", \"type\": \"Generator\", \"portsIn\": {}, \"portsOut\": {\"job\": \"job\"}}]", 13),
     ("[{\"id\": \"g\", \"type\": \"Generator\", \"portsIn\": {}, \"portsOut\": {\"job\": \"job\"}, "
-     "\"messageInterdepartureTime\": {\"gamma\": {\"shape\": 1, \"scale\": 1}}}]", 33),
+     "\"messageInterdepartureTime\": {\"beta\": {\"alpha\": 1, \"beta\": 1}}}]", 33),
     ("not json", 13),
     ("[]", 1),
 ])

@@ -185,3 +185,29 @@ def test_distribution_parameter_errors_surface_per_draw():
     assert O.sample_continuous(ContinuousRandomVariable.Triangular(0.0, 1.0, 2.0), 1)[0] == 18
     assert O.sample_continuous(ContinuousRandomVariable.Triangular(1.0, 1.0, 1.0), 1)[0] == 18
     assert O.sample_continuous(ContinuousRandomVariable.Uniform(2.0, 1.0), 1)[0] == 34
+
+
+# ---- SURVEY.md 8(f)-3 variables: the reference's own mean tests (random_variable.rs:232-252, 348-357) ----------
+def test_gamma_mean():
+    e, x, _ = O.sample_continuous(ContinuousRandomVariable.Gamma(7.0, 11.0), 10000, rng_kind=1)
+    assert e == 0 and abs(x.mean() - 77.0) / 77.0 < 0.025 and (x > 0).all()
+    e, x, _ = O.sample_continuous(ContinuousRandomVariable.Gamma(0.4, 2.0), 20000, rng_kind=1)  # small-shape path
+    assert e == 0 and abs(x.mean() - 0.8) / 0.8 < 0.05
+    e, x, used = O.sample_continuous(ContinuousRandomVariable.Gamma(1.0, 3.0), 10000, rng_kind=1)  # Exp(1/scale)
+    assert e == 0 and abs(x.mean() - 3.0) / 3.0 < 0.025
+    assert O.sample_continuous(ContinuousRandomVariable.Gamma(0.0, 1.0), 1)[0] == 16
+    assert O.sample_continuous(ContinuousRandomVariable.Gamma(1.0, -1.0), 1)[0] == 16
+
+
+def test_lognormal_mean():
+    e, x, _ = O.sample_continuous(ContinuousRandomVariable.LogNormal(11.0, 1.0), 10000, rng_kind=1)
+    expected = math.exp(11.0 + 0.5)
+    assert e == 0 and abs(x.mean() - expected) / expected < 0.06  # heavy tail: the reference's 2.5 % holds for ITS seed
+
+
+def test_weibull_mean_pins_the_swapped_parameters():
+    """random_variable.rs:348-357 expects mean 14 for {shape: 7, scale: 0.5}: that is rand_distr's
+    Weibull(scale = 7, shape = 0.5), 7 * Gamma(3) -- the reference passes the two parameters swapped."""
+    e, x, _ = O.sample_continuous(ContinuousRandomVariable.Weibull(7.0, 0.5), 40000, rng_kind=1)
+    assert e == 0 and abs(x.mean() - 14.0) / 14.0 < 0.04
+    assert O.sample_continuous(ContinuousRandomVariable.Weibull(0.0, 1.0), 1)[0] == 19
