@@ -901,10 +901,10 @@ int simb_describe(simb_sim* s, char* out, uint64_t capacity) {
     std::snprintf(buf, sizeof buf,
                   "{\"models\": %u, \"connectors\": %u, \"routes\": %u, \"f64_rows\": %u, \"u32_rows\": %u, "
                   "\"state_bytes_per_replication\": %u, \"max_pending\": %u, \"ring_u32_slots\": %u, \"ring_f64_slots\": %u, "
-                  "\"tile\": %u, \"stages\": %u, \"grid\": %u, \"smem_bytes\": %u, \"steps_per_launch\": %u, \"stride\": %llu, \"replications\": %llu, "
+                  "\"tile\": %u, \"smem_bytes\": %u, \"steps_per_launch\": %u, \"stride\": %llu, \"replications\": %llu, "
                   "\"rng_kind\": %d, \"instrument\": %d, \"netdesc_bytes\": %u, \"kernel_shape\": \"%s\"}",
                   net.n_models, net.n_connectors, net.n_routes, net.n_drows, net.n_wrows, net.n_drows * 8u + net.n_wrows * 4u,
-                  net.max_pending, s->hn.ring_w_slots, s->hn.ring_d_slots, s->dims.tile, s->dims.stages, s->dims.grid, s->dims.smem_bytes, s->K,
+                  net.max_pending, s->hn.ring_w_slots, s->hn.ring_d_slots, s->dims.tile, s->dims.smem_bytes, s->K,
                   (unsigned long long)s->st.stride, (unsigned long long)s->st.n, s->rng_kind, s->instrument ? 1 : 0,
                   (unsigned)sizeof(SimbNetDesc), engine_shape_name(s->dims.shape));
     put_str(out, capacity, buf);

@@ -19,10 +19,8 @@
 
 #ifdef __CUDACC__
 #define SIMB_HD __host__ __device__ __forceinline__
-#define SIMB_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define SIMB_HD inline
-#define SIMB_HD_NOINLINE
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -39,13 +37,6 @@ namespace simb {
 SIMB_HD uint32_t warp_or(uint32_t v) {
 #if SIMB_ON_DEVICE
     return __reduce_or_sync(0xFFFFFFFFu, v);
-#else
-    return v;
-#endif
-}
-SIMB_HD uint32_t warp_max(uint32_t v) {
-#if SIMB_ON_DEVICE
-    return __reduce_max_sync(0xFFFFFFFFu, v);
 #else
     return v;
 #endif

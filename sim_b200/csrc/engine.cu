@@ -240,10 +240,9 @@ int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool inst
     // (shared memory 227 KB, 64 registers per thread -> at most 32 warps, at most 32 CTAs); among equals
     // prefer the wider tile (fewer, larger bulk copies), and keep half of the SM's unified storage for L1
     // when that costs no occupancy (the ring slots live in L1 between steps).
-    const uint32_t stages = 1;
     uint32_t tile = 256, best_warps = 0;
     for (uint32_t cand = 256; cand >= 32; cand >>= 1) {
-        const uint32_t smem = smem_plan(net, cand, stages).total;
+        const uint32_t smem = smem_plan(net, cand).total;
         if (smem > 227u * 1024u) continue;
         uint32_t ctas = (227u * 1024u) / smem;
         const uint32_t by_regs = 65536u / (64u * cand), by_threads = 2048u / cand;
@@ -263,19 +262,14 @@ int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool inst
         if (t < tile) tile = t;
     }
     if (dims->shape >= 0 && tile != SIMB_SHAPE_TILE) dims->shape = -1;  // baked-shape kernels assume the full tile width
-    SmemPlan sp = smem_plan(net, tile, stages);
+    SmemPlan sp = smem_plan(net, tile);
     if (sp.total > 227u * 1024u) return (int)cudaErrorInvalidConfiguration;
     dims->tile = tile;
-    dims->stages = stages;
     dims->smem_bytes = sp.total;
     cudaError_t e = cudaFuncSetAttribute((const void*)pick_kernel(rng_kind, instrument, dims->shape),
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
     if (e != cudaSuccess) return (int)e;
-    // One CTA per tile.  Measured (profiles/r01_pipeline_experiments.txt): a persistent grid of
-    // SMs x resident CTAs with static tile assignment is 8 % slower at K = 64 (no dynamic load balance)
-    // and double buffering inside a CTA gains nothing at K = 1, where the 4 co-resident CTAs per SM already
-    // overlap each other's load / compute / store phases.
-    dims->grid = 0;
+    dims->grid = 0;  // one CTA per tile (profiles/r01_pipeline_experiments.txt: persistent / double-buffered variants lost)
     return (int)cudaSuccess;
 }
 
@@ -283,7 +277,6 @@ int engine_launch_step(const SimbNetDesc& net, const SimbDevState& st, const Sim
                        int rng_kind, bool instrument, bool count_active, cudaStream_t stream) {
     const uint32_t grid = (uint32_t)(st.stride / dims.tile);
     SimbLaunch la = la_in;
-    la.stages = 1;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(grid);

@@ -10,8 +10,7 @@ namespace simb {
 struct EngineDims {
     uint32_t tile;        // replications per CTA (= threads per CTA)
     uint32_t smem_bytes;  // dynamic shared memory per CTA
-    uint32_t grid;        // persistent CTAs per launch (SM count x resident CTAs per SM)
-    uint32_t stages;      // tile buffers per CTA (2 = double-buffered pipeline)
+    uint32_t grid;        // reserved (the launch uses one CTA per tile)
     int shape;            // baked shape id whose specialised kernel is used, or -1 (generic interpreter)
 };
 int engine_match_shape(const SimbNetDesc& net, int rng_kind, bool instrument);

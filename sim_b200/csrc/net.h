@@ -169,6 +169,4 @@ struct SimbLaunch {
     uint32_t epoch;       // step_until call epoch (ctl epoch == epoch => finished in this call)
     uint32_t settle;      // 1 = pay every deferred draw before the state is stored (last launch of an API call)
     double until;
-    uint32_t stages;      // tile buffers per CTA: 2 = prefetch the next tile while computing (small k), else 1
-    uint32_t pad;
 };

@@ -54,12 +54,12 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// shared memory carve-up (all offsets multiples of 16 B).  `stages` tile buffers (1, or 2 for the
-// double-buffered pipeline) are laid out back to back, each holding the f64 rows then the u32 rows.
+// shared memory carve-up (all offsets multiples of 16 B): barrier, reduction scratch, ziggurat x tables, then
+// the state tile (f64 rows followed by u32 rows).
 struct SmemPlan {
     uint32_t off_bar, off_red, off_expx, off_normx, off_tiles, stage_bytes, d_bytes, total;
 };
-__host__ __device__ inline SmemPlan smem_plan(const SimbNetDesc& net, uint32_t tile, uint32_t stages) {
+__host__ __device__ inline SmemPlan smem_plan(const SimbNetDesc& net, uint32_t tile) {
     SmemPlan p;
     uint32_t o = 0;
     p.off_bar = o;  // three mbarriers: one per stage + one for the tables
@@ -74,7 +74,7 @@ __host__ __device__ inline SmemPlan smem_plan(const SimbNetDesc& net, uint32_t t
     p.off_tiles = o;
     p.d_bytes = net.n_drows * tile * 8u;
     p.stage_bytes = (p.d_bytes + net.n_wrows * tile * 4u + 127u) & ~127u;
-    o += stages * p.stage_bytes;
+    o += p.stage_bytes;
     p.total = o;
     return p;
 }
@@ -119,7 +119,7 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t tile = SHAPE >= 0 ? SIMB_SHAPE_TILE : blockDim.x;
     const uint32_t tid = threadIdx.x;
-    const SmemPlan sp = smem_plan(net, tile, 1);
+    const SmemPlan sp = smem_plan(net, tile);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + sp.off_bar);
     unsigned long long* s_red = reinterpret_cast<unsigned long long*>(smem + sp.off_red);
     double* s_expx = reinterpret_cast<double*>(smem + sp.off_expx);
