@@ -216,6 +216,30 @@ int simb_get_trace(simb_sim* sim, uint64_t replication, simb_trace_event* out, u
 int simb_render_content(simb_sim* sim, uint32_t content, char* out, uint64_t capacity);
 int simb_intern_content(simb_sim* sim, const char* content, uint32_t* out);
 
+/* ---- string API (WebSimulation, sim/src/simulator/web.rs:87-215) --------------------------------
+ * The JSON forms of the calls above for ONE observed replication of the batch (every replication
+ * still steps).  *json points at a NUL-terminated string owned by the handle, valid until the next
+ * *_json call on it.  Text is what serde_json::to_string produces: Vec<Message> with the camelCase
+ * keys of coupling.rs:62-71, Vec<ModelRecord> as models/mod.rs:48-52, f64 in shortest round-trip
+ * form.  The stepping forms need an instrumented handle whose trace covers the replication
+ * (simb_config.trace_replications / trace_capacity).
+ * simb_get_messages_json <- get_messages_json (web.rs:87-89)
+ * simb_get_records_json  <- get_records_json (web.rs:109-111)
+ * simb_inject_input_json <- inject_input_json (web.rs:136-139); message = one serialised Message
+ * simb_step_json         <- step_json (web.rs:161-163): the messages Simulation::step returns
+ * simb_step_n_json       <- step_n_json (web.rs:207-209): messages of all n steps (mod.rs:293-303)
+ * simb_step_until_json   <- step_until_json (web.rs:184-186): messages of the steps that ended
+ *                           before `until`; the crossing step's are not returned (mod.rs:277-288)
+ * simb_format_f64: the number formatter alone (for tests of the text form)
+ */
+int simb_get_messages_json(simb_sim* sim, uint64_t replication, const char** json);
+int simb_get_records_json(simb_sim* sim, const char* model_id, uint64_t replication, const char** json);
+int simb_inject_input_json(simb_sim* sim, const char* message_json, const uint8_t* replica_mask);
+int simb_step_json(simb_sim* sim, uint64_t replication, const char** json);
+int simb_step_n_json(simb_sim* sim, uint64_t n, uint64_t replication, const char** json);
+int simb_step_until_json(simb_sim* sim, double until, uint64_t replication, const char** json);
+int simb_format_f64(double value, char* out, uint64_t capacity);
+
 /* ---- output_analysis (sim/src/output_analysis/mod.rs) ------------------------------------------
  * Device side: per-replication waiting-time accumulators of `stat_model_id` (the statistic of
  * sim/tests/web.rs:571-597: Processing Start - Arrival per job) and their reduction.

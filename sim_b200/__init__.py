@@ -22,7 +22,7 @@ def __getattr__(name):
     # Simulation / output_analysis load the CUDA library lazily so that describing models works
     # on machines without it.
     import importlib
-    if name in ("Simulation", "SimulationError", "SimbConfig"):
+    if name in ("Simulation", "WebSimulation", "SimulationError", "SimbConfig"):
         return getattr(importlib.import_module(".simulator", __name__), name)
     if name in ("output_analysis", "simulator"):
         return importlib.import_module("." + name, __name__)

@@ -13,6 +13,8 @@
 
 #include "../../include/simb.h"
 #include "engine.cuh"
+#include "json.hpp"
+#include "json_write.hpp"
 #include "lower.hpp"
 #include "output_analysis.hpp"
 
@@ -46,6 +48,7 @@ struct simb_sim {
     double kernel_ms = 0.0;
     bool instrument = false;
     int rng_kind = 0;
+    std::string json;  // result of the last *_json call (handle-owned, see simb.h)
 };
 
 namespace {
@@ -756,6 +759,147 @@ int simb_get_records(simb_sim* s, const char* model_id, uint64_t rep, simb_recor
     *count = k;
     return 0;
 }
+
+// ---- WebSimulation string API (sim/src/simulator/web.rs:87-215) for one observed replication ------
+namespace {
+void message_json(std::string& o, const std::string& sid, const std::string& sport, const std::string& tid,
+                  const std::string& tport, double time, const std::string& content) {
+    // field order and camelCase names of coupling.rs:62-71
+    o += "{\"sourceId\":";
+    json::write_string(o, sid);
+    o += ",\"sourcePort\":";
+    json::write_string(o, sport);
+    o += ",\"targetId\":";
+    json::write_string(o, tid);
+    o += ",\"targetPort\":";
+    json::write_string(o, tport);
+    o += ",\"time\":";
+    json::write_f64(o, time);
+    o += ",\"content\":";
+    json::write_string(o, content);
+    o += '}';
+}
+// messages the observed replication emitted in trace events [first, end): Simulation::step's return
+// value (mod.rs:271) concatenated over the steps of the call (step_n :293-303, step_until :277-288)
+int stepped_messages_json(simb_sim* s, uint64_t rep, uint32_t first, bool bounded, double until, const char** out) {
+    std::vector<SimbTraceRec> recs;
+    int e = fetch_trace(s, rep, &recs);
+    if (e) return e;
+    std::string& o = s->json;
+    o = "[";
+    bool any = false;
+    for (size_t i = first; i < recs.size(); i++) {
+        const SimbTraceRec& r = recs[i];
+        if (r.meta >> 31) continue;                 // model record
+        if (bounded && !(r.time < until)) continue; // the crossing step's messages are not returned (:281-285)
+        const uint32_t conn = r.meta & 0xFFFFu;
+        if (conn >= s->hn.connectors.size()) continue;
+        const HostConnector& c = s->hn.connectors[conn];
+        if (any) o += ',';
+        any = true;
+        message_json(o, c.source_id, c.source_port, c.target_id, c.target_port, r.time, s->hn.render(r.content));
+    }
+    o += ']';
+    *out = o.c_str();
+    return 0;
+}
+int traced_count(simb_sim* s, uint64_t rep, uint32_t* cnt) {
+    if (!s->instrument) return fail(SIMB_ERR_INVALID_ARGUMENT, "handle was not posted with SIMB_FLAG_INSTRUMENT");
+    if (rep >= s->st.trace_reps) return fail(SIMB_ERR_INVALID_ARGUMENT, "replication is not traced (simb_config.trace_replications)");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    CUDA_TRY(cudaMemcpy(cnt, s->st.trace_count + rep, 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+}  // namespace
+
+int simb_get_messages_json(simb_sim* s, uint64_t rep, const char** out) {
+    if (!s || !out) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    uint64_t n = 0;
+    int e = simb_get_messages(s, rep, nullptr, 0, &n);
+    if (e) return e;
+    std::vector<simb_message> ms(n ? n : 1);
+    if ((e = simb_get_messages(s, rep, ms.data(), n, &n))) return e;
+    std::string& o = s->json;
+    o = "[";
+    for (uint64_t i = 0; i < n; i++) {
+        if (i) o += ',';
+        message_json(o, ms[i].source_id, ms[i].source_port, ms[i].target_id, ms[i].target_port, ms[i].time, ms[i].content);
+    }
+    o += ']';
+    *out = o.c_str();
+    return 0;
+}
+int simb_get_records_json(simb_sim* s, const char* model_id, uint64_t rep, const char** out) {
+    if (!s || !model_id || !out) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    uint64_t n = 0;
+    int e = simb_get_records(s, model_id, rep, nullptr, 0, &n);
+    if (e) return e;
+    std::vector<simb_record> rs(n ? n : 1);
+    if ((e = simb_get_records(s, model_id, rep, rs.data(), n, &n))) return e;
+    std::string& o = s->json;
+    o = "[";
+    for (uint64_t i = 0; i < n; i++) {  // models/mod.rs:48-52
+        if (i) o += ',';
+        o += "{\"time\":";
+        json::write_f64(o, rs[i].time);
+        o += ",\"action\":";
+        json::write_string(o, rs[i].action);
+        o += ",\"subject\":";
+        json::write_string(o, rs[i].subject);
+        o += '}';
+    }
+    o += ']';
+    *out = o.c_str();
+    return 0;
+}
+int simb_inject_input_json(simb_sim* s, const char* message_json_text, const uint8_t* replica_mask) {
+    if (!s || !message_json_text) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    json::Value v;
+    json::Parser p(message_json_text);
+    if (!p.parse(v) || !v.is_object()) return fail(SIMB_ERR_INVALID_ARGUMENT, "message is not a JSON object");
+    // serde requires every field of Message (coupling.rs:62-71); web.rs:136-139 unwraps the error
+    const char* keys[] = {"sourceId", "sourcePort", "targetId", "targetPort", "content"};
+    for (const char* k : keys) {
+        const json::Value* f = v.get(k);
+        if (!f || !f->is_string()) return fail(SIMB_ERR_INVALID_ARGUMENT, std::string("message: missing field `") + k + "`");
+    }
+    const json::Value* t = v.get("time");
+    if (!t || !t->is_number()) return fail(SIMB_ERR_INVALID_ARGUMENT, "message: missing field `time`");
+    return simb_inject_input(s, v.get("targetId")->str.c_str(), v.get("targetPort")->str.c_str(),
+                             v.get("content")->str.c_str(), replica_mask);
+}
+int simb_step_json(simb_sim* s, uint64_t rep, const char** out) {
+    if (!s || !out) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    uint32_t first = 0;
+    int e = traced_count(s, rep, &first);
+    if (e) return e;
+    if ((e = simb_step(s))) return e;
+    return stepped_messages_json(s, rep, first, false, 0.0, out);
+}
+int simb_step_n_json(simb_sim* s, uint64_t n, uint64_t rep, const char** out) {
+    if (!s || !out) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    uint32_t first = 0;
+    int e = traced_count(s, rep, &first);
+    if (e) return e;
+    if ((e = simb_step_n(s, n))) return e;
+    return stepped_messages_json(s, rep, first, false, 0.0, out);
+}
+int simb_step_until_json(simb_sim* s, double until, uint64_t rep, const char** out) {
+    if (!s || !out) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    uint32_t first = 0;
+    int e = traced_count(s, rep, &first);
+    if (e) return e;
+    if ((e = simb_step_until(s, until))) return e;
+    return stepped_messages_json(s, rep, first, true, until, out);
+}
+int simb_format_f64(double v, char* out, uint64_t capacity) {
+    if (!out) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    std::string o;
+    json::write_f64(o, v);
+    put_str(out, capacity, o);
+    return 0;
+}
+
 int simb_render_content(simb_sim* s, uint32_t content, char* out, uint64_t capacity) {
     if (!s || !out) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
     put_str(out, capacity, s->hn.render(content));

@@ -128,6 +128,13 @@ def load_library() -> C.CDLL:
     L.simb_oa_t_score.argtypes = [C.c_double, C.c_uint64, C.POINTER(C.c_double)]
     L.simb_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
     L.simb_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.simb_get_messages_json.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_char_p)]
+    L.simb_get_records_json.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.POINTER(C.c_char_p)]
+    L.simb_inject_input_json.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+    L.simb_step_json.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_char_p)]
+    L.simb_step_n_json.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_char_p)]
+    L.simb_step_until_json.argtypes = [C.c_void_p, C.c_double, C.c_uint64, C.POINTER(C.c_char_p)]
+    L.simb_format_f64.argtypes = [C.c_double, C.c_char_p, C.c_uint64]
     _lib = L
     return L
 
@@ -382,6 +389,82 @@ class Simulation:
         buf = C.create_string_buffer(2048)
         _check(load_library().simb_describe(self._h, buf, 2048))
         return json.loads(buf.value.decode())
+
+
+class WebSimulation:
+    """String API of the reference's ``WebSimulation`` (sim/src/simulator/web.rs:16-215) over a batch.
+
+    Every call acts on all ``replications``; the JSON that comes back describes the observed
+    ``replication`` (default 0), which must lie inside the traced prefix of the batch."""
+
+    def __init__(self, simulation: Simulation, replication: int = 0):
+        self.simulation = simulation
+        self.replication = replication
+
+    @classmethod
+    def post_json(cls, models: str, connectors: str, replications: int = 1, *, replication: int = 0,
+                  trace_capacity: int = 1 << 16, **kw) -> "WebSimulation":
+        """``WebSimulation::post_json`` (web.rs:23-31)."""
+        kw.setdefault("trace_replications", replication + 1)
+        sim = Simulation.post_json(models, connectors, replications, instrument=True, trace_capacity=trace_capacity, **kw)
+        return cls(sim, replication)
+
+    def put_json(self, models: str, connectors: str):
+        """``put_json`` (web.rs:35-40)."""
+        _check(load_library().simb_put_json(self.simulation._h, models.encode(), connectors.encode()))
+
+    def _text(self, fn, *args) -> str:
+        out = C.c_char_p()
+        _check(fn(self.simulation._h, *args, C.byref(out)))
+        return out.value.decode()
+
+    def get_messages_json(self) -> str:
+        """``get_messages_json`` (web.rs:87-89)."""
+        return self._text(load_library().simb_get_messages_json, self.replication)
+
+    def get_global_time(self) -> float:
+        """``get_global_time`` (web.rs:98-100)."""
+        return float(self.simulation.get_global_time()[self.replication])
+
+    def get_status(self, model_id: str) -> str:
+        """``get_status`` (web.rs:103-105)."""
+        return self.simulation.get_status(model_id, self.replication)
+
+    def get_records_json(self, model_id: str) -> str:
+        """``get_records_json`` (web.rs:109-111)."""
+        return self._text(load_library().simb_get_records_json, model_id.encode(), self.replication)
+
+    def reset(self):
+        self.simulation.reset()
+
+    def reset_messages(self):
+        self.simulation.reset_messages()
+
+    def reset_global_time(self):
+        self.simulation.reset_global_time()
+
+    def inject_input_json(self, message: str):
+        """``inject_input_json`` (web.rs:136-139)."""
+        _check(load_library().simb_inject_input_json(self.simulation._h, message.encode(), None))
+
+    def step_json(self) -> str:
+        """``step_json`` (web.rs:161-163)."""
+        return self._text(load_library().simb_step_json, self.replication)
+
+    def step_until_json(self, until: float) -> str:
+        """``step_until_json`` (web.rs:184-186)."""
+        return self._text(load_library().simb_step_until_json, C.c_double(until), self.replication)
+
+    def step_n_json(self, n: int) -> str:
+        """``step_n_json`` (web.rs:207-209)."""
+        return self._text(load_library().simb_step_n_json, C.c_uint64(n), self.replication)
+
+
+def format_f64(value: float) -> str:
+    """serde_json's text form of an f64 (the formatter behind the ``*_json`` calls)."""
+    buf = C.create_string_buffer(64)
+    _check(load_library().simb_format_f64(C.c_double(value), buf, 64))
+    return buf.value.decode()
 
 
 def device_count() -> int:
