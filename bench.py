@@ -258,13 +258,17 @@ def main():
         launches_ = max(1, ctr_["launches"])
         # ring touches per replication-step for this network: ~0.4 slots of 4 B (+8 B arrival time)
         ring_b = 0.4 * (4 + (8 if stat else 0)) if desc_["ring_u32_slots"] else 0.0
-        alg = desc_["stride"] * (2.0 * state_b) + (rsteps_local / launches_) * ring_b
+        # a pass over the batch is issued as `grids` concurrent grids on their own streams, each covering
+        # 1/grids of the replications; launch_ms is the device time of the call divided by the launches
+        grids = max(1, int(desc_.get("grids_per_pass", 1)))
+        alg = desc_["stride"] * (2.0 * state_b) / grids + (rsteps_local / launches_) * ring_b
         launch_ms_ = ctr_["kernel_ms"] / launches_
         ach = alg / (launch_ms_ * 1e-3) / 1e9 if launch_ms_ > 0 else 0.0
         cap = ncu.get(tag, {})
         return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": cap.get("dram_bytes_per_launch"), "kernel": "simb_step_kernel<%s>" % desc_["kernel_shape"],
-                "launches": ctr_["launches"], "launch_ms": launch_ms_, "algorithmic_bytes_per_launch": alg,
+                "launches": ctr_["launches"], "grids_per_pass": grids, "launch_ms": launch_ms_,
+                "algorithmic_bytes_per_launch": alg,
                 "steps_per_launch": desc_["steps_per_launch"], "state_bytes_per_replication": state_b,
                 "peak_source": peak_src, "kernel_share_of_step": ctr_["kernel_ms"] * 1e-3 / wall_s if wall_s > 0 else None,
                 "ncu": cap or None}

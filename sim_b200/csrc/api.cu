@@ -4,9 +4,11 @@
 // SIMB_ERR_CUDA when CUDA is unavailable.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -31,6 +33,12 @@ struct simb_sim {
     EngineDims dims;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // a pass over the batch is issued as `n_lanes` concurrent grids (contiguous tile ranges) on their own
+    // streams, so that one grid's drain overlaps the others' work; lane 0 is `stream`
+    static const int MAX_LANES = 4;
+    int n_lanes = 1;
+    cudaStream_t side[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
     // device allocations
     double* d_dinit = nullptr;
     uint32_t* d_winit = nullptr;
@@ -76,6 +84,17 @@ void ensure_pool(int device) {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     done[device] = true;
+}
+
+void destroy_streams(simb_sim* s) {
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->fork) cudaEventDestroy(s->fork);
+    for (int i = 1; i < simb_sim::MAX_LANES; i++) {
+        if (s->join[i]) cudaEventDestroy(s->join[i]);
+        if (s->side[i]) cudaStreamDestroy(s->side[i]);
+    }
+    if (s->stream) cudaStreamDestroy(s->stream);
 }
 
 void free_device(simb_sim* s) {
@@ -187,8 +206,45 @@ int first_error(simb_sim* s, uint64_t failed_hint) {
 }
 
 // drive the step kernel.  mode 0: exactly n steps; mode 1: until every replication's clock >= until.
+// small batches (fewer than two full waves of CTAs per grid) are not split
+int grids_per_pass(const simb_sim* s) {
+    const uint32_t tiles = (uint32_t)(s->st.stride / s->dims.tile);
+    return tiles >= 2u * 592u * (uint32_t)s->n_lanes ? s->n_lanes : 1;
+}
+// One pass over the batch: the step kernel on every tile, issued as s->n_lanes concurrent grids.  The side
+// streams must have been forked from s->stream (pass_fork) and are joined back by pass_join.
+int launch_pass(simb_sim* s, const SimbLaunch& la, bool count_active, uint64_t* issued) {
+    const SimbNetDesc& net = s->hn.desc;
+    const uint32_t tiles = (uint32_t)(s->st.stride / s->dims.tile);
+    const int lanes = grids_per_pass(s);
+    const uint32_t per = (tiles + lanes - 1) / lanes;
+    for (int i = 0; i < lanes; i++) {
+        const uint32_t t0 = (uint32_t)i * per;
+        if (t0 >= tiles) break;
+        const uint32_t nt = std::min(per, tiles - t0);
+        CUDA_TRY(engine_launch_step(net, s->st, la, s->dims, s->rng_kind, s->instrument, count_active,
+                                    i == 0 ? s->stream : s->side[i], t0, nt));
+        (*issued)++;
+    }
+    return 0;
+}
+int pass_fork(simb_sim* s) {
+    if (s->n_lanes <= 1) return 0;
+    CUDA_TRY(cudaEventRecord(s->fork, s->stream));
+    for (int i = 1; i < s->n_lanes; i++) CUDA_TRY(cudaStreamWaitEvent(s->side[i], s->fork, 0));
+    return 0;
+}
+int pass_join(simb_sim* s) {
+    for (int i = 1; i < s->n_lanes; i++) {
+        CUDA_TRY(cudaEventRecord(s->join[i], s->side[i]));
+        CUDA_TRY(cudaStreamWaitEvent(s->stream, s->join[i], 0));
+    }
+    return 0;
+}
+
 int run_steps(simb_sim* s, int mode, uint64_t n, double until) {
     const SimbNetDesc& net = s->hn.desc;
+    (void)net;
     SimbLaunch la;
     std::memset(&la, 0, sizeof la);
     la.mode = (uint32_t)mode;
@@ -200,18 +256,24 @@ int run_steps(simb_sim* s, int mode, uint64_t n, double until) {
     unsigned long long tot[4] = {0, 0, 0, 0};
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
     uint64_t issued = 0;
+    int pe = 0;
     if (mode == 0) {
         uint64_t left = n;
+        if (n > 0) {
+            CUDA_TRY(cudaMemsetAsync(s->st.totals + 2, 0, 2 * sizeof(unsigned long long), s->stream));
+            if ((pe = pass_fork(s))) return pe;
+        }
         while (left > 0) {
             la.k = (uint32_t)std::min<uint64_t>(left, s->K);
             left -= la.k;
             const bool last = left == 0;
             la.settle = last ? 1u : 0u;  // the state the caller can observe owes no deferred draw
-            if (last) CUDA_TRY(cudaMemsetAsync(s->st.totals + 2, 0, 2 * sizeof(unsigned long long), s->stream));
-            CUDA_TRY(engine_launch_step(net, s->st, la, s->dims, s->rng_kind, s->instrument, last, s->stream));
-            issued++;
+            if ((pe = launch_pass(s, la, last, &issued))) return pe;
         }
-        if (n > 0) CUDA_TRY(cudaMemcpyAsync(tot, s->st.totals, sizeof tot, cudaMemcpyDeviceToHost, s->stream));
+        if (n > 0) {
+            if ((pe = pass_join(s))) return pe;
+            CUDA_TRY(cudaMemcpyAsync(tot, s->st.totals, sizeof tot, cudaMemcpyDeviceToHost, s->stream));
+        }
         CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
     } else {
@@ -219,13 +281,14 @@ int run_steps(simb_sim* s, int mode, uint64_t n, double until) {
         // launches between termination checks: about 256 steps' worth
         const uint32_t round = std::max<uint32_t>(1u, 256u / std::max<uint32_t>(1u, s->K));
         for (;;) {
+            CUDA_TRY(cudaMemsetAsync(s->st.totals + 2, 0, 2 * sizeof(unsigned long long), s->stream));
+            if ((pe = pass_fork(s))) return pe;
             for (uint32_t i = 0; i < round; i++) {
                 const bool last = i + 1 == round;
                 la.settle = last ? 1u : 0u;
-                if (last) CUDA_TRY(cudaMemsetAsync(s->st.totals + 2, 0, 2 * sizeof(unsigned long long), s->stream));
-                CUDA_TRY(engine_launch_step(net, s->st, la, s->dims, s->rng_kind, s->instrument, last, s->stream));
-                issued++;
+                if ((pe = launch_pass(s, la, last, &issued))) return pe;
             }
+            if ((pe = pass_join(s))) return pe;
             CUDA_TRY(cudaMemcpyAsync(tot, s->st.totals, sizeof tot, cudaMemcpyDeviceToHost, s->stream));
             CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
             CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -343,9 +406,7 @@ int simb_post_json(const char* models_json, const char* connectors_json, const s
     std::memset(&s->st, 0, sizeof s->st);
     auto bail = [&](int code) {
         free_device(s);
-        if (s->ev0) cudaEventDestroy(s->ev0);
-        if (s->ev1) cudaEventDestroy(s->ev1);
-        if (s->stream) cudaStreamDestroy(s->stream);
+        destroy_streams(s);
         delete s;
         return code;
     };
@@ -354,6 +415,18 @@ int simb_post_json(const char* models_json, const char* connectors_json, const s
         return bail(fail(SIMB_ERR_CUDA, "cudaStreamCreate failed"));
     if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess)
         return bail(fail(SIMB_ERR_CUDA, "cudaEventCreate failed"));
+    {
+        // measured (profiles/r01_pipeline_experiments.txt): two concurrent half-batch grids hide the grid
+        // drain / ramp between dependent launches (+12 % at one step per launch); SIMB_STREAMS is the A/B switch
+        const char* ns = getenv("SIMB_STREAMS");
+        int want = ns && *ns ? atoi(ns) : 2;
+        s->n_lanes = want < 1 ? 1 : want > simb_sim::MAX_LANES ? simb_sim::MAX_LANES : want;
+        bool ok = cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 1; i < s->n_lanes && ok; i++)
+            ok = cudaStreamCreateWithFlags(&s->side[i], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&s->join[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) return bail(fail(SIMB_ERR_CUDA, "side stream creation failed"));
+    }
     ensure_pool(config->device);
     e = build_device(s, 0, nullptr);
     if (e) return bail(e);
@@ -467,9 +540,7 @@ int simb_destroy(simb_sim* s) {
     cudaSetDevice(s->cfg.device);
     free_device(s);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    if (s->ev0) cudaEventDestroy(s->ev0);
-    if (s->ev1) cudaEventDestroy(s->ev1);
-    if (s->stream) cudaStreamDestroy(s->stream);
+    destroy_streams(s);
     delete s;
     return 0;
 }
@@ -1046,11 +1117,11 @@ int simb_describe(simb_sim* s, char* out, uint64_t capacity) {
                   "{\"models\": %u, \"connectors\": %u, \"routes\": %u, \"f64_rows\": %u, \"u32_rows\": %u, "
                   "\"state_bytes_per_replication\": %u, \"max_pending\": %u, \"ring_u32_slots\": %u, \"ring_f64_slots\": %u, "
                   "\"tile\": %u, \"smem_bytes\": %u, \"steps_per_launch\": %u, \"stride\": %llu, \"replications\": %llu, "
-                  "\"rng_kind\": %d, \"instrument\": %d, \"netdesc_bytes\": %u, \"kernel_shape\": \"%s\"}",
+                  "\"rng_kind\": %d, \"instrument\": %d, \"netdesc_bytes\": %u, \"kernel_shape\": \"%s\", \"grids_per_pass\": %d}",
                   net.n_models, net.n_connectors, net.n_routes, net.n_drows, net.n_wrows, net.n_drows * 8u + net.n_wrows * 4u,
                   net.max_pending, s->hn.ring_w_slots, s->hn.ring_d_slots, s->dims.tile, s->dims.smem_bytes, s->K,
                   (unsigned long long)s->st.stride, (unsigned long long)s->st.n, s->rng_kind, s->instrument ? 1 : 0,
-                  (unsigned)sizeof(SimbNetDesc), engine_shape_name(s->dims.shape));
+                  (unsigned)sizeof(SimbNetDesc), engine_shape_name(s->dims.shape), grids_per_pass(s));
     put_str(out, capacity, buf);
     return 0;
 }

@@ -274,9 +274,12 @@ int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool inst
 }
 
 int engine_launch_step(const SimbNetDesc& net, const SimbDevState& st, const SimbLaunch& la_in, const EngineDims& dims,
-                       int rng_kind, bool instrument, bool count_active, cudaStream_t stream) {
-    const uint32_t grid = (uint32_t)(st.stride / dims.tile);
+                       int rng_kind, bool instrument, bool count_active, cudaStream_t stream, uint32_t tile0,
+                       uint32_t n_tiles) {
+    const uint32_t all = (uint32_t)(st.stride / dims.tile);
+    const uint32_t grid = n_tiles ? n_tiles : all - tile0;
     SimbLaunch la = la_in;
+    la.tile0 = tile0;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(grid);

@@ -19,9 +19,11 @@ const char* engine_shape_name(int shape);
 // chooses the tile width for a layout and sets the kernel attributes; returns cudaError_t
 int engine_configure(const SimbNetDesc& net, uint64_t stride_hint, int rng_kind, bool instrument, EngineDims* dims);
 
-// one step-kernel launch: every live replication executes up to la.k Simulation::step()s
+// one step-kernel launch over tiles [tile0, tile0 + n_tiles) (n_tiles 0 = to the end): every live replication
+// of those tiles executes up to la.k Simulation::step()s
 int engine_launch_step(const SimbNetDesc& net, const SimbDevState& st, const SimbLaunch& la, const EngineDims& dims,
-                       int rng_kind, bool instrument, bool count_active, cudaStream_t stream);
+                       int rng_kind, bool instrument, bool count_active, cudaStream_t stream, uint32_t tile0 = 0,
+                       uint32_t n_tiles = 0);
 
 // state initialisation (Simulation::post / put): row constants, RNG state, absent padding lanes.
 // keep_mask bit 0: keep clock, bit 1: keep mailbox (ctl.npend + pending rows), bit 2: keep RNG rows

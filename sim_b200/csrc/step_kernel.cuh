@@ -127,7 +127,7 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
     double* s_d = reinterpret_cast<double*>(smem + sp.off_tiles);
     uint32_t* s_w = reinterpret_cast<uint32_t*>(smem + sp.off_tiles + sp.d_bytes);
     const uint32_t n_rows = net.n_drows + net.n_wrows;
-    const uint64_t base = (uint64_t)blockIdx.x * tile;  // first replication (padded index) of this tile
+    const uint64_t base = (uint64_t)(blockIdx.x + la.tile0) * tile;  // first replication (padded index) of this tile
 
     if (tid == 0) {
         mbar_init(bar, 1);
