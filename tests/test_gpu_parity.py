@@ -414,3 +414,77 @@ def test_streaming_batch_means_on_device():
     ok = batches == 30
     grand = oa.IndependentSample.post(mean[ok]).confidence_interval_mean(0.05)
     assert grand.half_width() < 0.05 * abs(mean[ok].mean())
+
+
+# ---- BASELINE.json full sizes of the other networks (configs[2..4]) ---------------------------------------
+def _sampled_equal(sim, models, conns, seed, picks, until=None, nsteps=None, stat=None):
+    t, steps, events = sim.get_global_time(), sim.get_steps(), sim.get_events()
+    if stat:  # the oracle derives the waiting times from the records of that model
+        for m in models:
+            m.inner.store_records = True
+    o = oracle_api.OracleSimulation(models, conns)
+    for r0 in picks:
+        ref = o.run_batch(seed, r0, 2, threads=2, until=until, nsteps=nsteps, stat_model_id=stat, trace_hash=False)
+        sl = slice(r0, r0 + 2)
+        assert ref["err"] == 0
+        assert (steps[sl] == ref["steps"]).all() and (events[sl] == ref["events"]).all()
+        assert _close(t[sl], ref["time"])
+        if stat:
+            s, cnt = sim.get_wait_stats()
+            assert (cnt[sl] == ref["wait_n"]).all() and _close(s[sl], ref["wait_sum"])
+
+
+def test_full_size_tandem_batch_means():
+    """configs[2]: tandem queue, 2^22 replications, steady-state batch means per replication on the device."""
+    n, until, warm, size = 1 << 22, 260.0, 20, 6
+    models, conns = networks.tandem()
+    sim = _sim(models, conns, n, seed=21, instrument=False, stat_model_id="processor-3", batch_warmup=warm, batch_size=size)
+    sim.step_until(until)
+    assert (sim.get_errors() == 0).all()
+    t = sim.get_global_time()
+    assert (t >= until).all() and (t < until + 30.0).all()
+    mean, var, batches = sim.get_batch_means()
+    assert (batches <= 30).all() and (batches >= 10).mean() > 0.99
+    ok = batches >= 10
+    assert np.isfinite(mean[ok]).all() and (mean[ok] >= 0).all() and (var[ok] >= 0).all()
+    # whole-batch accounting: every job that started service at the observed stage is in the wait count
+    s, cnt = sim.get_wait_stats()
+    done = np.minimum((np.maximum(cnt.astype(np.int64) - warm, 0)) // size, 30)
+    assert np.array_equal(done, batches.astype(np.int64))
+    _sampled_equal(sim, models, conns, 21, (0, 4095, 1 << 21, n - 2), until=until, stat="processor-3")
+    from sim_b200 import output_analysis as oa
+    grand = oa.IndependentSample.post(mean[ok]).confidence_interval_mean(0.05)
+    assert grand.half_width() < 0.01 * abs(grand.lower() + grand.upper()) / 2.0
+
+
+def test_full_size_gateway_network():
+    """configs[3]: 16-model gateway DAG (exclusive / parallel / stochastic gates, batcher), 2^20 replications."""
+    n, until = 1 << 20, 40.0
+    models, conns = networks.gateway_network()
+    sim = _sim(models, conns, n, seed=33, instrument=False)
+    sim.step_until(until)
+    assert (sim.get_errors() == 0).all()
+    t, steps, events = sim.get_global_time(), sim.get_steps(), sim.get_events()
+    assert (t >= until).all() and np.isfinite(t).all()
+    assert (events >= steps).all() and np.unique(steps).size > 100
+    c = sim.get_counters()
+    assert c["steps"] == int(steps.astype(np.uint64).sum()) and c["events"] == int(events.astype(np.uint64).sum())
+    _sampled_equal(sim, models, conns, 33, (0, 511, 500000, n - 2), until=until)
+
+
+def test_full_size_large_mixed_shard():
+    """configs[4]: 32-model network; one GPU's shard of the 2^26-replication job at 8 GPUs (2^23 replications,
+    44 GB of state and rings), posted with the replication offset of rank 5."""
+    n, nsteps, offset = 1 << 23, 48, 5 << 23
+    models, conns = networks.large_mixed()
+    sim = _sim(models, conns, n, seed=7, instrument=False, replication_offset=offset, steps_per_launch=16)
+    sim.step_n(nsteps)
+    assert (sim.get_errors() == 0).all()
+    steps, events, t = sim.get_steps(), sim.get_events(), sim.get_global_time()
+    assert (steps == nsteps).all() and (events >= steps).all() and np.isfinite(t).all()
+    o = oracle_api.OracleSimulation(models, conns)
+    for r0 in (0, 1 << 22, n - 2):  # global replication index = offset + local index
+        ref = o.run_batch(7, offset + r0, 2, threads=2, nsteps=nsteps, trace_hash=False)
+        sl = slice(r0, r0 + 2)
+        assert (events[sl] == ref["events"]).all() and _close(t[sl], ref["time"])
+    sim.close()
