@@ -185,14 +185,18 @@ StepKernel simb_shape_kernel_0();
 StepKernel simb_shape_kernel_1();
 StepKernel simb_shape_kernel_2();
 StepKernel simb_shape_kernel_3();
+StepKernel simb_shape_stream_kernel_0();
+StepKernel simb_shape_stream_kernel_1();
+StepKernel simb_shape_stream_kernel_2();
+StepKernel simb_shape_stream_kernel_3();
 
-static StepKernel pick_kernel(int rng_kind, bool instrument, int shape) {
+static StepKernel pick_kernel(int rng_kind, bool instrument, int shape, bool stream = false) {
     if (!instrument && rng_kind == 0) {  // baked shapes exist for the production configuration only
         switch (shape) {
-            case 0: return simb_shape_kernel_0();
-            case 1: return simb_shape_kernel_1();
-            case 2: return simb_shape_kernel_2();
-            case 3: return simb_shape_kernel_3();
+            case 0: return stream ? simb_shape_stream_kernel_0() : simb_shape_kernel_0();
+            case 1: return stream ? simb_shape_stream_kernel_1() : simb_shape_kernel_1();
+            case 2: return stream ? simb_shape_stream_kernel_2() : simb_shape_kernel_2();
+            case 3: return stream ? simb_shape_stream_kernel_3() : simb_shape_kernel_3();
             default: break;
         }
     }
@@ -269,6 +273,11 @@ int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool inst
     cudaError_t e = cudaFuncSetAttribute((const void*)pick_kernel(rng_kind, instrument, dims->shape),
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
     if (e != cudaSuccess) return (int)e;
+    if (dims->shape >= 0) {
+        e = cudaFuncSetAttribute((const void*)pick_kernel(rng_kind, instrument, dims->shape, true),
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
+        if (e != cudaSuccess) return (int)e;
+    }
     dims->grid = 0;  // one CTA per tile (profiles/r01_pipeline_experiments.txt: persistent / double-buffered variants lost)
     return (int)cudaSuccess;
 }
@@ -292,7 +301,8 @@ int engine_launch_step(const SimbNetDesc& net, const SimbDevState& st, const Sim
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const uint32_t ca = count_active ? 1u : 0u;
-    return (int)cudaLaunchKernelEx(&cfg, pick_kernel(rng_kind, instrument, dims.shape), net, st, la, ca);
+    return (int)cudaLaunchKernelEx(&cfg, pick_kernel(rng_kind, instrument, dims.shape, la.k <= SIMB_STREAM_MAX_K), net, st,
+                                   la, ca);
 }
 
 static inline uint32_t blocks_for(uint64_t n, uint32_t t) { return (uint32_t)((n + t - 1) / t); }

@@ -10,8 +10,10 @@
 
 namespace simb {
 #if SIMB_SHAPE_ID < SIMB_N_SHAPES
-StepKernel SIMB_CAT(simb_shape_kernel_, SIMB_SHAPE_ID)() { return simb_step_kernel<0, false, SIMB_SHAPE_ID>; }
+StepKernel SIMB_CAT(simb_shape_kernel_, SIMB_SHAPE_ID)() { return simb_step_kernel<0, false, SIMB_SHAPE_ID, false>; }
+StepKernel SIMB_CAT(simb_shape_stream_kernel_, SIMB_SHAPE_ID)() { return simb_step_kernel<0, false, SIMB_SHAPE_ID, true>; }
 #else
 StepKernel SIMB_CAT(simb_shape_kernel_, SIMB_SHAPE_ID)() { return nullptr; }
+StepKernel SIMB_CAT(simb_shape_stream_kernel_, SIMB_SHAPE_ID)() { return nullptr; }
 #endif
 }  // namespace simb

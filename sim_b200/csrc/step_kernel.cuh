@@ -79,6 +79,16 @@ __host__ __device__ inline SmemPlan smem_plan(const SimbNetDesc& net, uint32_t t
     return p;
 }
 
+// Baked shapes need few registers, so more CTAs fit an SM.  Measured on M/M/1 (profiles/r01_pipeline_experiments.txt):
+// fused launches (K = 128) are best at 5 CTAs / SM (48 registers); streaming launches (one or two steps per state
+// load) want the most tile loads in flight: 6 CTAs / SM (40 registers) -> two instantiations, chosen per launch.
+#ifndef SIMB_SHAPE_MIN_BLOCKS
+#define SIMB_SHAPE_MIN_BLOCKS 5
+#endif
+#ifndef SIMB_SHAPE_STREAM_MIN_BLOCKS
+#define SIMB_SHAPE_STREAM_MIN_BLOCKS 6
+#endif
+#define SIMB_STREAM_MAX_K 2u /* launches with k <= this use the streaming instantiation */
 #ifndef SIMB_MIN_BLOCKS
 #define SIMB_MIN_BLOCKS 4 /* <= 64 registers: 32 resident warps per SM measured +15% over 3 (24 warps) */
 #endif
@@ -111,8 +121,9 @@ __host__ __device__ constexpr int shape_tier() {  // model-count tier of a baked
 // One CTA = one tile of blockDim.x consecutive replications.  Kernels of baked shapes are only launched
 // with SIMB_SHAPE_TILE threads, so their shared-memory row offsets are immediates.
 #define SIMB_SHAPE_TILE 256u
-template <int RNG, bool INSTR, int SHAPE>
-__global__ void __launch_bounds__(256, SIMB_MIN_BLOCKS)
+template <int RNG, bool INSTR, int SHAPE, bool STREAM = false>
+__global__ void __launch_bounds__(256, SHAPE >= 0 ? (STREAM ? SIMB_SHAPE_STREAM_MIN_BLOCKS : SIMB_SHAPE_MIN_BLOCKS)
+                                                  : SIMB_MIN_BLOCKS)
 simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_constant__ SimbDevState st,
                  const __grid_constant__ SimbLaunch la, const uint32_t count_active) {
     const SimbNetDesc& net = shape_desc<SHAPE>(net_param);
