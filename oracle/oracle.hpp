@@ -98,6 +98,7 @@ enum DistKind : int {
     D_GAMMA = 4,        // Continuous::Gamma{shape,scale}      a=shape, b=scale
     D_LOGNORMAL = 5,    // Continuous::LogNormal{mu,sigma}     a=mu, b=sigma
     D_WEIBULL = 6,      // Continuous::Weibull{shape,scale}    a=shape, b=scale (passed to rand_distr SWAPPED)
+    D_BETA = 7,         // Continuous::Beta{alpha,beta}        a=alpha, b=beta
 };
 struct Continuous {
     int kind = D_EXP;

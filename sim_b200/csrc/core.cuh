@@ -353,6 +353,59 @@ struct Engine {
                 const double x = (double)((next_u64(ln) >> 11) + 1ull) * (1.0 / 9007199254740992.0);
                 return pd.p0 * pow(-log(x), pd.p1);
             }
+            case DK_BETA: {  // rand_distr 0.4.3 Beta (Cheng BB / BC); p0 = a, p1 = b, q0 = flags
+                const double aa = pd.p0, bb = pd.p1;
+                const double LN4 = 1.3862943611198906, LN5 = 1.6094379124341003;  // ln 4, ln 5
+                const double alpha = aa + bb;
+                double w = 0.0;
+                if (!(pd.q0 & 1u)) {  // BB
+                    const double beta = sqrt((alpha - 2.0) / (2.0 * aa * bb - alpha));
+                    const double gamma = aa + 1.0 / beta;
+                    for (;;) {
+                        const double u1 = open01(ln);
+                        const double u2 = open01(ln);
+                        const double v = beta * log(u1 / (1.0 - u1));
+                        w = aa * exp(v);
+                        const double z = u1 * u1 * u2;
+                        const double r = gamma * v - LN4;
+                        const double s_ = aa + r - w;
+                        if (s_ + 1.0 + LN5 >= 5.0 * z) break;
+                        const double t = log(z);
+                        if (s_ >= t) break;
+                        if (!(r + alpha * log(alpha / (bb + w)) < t)) break;
+                        if (ln.err) break;
+                    }
+                } else {  // BC
+                    const double beta = 1.0 / bb;
+                    const double delta = 1.0 + aa - bb;
+                    const double kappa1 = delta * (1.0 / 18.0 / 4.0 + 3.0 / 18.0 / 4.0 * bb) / (aa * beta - 14.0 / 18.0);
+                    const double kappa2 = 0.25 + (0.5 + 0.25 / delta) * bb;
+                    for (;;) {
+                        double z;
+                        const double u1 = open01(ln);
+                        const double u2 = open01(ln);
+                        if (ln.err) break;
+                        if (u1 < 0.5) {
+                            const double y = u1 * u2;
+                            z = u1 * y;
+                            if (0.25 * u2 + z - y >= kappa1) continue;
+                        } else {
+                            z = u1 * u1 * u2;
+                            if (z <= 0.25) {
+                                const double v = beta * log(u1 / (1.0 - u1));
+                                w = aa * exp(v);
+                                break;
+                            }
+                            if (z >= kappa2) continue;
+                        }
+                        const double v = beta * log(u1 / (1.0 - u1));
+                        w = aa * exp(v);
+                        if (!(alpha * (log(alpha / (bb + w)) + v) - LN4 < log(z))) break;
+                    }
+                }
+                if (!(pd.q0 & 2u)) return (w == SIMB_INF) ? 1.0 : w / (bb + w);
+                return bb / (bb + w);
+            }
             default: {  // DK_UNIFORM: p0 = low, p1 = scale
                 double value1_2 = bits_f64((next_u64(ln) >> 12) | 0x3FF0000000000000ull);
                 double value0_1 = value1_2 - 1.0;

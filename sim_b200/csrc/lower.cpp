@@ -250,8 +250,28 @@ int lower_continuous(Ctx& c, const Value* v, SimbModelDesc* md) {
         md->p1 = 1.0 / scale;  // acts as rand_distr's 1/shape
         return 0;
     }
-    if (kind == "beta")
-        return c.fail(33, "random variable `beta` is outside the accelerated path (SURVEY.md 8f-3)");
+    if (kind == "beta") {  // rand_distr 0.4.3 Beta::new: Cheng's BB (min(alpha, beta) > 1) or BC
+        double alpha, beta;
+        if (!get_num(p, "alpha", &alpha) || !get_num(p, "beta", &beta)) return c.fail(13, "beta: missing field");
+        md->dist_kind = DK_BETA;
+        if (!(alpha > 0.0) || !(beta > 0.0)) {
+            md->dist_err = 14;
+            return 0;
+        }
+        double a = alpha < beta ? alpha : beta, b = alpha < beta ? beta : alpha;
+        bool switched = !(alpha < beta);
+        uint64_t flags = 0;
+        if (!(a > 1.0)) {  // BC works with a = max, b = min
+            std::swap(a, b);
+            switched = !switched;
+            flags |= 1;
+        }
+        if (switched) flags |= 2;
+        md->p0 = a;
+        md->p1 = b;
+        md->q0 = flags;
+        return 0;
+    }
     return c.fail(13, "unknown variant `" + kind + "`");
 }
 

@@ -36,6 +36,7 @@ enum SimbDistKind : uint8_t {
     DK_GAMMA = 4,      // p0 = d, p1 = c, p2 = scale; q0 = 0 large shape / 1 small shape (q1 = bits of 1/shape)
     DK_LOGNORMAL = 5,  // p0 = mu, p1 = sigma
     DK_WEIBULL = 6,    // p0 = scale, p1 = 1/shape (rand_distr's roles, i.e. the reference's swapped ones)
+    DK_BETA = 7,       // p0 = a, p1 = b as rand_distr's Beta keeps them; q0 bit 0: algorithm BC, bit 1: switched_params
     DK_NONE = 255
 };
 

@@ -21,8 +21,8 @@ class _Variant:
 
 
 class ContinuousRandomVariable:
-    """``Continuous`` (random_variable.rs:17-28): Exp, Normal, Triangular, Uniform, Gamma, LogNormal, Weibull
-    (Beta is not on the accelerated path)."""
+    """``Continuous`` (random_variable.rs:17-28): Beta, Exp, Normal, Triangular, Uniform, Gamma, LogNormal, Weibull
+    ."""
 
     @staticmethod
     def Exp(lambda_: float) -> _Variant:
@@ -40,6 +40,10 @@ class ContinuousRandomVariable:
     def Uniform(min: float, max: float) -> _Variant:  # noqa: A002
         return _Variant("uniform", {"min": float(min), "max": float(max)})
 
+
+    @staticmethod
+    def Beta(alpha: float, beta: float) -> _Variant:
+        return _Variant("beta", {"alpha": float(alpha), "beta": float(beta)})
 
     @staticmethod
     def Gamma(shape: float, scale: float) -> _Variant:

@@ -237,6 +237,27 @@ def more_variables():
     return models, connectors
 
 
+def beta_variables():
+    """Continuous::Beta (random_variable.rs:20,72) through every branch of rand_distr 0.4.3's sampler:
+    Cheng's BB (min(alpha, beta) > 1) and BC, each with and without switched parameters."""
+    T = ContinuousRandomVariable
+    models = [
+        Model.new("gen", Generator.new(T.Beta(2.0, 5.0), None, "job", False, None)),
+        Model.new("p-bb-switched", Processor.new(T.Beta(5.0, 2.0), 12, "job", "done", False, None)),
+        Model.new("p-bc", Processor.new(T.Beta(0.5, 0.7), 12, "job", "done", False, None)),
+        Model.new("p-bc-switched", Processor.new(T.Beta(3.0, 0.8), 12, "job", "done", False, None)),
+        Model.new("p-uniform", Processor.new(T.Beta(1.0, 1.0), 12, "job", "done", False, None)),
+        _storage("sink"),
+    ]
+    C = Connector.new
+    connectors = [
+        C("c1", "gen", "p-bb-switched", "job", "job"), C("c2", "p-bb-switched", "p-bc", "done", "job"),
+        C("c3", "p-bc", "p-bc-switched", "done", "job"), C("c4", "p-bc-switched", "p-uniform", "done", "job"),
+        C("c5", "p-uniform", "sink", "done", "store"),
+    ]
+    return models, connectors
+
+
 # ---- BASELINE.json configurations (shapes fixed in SURVEY.md 8(d)) -----------------------------------
 def tandem():
     """config 3: generator Exp(1.0) -> load balancer (3 paths) -> 3x stage-1 processor Exp(0.4) cap 8 ->
@@ -363,6 +384,6 @@ ALL = {
     "gate_blocking": gate_blocking, "load_balancer": load_balancer, "parallel_gateway": parallel_gateway,
     "stochastic_gate": stochastic_gate, "batcher": batcher, "stopwatch": stopwatch,
     "processor_from_queue": processor_from_queue, "processor_network": processor_network,
-    "generator_passive": generator_passive, "more_variables": more_variables, "tandem": tandem, "gateway_network": gateway_network,
+    "generator_passive": generator_passive, "more_variables": more_variables, "beta_variables": beta_variables, "tandem": tandem, "gateway_network": gateway_network,
     "large_mixed": large_mixed,
 }

@@ -10,7 +10,7 @@ from sim_b200 import models as M
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _lib = None
 
-DIST_KIND = {"exp": 0, "normal": 1, "triangular": 2, "uniform": 3, "gamma": 4, "logNormal": 5, "weibull": 6}
+DIST_KIND = {"exp": 0, "normal": 1, "triangular": 2, "uniform": 3, "gamma": 4, "logNormal": 5, "weibull": 6, "beta": 7}
 
 
 def lib():
@@ -51,6 +51,8 @@ def _dist(v):
         return DIST_KIND[k], p["mu"], p["sigma"], 0.0
     if k == "weibull":
         return DIST_KIND[k], p["shape"], p["scale"], 0.0
+    if k == "beta":
+        return DIST_KIND[k], p["alpha"], p["beta"], 0.0
     raise ValueError(k)
 
 

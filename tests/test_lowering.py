@@ -37,7 +37,7 @@ def test_field_order_is_irrelevant_and_unknown_fields_are_ignored():
     ("[{\"id\": \"x\"}]", 13),                                   # missing field `type`
     ("[{\"id\": \"g\", \"type\": \"Generator\", \"portsIn\": {}, \"portsOut\": {\"job\": \"job\"}}]", 13),
     ("[{\"id\": \"g\", \"type\": \"Generator\", \"portsIn\": {}, \"portsOut\": {\"job\": \"job\"}, "
-     "\"messageInterdepartureTime\": {\"beta\": {\"alpha\": 1, \"beta\": 1}}}]", 33),
+     "\"messageInterdepartureTime\": {\"cauchy\": {\"median\": 1, \"scale\": 1}}}]", 13),  # unknown variant
     ("not json", 13),
     ("[]", 1),
 ])

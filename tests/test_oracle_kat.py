@@ -199,6 +199,23 @@ def test_gamma_mean():
     assert O.sample_continuous(ContinuousRandomVariable.Gamma(1.0, -1.0), 1)[0] == 16
 
 
+def test_beta_mean_and_variance():
+    """random_variable.rs:214-222 (alpha 7, beta 11 -> mean 7/18 within 2.5 %), plus every branch of
+    rand_distr 0.4.3's sampler: BB (min > 1) with and without switched parameters, BC (min <= 1) likewise."""
+    for alpha, beta in ((7.0, 11.0), (11.0, 7.0), (2.0, 2.0), (0.5, 0.7), (3.0, 0.8), (0.8, 3.0), (1.0, 1.0), (0.3, 0.3)):
+        e, x, _ = O.sample_continuous(ContinuousRandomVariable.Beta(alpha, beta), 40000, rng_kind=1)
+        mean = alpha / (alpha + beta)
+        var = alpha * beta / ((alpha + beta) ** 2 * (alpha + beta + 1.0))
+        assert e == 0 and (x >= 0).all() and (x <= 1).all()
+        assert abs(x.mean() - mean) / mean < 0.025, (alpha, beta, x.mean(), mean)
+        assert abs(x.var() - var) / var < 0.06, (alpha, beta, x.var(), var)
+    # a symmetric Beta is symmetric: the third central moment vanishes
+    e, x, _ = O.sample_continuous(ContinuousRandomVariable.Beta(2.0, 2.0), 40000, rng_kind=1)
+    assert abs(((x - 0.5) ** 3).mean()) < 8e-4
+    assert O.sample_continuous(ContinuousRandomVariable.Beta(0.0, 1.0), 1)[0] == 14
+    assert O.sample_continuous(ContinuousRandomVariable.Beta(1.0, -2.0), 1)[0] == 14
+
+
 def test_lognormal_mean():
     e, x, _ = O.sample_continuous(ContinuousRandomVariable.LogNormal(11.0, 1.0), 10000, rng_kind=1)
     expected = math.exp(11.0 + 0.5)
