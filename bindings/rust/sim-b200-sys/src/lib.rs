@@ -90,4 +90,12 @@ extern "C" {
     pub fn simb_get_counters(sim: *mut simb_sim, out: *mut simb_counters) -> c_int;
     pub fn simb_get_wait_stats(sim: *mut simb_sim, sum: *mut f64, count: *mut u32, capacity: u64) -> c_int;
     pub fn simb_independent_sample_ci(sim: *mut simb_sim, alpha: f64, out: *mut simb_ci) -> c_int;
+    // WebSimulation string API (sim/src/simulator/web.rs:87-215); *json is owned by the handle
+    pub fn simb_get_messages_json(sim: *mut simb_sim, replication: u64, json: *mut *const c_char) -> c_int;
+    pub fn simb_get_records_json(sim: *mut simb_sim, model_id: *const c_char, replication: u64,
+                                 json: *mut *const c_char) -> c_int;
+    pub fn simb_inject_input_json(sim: *mut simb_sim, message_json: *const c_char, replica_mask: *const u8) -> c_int;
+    pub fn simb_step_json(sim: *mut simb_sim, replication: u64, json: *mut *const c_char) -> c_int;
+    pub fn simb_step_n_json(sim: *mut simb_sim, n: u64, replication: u64, json: *mut *const c_char) -> c_int;
+    pub fn simb_step_until_json(sim: *mut simb_sim, until: f64, replication: u64, json: *mut *const c_char) -> c_int;
 }

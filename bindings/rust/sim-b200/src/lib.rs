@@ -106,6 +106,22 @@ impl BatchedSimulation {
         Ok(out)
     }
 
+    /// `WebSimulation::step_json` (web.rs:161-163) for one observed replication of an instrumented batch:
+    /// the text deserialises into the reference's own `Vec<Message>`.
+    pub fn step_json(&mut self, replication: u64) -> Result<String, SimbError> {
+        let mut out: *const std::os::raw::c_char = ptr::null();
+        check(unsafe { sys::simb_step_json(self.raw, replication, &mut out) })?;
+        Ok(unsafe { CStr::from_ptr(out) }.to_string_lossy().into_owned())
+    }
+
+    /// `WebSimulation::get_records_json` (web.rs:109-111): deserialises into `Vec<ModelRecord>`.
+    pub fn get_records_json(&self, model_id: &str, replication: u64) -> Result<String, SimbError> {
+        let id = CString::new(model_id).unwrap();
+        let mut out: *const std::os::raw::c_char = ptr::null();
+        check(unsafe { sys::simb_get_records_json(self.raw, id.as_ptr(), replication, &mut out) })?;
+        Ok(unsafe { CStr::from_ptr(out) }.to_string_lossy().into_owned())
+    }
+
     pub fn counters(&self) -> Result<sys::simb_counters, SimbError> {
         let mut c = sys::simb_counters::default();
         check(unsafe { sys::simb_get_counters(self.raw, &mut c) })?;

@@ -444,7 +444,8 @@ int simb_put_json(simb_sim* s, const char* models_json, const char* connectors_j
     if (e) return fail(e, err);
     const SimbNetDesc& o = s->hn.desc;
     const SimbNetDesc& nw = hn.desc;
-    const bool same_layout = o.n_drows == nw.n_drows && o.n_wrows == nw.n_wrows && o.wrow_pend == nw.wrow_pend &&
+    const bool same_layout = o.n_models == nw.n_models && o.n_connectors == nw.n_connectors &&  // counter arrays
+                             o.n_drows == nw.n_drows && o.n_wrows == nw.n_wrows && o.wrow_pend == nw.wrow_pend &&
                              o.max_pending == nw.max_pending && o.wrow_rng == nw.wrow_rng &&
                              s->hn.ring_w_slots == hn.ring_w_slots && s->hn.ring_d_slots == hn.ring_d_slots &&
                              s->hn.ring_preload.size() == hn.ring_preload.size();
@@ -483,6 +484,11 @@ int simb_put_json(simb_sim* s, const char* models_json, const char* connectors_j
     }
     CUDA_TRY(engine_launch_init(s->hn.desc, s->st, s->d_dinit, s->d_winit, s->d_pre_slots, s->d_pre_vals, s->n_pre, s->rng_kind,
                                 s->instrument, 1u | 2u | 4u, s->stream));
+    if (s->instrument) {  // records live in the models that were just replaced (mod.rs:82-85): the capture starts over
+        if (s->st.trace_count) CUDA_TRY(cudaMemsetAsync(s->st.trace_count, 0, (size_t)s->st.stride * sizeof(uint32_t), s->stream));
+        CUDA_TRY(cudaMemsetAsync(s->st.record_count, 0, (size_t)nw.n_models * ACT_COUNT * sizeof(unsigned long long), s->stream));
+        CUDA_TRY(cudaMemsetAsync(s->st.conn_count, 0, (size_t)(nw.n_connectors ? nw.n_connectors : 1) * sizeof(unsigned long long), s->stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     return 0;
 }

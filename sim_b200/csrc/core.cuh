@@ -166,7 +166,9 @@ static inline U64Pair philox_pair_cold(uint32_t key0, uint32_t key1, uint32_t ct
 // most SM models: the model loops are expanded with literal indices so every structural read (types,
 // rows, routes) folds to an immediate and the handlers of absent model types disappear; the
 // distribution parameters still come from the launch's descriptor `par`.  SM == 0: generic interpreter.
-template <int RNG, int SM = 0>
+// RARE: the less common continuous variables (Beta, Gamma, LogNormal, Weibull) are compiled in.  The generic
+// kernel exists with and without them: they triple its code size, and it is bound by instruction fetch.
+template <int RNG, int SM = 0, bool RARE = true>
 struct Engine {
     static constexpr bool STATIC = SM > 0;
     const SimbNetDesc& net;  // structure
@@ -297,31 +299,8 @@ struct Engine {
             if (ln.err) return x;
         }
     }
-    // Continuous::random_variate (random_variable.rs:69-89); parameter errors surface per draw
-    SIMB_HD double sample_continuous(Lane& ln, const SimbModelDesc& md, const SimbModelDesc& pd) {
-        return sample_continuous_kind(ln, md.dist_kind, pd);
-    }
-    SIMB_HD double sample_continuous_kind(Lane& ln, uint32_t dist_kind, const SimbModelDesc& pd) {
-        if (pd.dist_err) {
-            if (!ln.err) ln.err = pd.dist_err;
-            return 0.0;
-        }
+    SIMB_HD double sample_continuous_rare(Lane& ln, uint32_t dist_kind, const SimbModelDesc& pd) {
         switch (dist_kind) {
-            case DK_EXP:
-                return sample_exp1(ln) * pd.p0;  // Exp1 * lambda_inverse
-            case DK_NORMAL: {
-                double n = sample_standard_normal(ln);
-                return pd.p0 + pd.p1 * n;
-            }
-            case DK_TRIANGULAR: {
-                double mn = pd.p0, mx = pd.p1, mode = pd.p2;
-                double f = standard_f64(ln);
-                double diff_mode_min = mode - mn;
-                double range = mx - mn;
-                double f_range = f * range;
-                if (f_range < diff_mode_min) return mn + sqrt(f_range * diff_mode_min);
-                return mx - sqrt((range - f_range) * (mx - mode));
-            }
             case DK_GAMMA: {  // rand_distr 0.4 Gamma (Marsaglia-Tsang); shape == 1 is lowered to DK_EXP
                 const double d = pd.p0, cc = pd.p1, scale = pd.p2;
                 double u_small = 0.0;
@@ -406,11 +385,42 @@ struct Engine {
                 if (!(pd.q0 & 2u)) return (w == SIMB_INF) ? 1.0 : w / (bb + w);
                 return bb / (bb + w);
             }
-            default: {  // DK_UNIFORM: p0 = low, p1 = scale
+            default:
+                return 0.0;
+        }
+    }
+    // Continuous::random_variate (random_variable.rs:69-89); parameter errors surface per draw
+    SIMB_HD double sample_continuous(Lane& ln, const SimbModelDesc& md, const SimbModelDesc& pd) {
+        return sample_continuous_kind(ln, md.dist_kind, pd);
+    }
+    SIMB_HD double sample_continuous_kind(Lane& ln, uint32_t dist_kind, const SimbModelDesc& pd) {
+        if (pd.dist_err) {
+            if (!ln.err) ln.err = pd.dist_err;
+            return 0.0;
+        }
+        switch (dist_kind) {
+            case DK_EXP:
+                return sample_exp1(ln) * pd.p0;  // Exp1 * lambda_inverse
+            case DK_NORMAL: {
+                double n = sample_standard_normal(ln);
+                return pd.p0 + pd.p1 * n;
+            }
+            case DK_TRIANGULAR: {
+                double mn = pd.p0, mx = pd.p1, mode = pd.p2;
+                double f = standard_f64(ln);
+                double diff_mode_min = mode - mn;
+                double range = mx - mn;
+                double f_range = f * range;
+                if (f_range < diff_mode_min) return mn + sqrt(f_range * diff_mode_min);
+                return mx - sqrt((range - f_range) * (mx - mode));
+            }
+            case DK_UNIFORM: {  // p0 = low, p1 = scale
                 double value1_2 = bits_f64((next_u64(ln) >> 12) | 0x3FF0000000000000ull);
                 double value0_1 = value1_2 - 1.0;
                 return value0_1 * pd.p1 + pd.p0;
             }
+            default:
+                return RARE ? sample_continuous_rare(ln, dist_kind, pd) : 0.0;
         }
     }
     // rand 0.8 UniformInt<u64>::sample: widening multiply + zone rejection

@@ -190,7 +190,10 @@ StepKernel simb_shape_stream_kernel_1();
 StepKernel simb_shape_stream_kernel_2();
 StepKernel simb_shape_stream_kernel_3();
 
-static StepKernel pick_kernel(int rng_kind, bool instrument, int shape, bool stream = false) {
+// generic interpreter with the rare continuous variables compiled in (engine_rare.cu)
+StepKernel simb_generic_rare_kernel(int rng_kind, bool instrument);
+
+static StepKernel pick_kernel(int rng_kind, bool instrument, int shape, bool stream = false, bool rare = true) {
     if (!instrument && rng_kind == 0) {  // baked shapes exist for the production configuration only
         switch (shape) {
             case 0: return stream ? simb_shape_stream_kernel_0() : simb_shape_kernel_0();
@@ -200,14 +203,22 @@ static StepKernel pick_kernel(int rng_kind, bool instrument, int shape, bool str
             default: break;
         }
     }
+    if (rare) return simb_generic_rare_kernel(rng_kind, instrument);
     if (instrument) {
-        if (rng_kind == 0) return simb_step_kernel<0, true, -1>;
-        if (rng_kind == 1) return simb_step_kernel<1, true, -1>;
-        return simb_step_kernel<2, true, -1>;
+        if (rng_kind == 0) return simb_step_kernel<0, true, -1, false, false>;
+        if (rng_kind == 1) return simb_step_kernel<1, true, -1, false, false>;
+        return simb_step_kernel<2, true, -1, false, false>;
     }
-    if (rng_kind == 0) return simb_step_kernel<0, false, -1>;
-    if (rng_kind == 1) return simb_step_kernel<1, false, -1>;
-    return simb_step_kernel<2, false, -1>;
+    if (rng_kind == 0) return simb_step_kernel<0, false, -1, false, false>;
+    if (rng_kind == 1) return simb_step_kernel<1, false, -1, false, false>;
+    return simb_step_kernel<2, false, -1, false, false>;
+}
+static bool uses_rare_variables(const SimbNetDesc& net) {
+    for (uint32_t m = 0; m < net.n_models; m++) {
+        const uint32_t k = net.models[m].dist_kind;
+        if (k == DK_GAMMA || k == DK_LOGNORMAL || k == DK_WEIBULL || k == DK_BETA) return true;
+    }
+    return false;
 }
 
 // structure = everything except the distribution values (p0..p2, q0..q2, dist_err, wcum)
@@ -240,6 +251,7 @@ const char* engine_shape_name(int shape) { return (shape >= 0 && shape < SIMB_N_
 
 int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool instrument, EngineDims* dims) {
     dims->shape = engine_match_shape(net, rng_kind, instrument);
+    dims->rare = uses_rare_variables(net);
     // Tile width = replications per CTA.  Pick the width that keeps the most warps resident per SM
     // (shared memory 227 KB, 64 registers per thread -> at most 32 warps, at most 32 CTAs); among equals
     // prefer the wider tile (fewer, larger bulk copies), and keep half of the SM's unified storage for L1
@@ -270,7 +282,7 @@ int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool inst
     if (sp.total > 227u * 1024u) return (int)cudaErrorInvalidConfiguration;
     dims->tile = tile;
     dims->smem_bytes = sp.total;
-    cudaError_t e = cudaFuncSetAttribute((const void*)pick_kernel(rng_kind, instrument, dims->shape),
+    cudaError_t e = cudaFuncSetAttribute((const void*)pick_kernel(rng_kind, instrument, dims->shape, false, dims->rare),
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
     if (e != cudaSuccess) return (int)e;
     if (dims->shape >= 0) {
@@ -301,7 +313,7 @@ int engine_launch_step(const SimbNetDesc& net, const SimbDevState& st, const Sim
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const uint32_t ca = count_active ? 1u : 0u;
-    return (int)cudaLaunchKernelEx(&cfg, pick_kernel(rng_kind, instrument, dims.shape, la.k <= SIMB_STREAM_MAX_K), net, st,
+    return (int)cudaLaunchKernelEx(&cfg, pick_kernel(rng_kind, instrument, dims.shape, la.k <= SIMB_STREAM_MAX_K, dims.rare), net, st,
                                    la, ca);
 }
 

@@ -121,7 +121,7 @@ __host__ __device__ constexpr int shape_tier() {  // model-count tier of a baked
 // One CTA = one tile of blockDim.x consecutive replications.  Kernels of baked shapes are only launched
 // with SIMB_SHAPE_TILE threads, so their shared-memory row offsets are immediates.
 #define SIMB_SHAPE_TILE 256u
-template <int RNG, bool INSTR, int SHAPE, bool STREAM = false>
+template <int RNG, bool INSTR, int SHAPE, bool STREAM = false, bool RARE = true>
 __global__ void __launch_bounds__(256, SHAPE >= 0 ? (STREAM ? SIMB_SHAPE_STREAM_MIN_BLOCKS : SIMB_SHAPE_MIN_BLOCKS)
                                                   : SIMB_MIN_BLOCKS)
 simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_constant__ SimbDevState st,
@@ -177,7 +177,7 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
     tab.exp_f = ZIG_EXP_F;
     tab.norm_x = s_normx;
     tab.norm_f = ZIG_NORM_F;
-    Engine<RNG, shape_tier<SHAPE>()> eng(net, net_param, st, tab);
+    Engine<RNG, shape_tier<SHAPE>(), RARE> eng(net, net_param, st, tab);
     while (!mbar_try_wait(bar, 0)) {
     }
 

@@ -460,6 +460,44 @@ class WebSimulation:
         return self._text(load_library().simb_step_n_json, C.c_uint64(n), self.replication)
 
 
+    # ---- YAML forms (web.rs:49-70, 93-95, 115-117, 143-146, 167-169, 190-192, 213-215).  YAML is a host-side
+    # notation only: documents are converted to / from the JSON wire form of the C ABI with PyYAML.
+    @classmethod
+    def post_yaml(cls, models: str, connectors: str, replications: int = 1, **kw) -> "WebSimulation":
+        return cls.post_json(_yaml_to_json(models), _yaml_to_json(connectors), replications, **kw)
+
+    def put_yaml(self, models: str, connectors: str):
+        self.put_json(_yaml_to_json(models), _yaml_to_json(connectors))
+
+    def get_messages_yaml(self) -> str:
+        return _json_to_yaml(self.get_messages_json())
+
+    def get_records_yaml(self, model_id: str) -> str:
+        return _json_to_yaml(self.get_records_json(model_id))
+
+    def inject_input_yaml(self, message: str):
+        self.inject_input_json(_yaml_to_json(message))
+
+    def step_yaml(self) -> str:
+        return _json_to_yaml(self.step_json())
+
+    def step_until_yaml(self, until: float) -> str:
+        return _json_to_yaml(self.step_until_json(until))
+
+    def step_n_yaml(self, n: int) -> str:
+        return _json_to_yaml(self.step_n_json(n))
+
+
+def _yaml_to_json(text: str) -> str:
+    import yaml
+    return json.dumps(yaml.safe_load(text))
+
+
+def _json_to_yaml(text: str) -> str:
+    import yaml
+    return yaml.safe_dump(json.loads(text), sort_keys=False)
+
+
 def format_f64(value: float) -> str:
     """serde_json's text form of an f64 (the formatter behind the ``*_json`` calls)."""
     buf = C.create_string_buffer(64)

@@ -189,3 +189,23 @@ def test_web_ci_half_width_replication_loop():
     assert len(means) == 12 and len(set(means)) == 12  # the uniform stream continues across replications
     ci = oa.IndependentSample.post(means).confidence_interval_mean(0.05)
     assert ci.lower() < ci.upper() and ci.half_width() > 0.0
+
+
+@pytest.mark.gpu
+def test_yaml_forms_round_trip():
+    """post_yaml / put_yaml / step_n_yaml / get_records_yaml (web.rs:49-70, 115-117, 213-215): the YAML documents
+    of sim/tests/web.rs:419-555 style describe the same network as their JSON form."""
+    import yaml
+    from sim_b200 import WebSimulation
+    from sim_b200.simulator import connectors_to_json, models_to_json
+    models, conns = networks.mm1(store_records=True)
+    my = yaml.safe_dump(json.loads(models_to_json(models)), sort_keys=False)
+    cy = yaml.safe_dump(json.loads(connectors_to_json(conns)), sort_keys=False)
+    a = WebSimulation.post_yaml(my, cy, 2, replication=1, seed=5)
+    b = _web(models, conns, n=2, replication=1, seed=5)
+    assert yaml.safe_load(a.step_n_yaml(60)) == json.loads(b.step_n_json(60))
+    assert yaml.safe_load(a.get_records_yaml("processor-01")) == json.loads(b.get_records_json("processor-01"))
+    a.put_yaml(my, cy)
+    assert json.loads(a.get_records_json("processor-01")) == []
+    a.inject_input_yaml("sourceId: manual\nsourcePort: manual\ntargetId: storage-01\ntargetPort: store\ntime: 0.0\ncontent: x\n")
+    assert yaml.safe_load(a.get_messages_yaml())[-1]["content"] == "x"
