@@ -69,3 +69,63 @@ def test_every_network_fits_the_descriptor():
         models, conns = f()
         lay = H.HostSim(models, conns, n=1).layout()
         assert lay["n_models"] == len(models) and lay["n_connectors"] == len(conns), name
+
+
+def test_yaml_documents_of_the_reference_lower_like_their_json_form():
+    """simulation_serialization_deserialization_field_ordering / _round_trip (sim/tests/web.rs:321-414): the YAML
+    documents, in scrambled field order, describe the M/M/1 network; and a Model -> document -> Model round trip
+    is the identity."""
+    from sim_b200.simulator import _yaml_to_json, connectors_to_json, models_to_json
+    models_yaml = """
+- id: "generator-01"
+  portsIn: {}
+  portsOut:
+    job: "job"
+  messageInterdepartureTime:
+    exp:
+      lambda: 0.5
+  type: "Generator"
+- type: "Processor"
+  portsIn:
+    job: "job"
+  portsOut:
+    job: "processed job"
+  serviceTime:
+    exp:
+      lambda: 0.333333
+  queueCapacity: 14
+  id: "processor-01"
+- portsIn:
+    put: "store"
+    get: "read"
+  portsOut:
+    stored: "stored"
+  type: "Storage"
+  id: "storage-01"
+"""
+    connectors_yaml = """
+- sourcePort: "job"
+  targetPort: "job"
+  id: "connector-01"
+  sourceID: "generator-01"
+  targetID: "processor-01"
+- id: "connector-02"
+  targetPort: "store"
+  targetID: "storage-01"
+  sourcePort: "processed job"
+  sourceID: "processor-01"
+"""
+    from_yaml = _lower(_yaml_to_json(models_yaml), _yaml_to_json(connectors_yaml), instrument=False)
+    models, conns = networks.mm1()
+    conns[1].source_port = "processed job"
+    models[1].inner.processed_job_port = "processed job"
+    canonical = H.HostSim(models, conns, n=1, instrument=False)
+    assert from_yaml.layout() == canonical.layout()
+    # the scrambled document and the canonical models simulate the same replication
+    from_yaml.step_n(400)
+    canonical.step_n(400)
+    assert from_yaml.hash()[0] == canonical.hash()[0] and from_yaml.time()[0] == canonical.time()[0]
+    # round trip: document -> Model objects (to_dict) -> document
+    assert json.loads(models_to_json(models)) == json.loads(json.dumps([m.to_dict() for m in models]))
+    again = _lower(models_to_json(models), connectors_to_json(conns), instrument=False)
+    assert again.layout() == canonical.layout()
