@@ -26,6 +26,8 @@ pub struct simb_config {
     pub stat_model_id: *const c_char,
     pub batch_warmup: u32,
     pub batch_size: u32,
+    pub series_capacity: u32,
+    pub reserved1: u32,
 }
 
 #[repr(C)]

@@ -58,6 +58,8 @@ impl BatchedSimulation {
             stat_model_id: ptr::null(),
             batch_warmup: 0,
             batch_size: 0,
+            series_capacity: 0,
+            reserved1: 0,
         };
         let mut raw = ptr::null_mut();
         check(unsafe { sys::simb_post_json(mj.as_ptr(), cj.as_ptr(), &cfg, &mut raw) })?;

@@ -91,6 +91,9 @@ typedef struct simb_config {
     const char* stat_model_id;   /* Processor whose per-job waiting time is accumulated, or NULL */
     uint32_t batch_warmup;       /* streaming batch means of that statistic: jobs deleted at the start ... */
     uint32_t batch_size;         /* ... and jobs per batch (0 = off); at most 30 batches per replication */
+    uint32_t series_capacity;    /* waiting times of stat_model_id kept per replication for simb_steady_state
+                                    (0 = off; costs 8 x series_capacity bytes of HBM per replication) */
+    uint32_t reserved1;
 } simb_config;
 
 typedef struct simb_sim simb_sim; /* opaque handle: owns all device memory of one batched Simulation */
@@ -136,6 +139,13 @@ typedef struct simb_counters {
     uint64_t state_bytes_per_replication; /* bytes of the SoA state tile one launch loads (= stores) */
     uint64_t failed;         /* replications holding a sticky error */
 } simb_counters;
+
+/* SteadyStateOutput of one replication (sim/src/output_analysis/mod.rs:205-345) */
+typedef struct simb_steady_state_result {
+    double mean, variance, lower, upper; /* batches mean / population variance, confidence interval of the mean */
+    uint32_t deletion_point, batch_size, batch_count;
+    int32_t status;                      /* 0, or the simb_status the reference's calls would have produced */
+} simb_steady_state_result;
 
 typedef struct simb_ci {
     double mean, variance, lower, upper;
@@ -261,6 +271,13 @@ int simb_get_batch_means(simb_sim* sim, double* mean, double* variance, uint32_t
 /* SteadyStateOutput::confidence_interval_mean given (batches_mean, batches_variance, batch_count): note the
  * reference's asymmetric degrees of freedom (mod.rs:327 vs :330) */
 int simb_oa_batch_means_ci(double mean, double variance, uint64_t batch_count, double alpha, simb_ci* out);
+/* SteadyStateOutput::{post, confidence_interval_mean} (mod.rs:205-333) on the device, one result per replication,
+ * over the waiting-time series captured with simb_config.series_capacity: the reference's own deletion point
+ * (set_to_fixed_budget, mod.rs:224-260), <= 30 batches, asymmetric degrees of freedom.  Bit-equal to
+ * simb_oa_steady_state over simb_get_series.  A replication whose series outgrew the capacity reports
+ * SIMB_ERR_CAPACITY in its status. */
+int simb_steady_state(simb_sim* sim, double alpha, simb_steady_state_result* out, uint64_t capacity);
+int simb_get_series(simb_sim* sim, uint64_t replication, double* out, uint64_t capacity, uint64_t* count);
 int simb_stat_partial(simb_sim* sim, double* sum_of_means, uint64_t* n);
 int simb_stat_partial_sqdev(simb_sim* sim, double mean, double* sum_sqdev);
 int simb_independent_sample_ci(simb_sim* sim, double alpha, simb_ci* out);

@@ -112,6 +112,7 @@ void free_device(simb_sim* s) {
     F(s->st.conn_count);
     F(s->st.record_count);
     F(s->st.totals);
+    F(s->st.series);
     F(s->d_dinit);
     F(s->d_winit);
     F(s->d_pre_slots);
@@ -167,6 +168,10 @@ int build_device(simb_sim* s, uint32_t keep_mask, const simb_sim* old) {
         if ((r = dev_alloc(s->stream, &st.trace_count, (size_t)stride, true))) return r;
         if ((r = dev_alloc(s->stream, &st.conn_count, (size_t)net.n_connectors + 1, true))) return r;
         if ((r = dev_alloc(s->stream, &st.record_count, (size_t)net.n_models * ACT_COUNT, true))) return r;
+    }
+    if (s->cfg.series_capacity && s->hn.stat_model >= 0) {
+        st.series_cap = s->cfg.series_capacity;
+        if ((r = dev_alloc(s->stream, &st.series, (size_t)st.series_cap * stride, false))) return r;
     }
     if ((r = dev_alloc(s->stream, &st.totals, 4, true))) return r;
     if ((r = dev_alloc(s->stream, &s->d_dinit, net.n_drows, false))) return r;
@@ -369,9 +374,9 @@ int simb_device_count(int* count) {
 int simb_post_json(const char* models_json, const char* connectors_json, const simb_config* config, simb_sim** out) {
     if (!out || !config || !models_json || !connectors_json) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
-    // ABI evolution: version-1 callers pass the struct without the two trailing batch-means fields
-    const size_t v1_size = offsetof(simb_config, batch_warmup);
-    if (config->struct_size != sizeof(simb_config) && config->struct_size != v1_size)
+    // ABI evolution: earlier callers pass the struct without the trailing batch-means / series fields
+    const size_t v1_size = offsetof(simb_config, batch_warmup), v2_size = offsetof(simb_config, series_capacity);
+    if (config->struct_size != sizeof(simb_config) && config->struct_size != v1_size && config->struct_size != v2_size)
         return fail(SIMB_ERR_INVALID_ARGUMENT, "simb_config.struct_size mismatch");
     if (config->replications == 0) return fail(SIMB_ERR_INVALID_ARGUMENT, "replications must be > 0");
     if (config->rng_kind < 0 || config->rng_kind > 2) return fail(SIMB_ERR_INVALID_ARGUMENT, "unknown rng_kind");
@@ -1019,6 +1024,41 @@ int simb_get_batch_means(simb_sim* s, double* mean, double* variance, uint32_t* 
         if (mean) mean[r] = m;
         if (variance) variance[r] = b ? sq[r] / (double)b - m * m : std::nan("");  // population variance, one pass
     }
+    return 0;
+}
+int simb_steady_state(simb_sim* s, double alpha, simb_steady_state_result* out, uint64_t capacity) {
+    if (!s || !out) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!s->st.series) return fail(SIMB_ERR_INVALID_ARGUMENT, "no series was captured (simb_config.series_capacity, stat_model_id)");
+    if (capacity < s->st.n) return fail(SIMB_ERR_INVALID_ARGUMENT, "output buffer smaller than the replication count");
+    static_assert(sizeof(simb_steady_state_result) == sizeof(SimbSteadyState), "device / ABI result layouts differ");
+    double t_lo[31] = {0}, t_hi[31] = {0};
+    for (uint64_t b = 1; b <= 30; b++) {  // an unlisted alpha panics in the reference (t_scores.rs:19-22)
+        int e = oa::t_score(alpha, b, &t_lo[b]);
+        if (e) return fail(e, "alpha is not one of the tabulated levels");
+        if (b >= 2) oa::t_score(alpha, b - 1, &t_hi[b]);
+    }
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    SimbSteadyState* d_out = nullptr;
+    CUDA_TRY(cudaMallocAsync((void**)&d_out, s->st.n * sizeof(SimbSteadyState), s->stream));
+    int e = engine_launch_steady_state(s->hn.desc, s->st, t_lo, t_hi, d_out, s->stream);
+    if (!e) e = (int)cudaMemcpyAsync(out, d_out, s->st.n * sizeof(SimbSteadyState), cudaMemcpyDeviceToHost, s->stream);
+    cudaFreeAsync(d_out, s->stream);
+    CUDA_TRY(e);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+int simb_get_series(simb_sim* s, uint64_t rep, double* out, uint64_t capacity, uint64_t* count) {
+    if (!s || !count) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!s->st.series) return fail(SIMB_ERR_INVALID_ARGUMENT, "no series was captured (simb_config.series_capacity, stat_model_id)");
+    if (rep >= s->st.n) return fail(SIMB_ERR_INVALID_ARGUMENT, "replication index out of range");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    uint32_t n = 0;
+    CUDA_TRY(cudaMemcpy(&n, s->st.w + (uint64_t)s->hn.desc.wrow_waitn * s->st.stride + rep, 4, cudaMemcpyDeviceToHost));
+    *count = n;  // jobs that started service; only the first series_capacity of them are kept
+    const uint64_t have = std::min<uint64_t>(n, s->st.series_cap);
+    const uint64_t take = std::min<uint64_t>(have, capacity);
+    if (out && take)
+        CUDA_TRY(cudaMemcpy2D(out, 8, s->st.series + rep, s->st.stride * 8, 8, take, cudaMemcpyDeviceToHost));
     return 0;
 }
 int simb_oa_batch_means_ci(double mean, double variance, uint64_t batch_count, double alpha, simb_ci* out) {

@@ -604,6 +604,7 @@ struct Engine {
         const uint32_t j = ln.W(net.wrow_waitn);
         ln.W(net.wrow_waitn) = j + 1u;
         ln.D(net.drow_wait) += wt;
+        if (j < st.series_cap) st.series[(uint64_t)j * st.stride + ln.rep] = wt;  // series capture (0 = off)
         if (net.bm_size != 0u && j >= net.bm_warmup) {
             const uint32_t k = j - net.bm_warmup;
             if (k / net.bm_size < SIMB_MAX_BATCHES) {

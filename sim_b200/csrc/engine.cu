@@ -149,6 +149,110 @@ simb_reduce_kernel(const __grid_constant__ SimbNetDesc net, const __grid_constan
         pcnt[blockIdx.x] = sh_c[0];
     }
 }
+// SteadyStateOutput::{set_to_fixed_budget, calculate_batch_statistics, confidence_interval_mean}
+// (sim/src/output_analysis/mod.rs:224-333) of every replication's captured series, one thread per replication;
+// the series is [sample][replication], so a warp reads consecutive addresses.  Same operation order as
+// output_analysis.cpp (the host restatement), hence bit-equal results.  The MSER-style statistic of the
+// backward scan is evaluated twice (minimum over the first half, then the first index that attains it)
+// instead of being stored.  t_lo[b] = t(alpha, b), t_hi[b] = t(alpha, b - 1): note the asymmetric degrees
+// of freedom of the reference (:327 vs :330).
+struct SteadyTScores {
+    double t_lo[31], t_hi[31];
+};
+__global__ void __launch_bounds__(128)
+simb_steady_state_kernel(const __grid_constant__ SimbNetDesc net, const __grid_constant__ SimbDevState st,
+                         const __grid_constant__ SteadyTScores ts, SimbSteadyState* __restrict__ out) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= st.n) return;
+    SimbSteadyState o;
+    o.mean = o.variance = o.lower = o.upper = 0.0;
+    o.deletion_point = o.batch_size = o.batch_count = 0;
+    o.status = 0;
+    const uint64_t n = st.w[(uint64_t)net.wrow_waitn * st.stride + r];
+    const double* x = st.series + r;
+    const uint64_t ld = st.stride;
+    if (n > st.series_cap) o.status = 32;  // SIMB_ERR_CAPACITY: the series outgrew simb_config.series_capacity
+    else if (n < 2) o.status = 34;         // `len() - 2` underflows (mod.rs:227): panic
+    if (o.status) {
+        out[r] = o;
+        return;
+    }
+    const double nf = (double)n;
+    const uint64_t half = (n - 1) / 2;
+    double best = SIMB_INF;
+    {
+        double s = 0.0, q = 0.0;
+        for (uint64_t d = n - 1; d-- > 0;) {
+            const double v = x[(d + 1) * ld];
+            s += v;
+            q += v * v;
+            const double w = nf - (double)d;
+            const double m = q - (s * s) / (w * w * w);
+            if (d < half) best = fmin(best, m);
+        }
+    }
+    uint64_t del = n;
+    {
+        double s = 0.0, q = 0.0;
+        for (uint64_t d = n - 1; d-- > 0;) {
+            const double v = x[(d + 1) * ld];
+            s += v;
+            q += v * v;
+            const double w = nf - (double)d;
+            const double m = q - (s * s) / (w * w * w);
+            if (m == best) del = d;  // scanning downwards: the lowest index wins = the first match of the source
+        }
+    }
+    if (del == n) {
+        o.status = 10;  // PrerequisiteCalcError
+        out[r] = o;
+        return;
+    }
+    uint64_t batches;
+    {  // usize_sqrt (utils/mod.rs:84-92), at most 30 batches (mod.rs:253)
+        const uint64_t a = n - del;
+        uint64_t xx = a, y = 1;
+        while (xx > y) {
+            xx = (xx + y) / 2;
+            y = a / xx;
+        }
+        batches = xx > 30 ? 30 : xx;
+    }
+    if (batches == 0) {
+        o.status = 34;
+        out[r] = o;
+        return;
+    }
+    const uint64_t size = (n - del) / batches;
+    del = n - batches * size;
+    double means[30];
+    double total = 0.0;
+    for (uint64_t b = 0; b < batches; b++) {
+        double t = 0.0;
+        for (uint64_t i = del + size * b; i < del + size * (b + 1); i++) t = t + x[i * ld];
+        means[b] = t / (double)size;
+        total = total + means[b];
+    }
+    const double bm = total / (double)batches;
+    double acc = 0.0;
+    for (uint64_t b = 0; b < batches; b++) {
+        const double dev = means[b] - bm;
+        acc = acc + dev * dev;
+    }
+    const double bv = acc / (double)batches;
+    o.deletion_point = (uint32_t)del;
+    o.batch_size = (uint32_t)size;
+    o.batch_count = (uint32_t)batches;
+    o.mean = bm;
+    o.variance = bv;
+    if (batches == 1) {
+        o.lower = o.upper = bm;
+    } else {
+        o.lower = bm - ts.t_lo[batches] * sqrt(bv) / sqrt((double)batches);
+        o.upper = bm + ts.t_hi[batches] * sqrt(bv) / sqrt((double)batches);
+    }
+    out[r] = o;
+}
 // exact u64 sums of the steps / events rows
 __global__ void __launch_bounds__(RED_THREADS)
 simb_count_kernel(const __grid_constant__ SimbNetDesc net, const __grid_constant__ SimbDevState st,
@@ -337,6 +441,16 @@ int engine_launch_inject(const SimbNetDesc& net, const SimbDevState& st, uint32_
 }
 int engine_launch_set_rng(const SimbNetDesc& net, const SimbDevState& st, int rng_kind, cudaStream_t stream) {
     simb_set_rng_kernel<<<blocks_for(st.stride, 256), 256, 0, stream>>>(net, st, rng_kind);
+    return (int)cudaGetLastError();
+}
+int engine_launch_steady_state(const SimbNetDesc& net, const SimbDevState& st, const double* t_lo, const double* t_hi,
+                               SimbSteadyState* out, cudaStream_t stream) {
+    SteadyTScores ts;
+    for (int i = 0; i < 31; i++) {
+        ts.t_lo[i] = t_lo[i];
+        ts.t_hi[i] = t_hi[i];
+    }
+    simb_steady_state_kernel<<<blocks_for(st.n, 128), 128, 0, stream>>>(net, st, ts, out);
     return (int)cudaGetLastError();
 }
 uint32_t engine_reduce_blocks(uint64_t n) { return blocks_for(n, RED_THREADS * RED_ITEMS); }

@@ -50,6 +50,10 @@ int engine_launch_set_rng(const SimbNetDesc& net, const SimbDevState& st, int rn
 int engine_launch_reduce(const SimbNetDesc& net, const SimbDevState& st, int which, double mean, double* partial_sums,
                          unsigned long long* partial_counts, uint32_t* n_blocks, cudaStream_t stream);
 
+// per-replication SteadyStateOutput of the captured series; t_lo[b] = t(alpha, b), t_hi[b] = t(alpha, b - 1), b <= 30
+int engine_launch_steady_state(const SimbNetDesc& net, const SimbDevState& st, const double* t_lo, const double* t_hi,
+                               SimbSteadyState* out, cudaStream_t stream);
+
 uint32_t engine_reduce_blocks(uint64_t n);
 
 }  // namespace simb

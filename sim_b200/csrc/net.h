@@ -162,6 +162,16 @@ struct SimbDevState {
     unsigned long long* conn_count;    // [n_connectors]        (instrumented)
     unsigned long long* record_count;  // [n_models][ACT_COUNT] (instrumented)
     unsigned long long* totals;        // [4]: steps, events, still-active replications, failed
+    double* series;       // waiting-time series of the MF_STAT processor, [series_cap][stride], or null
+    uint32_t series_cap;  // samples kept per replication (simb_config.series_capacity)
+    uint32_t reserved;
+};
+
+// SteadyStateOutput of one replication's series, computed on the device (simb_steady_state_kernel)
+struct SimbSteadyState {
+    double mean, variance, lower, upper;
+    uint32_t deletion_point, batch_size, batch_count;
+    int32_t status;
 };
 
 struct SimbLaunch {

@@ -39,6 +39,7 @@ class SimbConfig(C.Structure):
         ("steps_per_launch", C.c_uint32), ("queue_capacity", C.c_uint32), ("max_pending", C.c_uint32),
         ("trace_replications", C.c_uint32), ("trace_capacity", C.c_uint32), ("reserved0", C.c_uint32),
         ("stat_model_id", C.c_char_p), ("batch_warmup", C.c_uint32), ("batch_size", C.c_uint32),
+        ("series_capacity", C.c_uint32), ("reserved1", C.c_uint32),
     ]
 
 
@@ -60,6 +61,12 @@ class _TraceEvent(C.Structure):
 class _Counters(C.Structure):
     _fields_ = [("steps", C.c_uint64), ("events", C.c_uint64), ("launches", C.c_uint64), ("kernel_ms", C.c_double),
                 ("state_bytes_per_replication", C.c_uint64), ("failed", C.c_uint64)]
+
+
+class _SteadyState(C.Structure):
+    _fields_ = [("mean", C.c_double), ("variance", C.c_double), ("lower", C.c_double), ("upper", C.c_double),
+                ("deletion_point", C.c_uint32), ("batch_size", C.c_uint32), ("batch_count", C.c_uint32),
+                ("status", C.c_int32)]
 
 
 class _CI(C.Structure):
@@ -117,6 +124,8 @@ def load_library() -> C.CDLL:
     L.simb_intern_content.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint32)]
     L.simb_get_wait_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.simb_get_batch_means.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.simb_steady_state.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_uint64]
+    L.simb_get_series.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.simb_oa_batch_means_ci.argtypes = [C.c_double, C.c_double, C.c_uint64, C.c_double, C.POINTER(_CI)]
     L.simb_stat_partial.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.simb_stat_partial_sqdev.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double)]
@@ -182,7 +191,7 @@ class Simulation:
                   rng_kind: int = RNG_PHILOX, replication_offset: int = 0, device: int = 0, steps_per_launch: int = 0,
                   queue_capacity: int = 0, max_pending: int = 0, instrument: bool = False, trace_replications: int = 0,
                   trace_capacity: int = 0, stat_model_id: Optional[str] = None, batch_warmup: int = 0,
-                  batch_size: int = 0) -> "Simulation":
+                  batch_size: int = 0, series_capacity: int = 0) -> "Simulation":
         """``WebSimulation::post_json`` (web.rs:23-31) form of ``post``."""
         L = load_library()
         cfg = SimbConfig()
@@ -201,6 +210,7 @@ class Simulation:
         cfg.stat_model_id = stat_model_id.encode() if stat_model_id else None
         cfg.batch_warmup = batch_warmup
         cfg.batch_size = batch_size
+        cfg.series_capacity = series_capacity
         h = C.c_void_p()
         _check(L.simb_post_json(models_json.encode(), connectors_json.encode(), C.byref(cfg), C.byref(h)))
         return cls(h, replications, models_json, connectors_json)
@@ -367,6 +377,26 @@ class Simulation:
         b = np.zeros(self.replications, np.uint32)
         _check(load_library().simb_get_batch_means(self._h, m.ctypes.data, v.ctypes.data, b.ctypes.data, self.replications))
         return m, v, b
+
+    def get_series(self, replication: int = 0) -> np.ndarray:
+        """The captured waiting-time series of one replication (``series_capacity`` > 0)."""
+        L = load_library()
+        cnt = C.c_uint64()
+        _check(L.simb_get_series(self._h, replication, None, 0, C.byref(cnt)))
+        out = np.zeros(cnt.value, np.float64)
+        _check(L.simb_get_series(self._h, replication, out.ctypes.data, out.size, C.byref(cnt)))
+        return out
+
+    def steady_state(self, alpha: float) -> np.ndarray:
+        """``SteadyStateOutput::post`` + ``confidence_interval_mean`` (output_analysis/mod.rs:205-333) of every
+        replication's captured series, computed on the device.  Structured array with fields mean, variance,
+        lower, upper, deletion_point, batch_size, batch_count, status."""
+        dt = np.dtype([("mean", "f8"), ("variance", "f8"), ("lower", "f8"), ("upper", "f8"), ("deletion_point", "u4"),
+                       ("batch_size", "u4"), ("batch_count", "u4"), ("status", "i4")])
+        assert dt.itemsize == C.sizeof(_SteadyState)
+        out = np.zeros(self.replications, dt)
+        _check(load_library().simb_steady_state(self._h, float(alpha), out.ctypes.data, self.replications))
+        return out
 
     def stat_partial(self):
         s = C.c_double()

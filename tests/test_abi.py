@@ -27,7 +27,7 @@ def test_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     from sim_b200.simulator import SimbConfig, _CI, _Counters, _Message, _Record, _TraceEvent
-    assert C.sizeof(SimbConfig) == 80 and C.sizeof(_Message) == 248 and C.sizeof(_Record) == 136
+    assert C.sizeof(SimbConfig) == 88 and C.sizeof(_Message) == 248 and C.sizeof(_Record) == 136
     assert C.sizeof(_TraceEvent) == 24 and C.sizeof(_Counters) == 48 and C.sizeof(_CI) == 40
 
 

@@ -488,3 +488,65 @@ def test_full_size_large_mixed_shard():
         sl = slice(r0, r0 + 2)
         assert (events[sl] == ref["events"]).all() and _close(t[sl], ref["time"])
     sim.close()
+
+
+def test_device_steady_state_output_matches_host_and_oracle():
+    """SteadyStateOutput (deletion point of set_to_fixed_budget, <= 30 batch means, asymmetric
+    degrees of freedom; output_analysis/mod.rs:205-333) per replication ON THE DEVICE over the captured waiting
+    time series.  Bit-equal to the host restatement over the same series; the series itself and the resulting
+    interval equal what the oracle's records give."""
+    from sim_b200 import SimulationError
+    from sim_b200 import output_analysis as oa
+    models, conns = networks.tandem()
+    n, until, cap = 4096, 700.0, 1024
+    sim = _sim(models, conns, n, seed=29, instrument=False, stat_model_id="processor-3", series_capacity=cap)
+    sim.step_until(until)
+    for alpha in (0.05, 0.001):
+        res = sim.steady_state(alpha)
+        assert (res["status"] == 0).all()
+        assert (res["batch_count"] <= 30).all() and (res["batch_count"] >= 1).all()
+        assert (res["lower"] <= res["mean"]).all() and (res["mean"] <= res["upper"]).all()
+        _, cnt = sim.get_wait_stats()
+        assert ((res["deletion_point"] + res["batch_size"] * res["batch_count"]) == cnt).all()
+        for r in (0, 1, 63, 64, 2047, n - 1):
+            series = sim.get_series(r)
+            assert series.size == cnt[r]
+            ss = oa.SteadyStateOutput.post(series)
+            ci = ss.confidence_interval_mean(alpha)
+            got = res[r]
+            assert (got["deletion_point"], got["batch_size"], got["batch_count"]) == (ss.deletion_point, ss.batch_size, ss.batch_count)
+            assert got["lower"] == ci.lower() and got["upper"] == ci.upper()  # same operation order: bit-equal
+    # against the oracle: the series from its records, its SteadyStateOutput
+    rec = networks.tandem()[0]
+    for m in rec:
+        m.inner.store_records = True
+    res = sim.steady_state(0.05)
+    for r in (5, 1000):
+        o = oracle_api.OracleSimulation(rec, conns)
+        o.set_rng_philox(29, r)
+        assert o.step_until(until, collect=False)[0] == 0
+        arrival, waits = {}, []
+        for t, action, subject in o.get_records("processor-3")[1]:
+            if action == "Arrival":
+                arrival[subject] = t
+            elif action == "Processing Start":
+                waits.append(t - arrival.pop(subject))
+        assert _close(sim.get_series(r), waits)
+        e, ref = oracle_api.steady_state(waits, 0.05)
+        assert e == 0
+        assert (res[r]["deletion_point"], res[r]["batch_size"], res[r]["batch_count"]) == \
+            (ref["deletion_point"], ref["batch_size"], ref["batch_count"])
+        assert abs(res[r]["lower"] - ref["lower"]) < 1e-9 and abs(res[r]["upper"] - ref["upper"]) < 1e-9
+    # the grand mean over replications has a tight IID interval around the replication estimates
+    grand = oa.IndependentSample.post(res["mean"]).confidence_interval_mean(0.05)
+    assert grand.half_width() < 0.05 * abs(res["mean"].mean())
+    # an unlisted alpha panics in the reference (t_scores.rs:19-22); a too-small capacity is reported per replication
+    with pytest.raises(SimulationError) as ei:
+        sim.steady_state(0.3)
+    assert ei.value.name == "Panic"
+    small = _sim(models, conns, 64, seed=29, instrument=False, stat_model_id="processor-3", series_capacity=16)
+    small.step_until(until)
+    assert (small.steady_state(0.05)["status"] == 32).all()
+    none = _sim(models, conns, 64, seed=29, instrument=False, stat_model_id="processor-3")
+    with pytest.raises(SimulationError):
+        none.steady_state(0.05)
