@@ -386,12 +386,16 @@ int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool inst
     if (sp.total > 227u * 1024u) return (int)cudaErrorInvalidConfiguration;
     dims->tile = tile;
     dims->smem_bytes = sp.total;
+    if (const char* pad = getenv("SIMB_SMEM_PAD")) {  // occupancy-sensitivity experiments: extra unused bytes per CTA
+        if (*pad) dims->smem_bytes += (uint32_t)atoi(pad);
+        if (dims->smem_bytes > 227u * 1024u) dims->smem_bytes = 227u * 1024u;
+    }
     cudaError_t e = cudaFuncSetAttribute((const void*)pick_kernel(rng_kind, instrument, dims->shape, false, dims->rare),
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dims->smem_bytes);
     if (e != cudaSuccess) return (int)e;
     if (dims->shape >= 0) {
         e = cudaFuncSetAttribute((const void*)pick_kernel(rng_kind, instrument, dims->shape, true),
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dims->smem_bytes);
         if (e != cudaSuccess) return (int)e;
     }
     dims->grid = 0;  // one CTA per tile (profiles/r01_pipeline_experiments.txt: persistent / double-buffered variants lost)
