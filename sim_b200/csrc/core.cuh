@@ -78,7 +78,10 @@ struct Tables {
     const double* exp_f;
     const double* norm_x;
     const double* norm_f;
+    uint64_t* rng_cache;  // baked shapes: Philox draw cache, [rng_slots][lane] (shared memory on the device)
+    uint32_t rng_slots;   // prefetched draws per replication there (power of two >= 2)
 };
+#define SIMB_RNG_CACHE 8u /* rng_slots of fused launches (streaming launches keep one block: 2) */
 
 // ---- per-lane view of the replication's state tile ----------------------------------------------
 // d/w point at row 0 of this lane's column; consecutive rows are `stride` elements apart
@@ -94,8 +97,12 @@ struct Lane {
     uint32_t phase_lo, phase_hi;
     uint64_t hash;
     uint64_t pcg_lo, pcg_hi;
-    uint64_t c0, c1, c2;  // next draws of the Philox stream: c0 is draw number draw_idx
-    uint32_t ccount;      // valid entries in c0..c2
+    // Philox prefetch, one of two forms (Engine::next_u64): the generic interpreter keeps the next three draws
+    // in registers; baked shapes keep tab.rng_slots draws in a column of shared memory
+    uint64_t c0, c1, c2;  // generic: c0 is draw number draw_idx
+    uint64_t* rc;         // baked: draw number i sits in slot i % rng_slots of this column
+    uint32_t rc_stride;   // elements between consecutive slots of that column
+    uint32_t ccount;      // cached draws ahead of draw_idx
     uint32_t tmask;       // bit m: the mailbox holds a message for model m
     uint32_t dm_int, dm_ext;  // deferred continuous draws: "until_next_event[m] = sample(dist[m])" still
                               // owed from the previous internal phase / this external phase
@@ -180,23 +187,38 @@ struct Engine {
     SIMB_HD Engine(const SimbNetDesc& structure, const SimbNetDesc& values, const SimbDevState& s, const Tables& t)
         : net(structure), par(values), st(s), tab(t) {}
 
-    // Append the next Philox block to the per-lane draw cache (call only with ccount <= 2).  Draw
-    // number i is word pair (i & 1) of block i >> 1, so the cache is a pure prefetch of the stream.
     // Philox key of this replication: (global replication index, seed) -- derived on demand, not kept in registers
     SIMB_HD uint32_t key0(const Lane& ln) const { return (uint32_t)(st.rep_offset + ln.rep); }
     SIMB_HD uint32_t key1(const Lane& ln) const { return (uint32_t)st.seed + (uint32_t)((st.rep_offset + ln.rep) >> 32); }
-    // Append the next Philox block to the three-entry draw cache (call only with ccount <= 1).  Draw
-    // number i is word pair (i & 1) of block i >> 1, so the cache is a pure prefetch of the stream.
+    // Philox prefetch.  Draw number i is word pair (i & 1) of block i >> 1, so a cache of upcoming draws is a pure
+    // prefetch of the stream: nothing of it is persisted, a launch starts with an empty cache.
+    //  * generic interpreter: three draws in registers; a lane whose cache is down to one draw refills at the
+    //    step's converged point (call cache_push only with ccount <= 1).
+    //  * baked shapes: tab.rng_slots draws per lane in shared memory (slot i % rng_slots holds draw i), topped up at
+    //    ONE warp-converged point: when any lane of the warp is down to its last draw, every lane with room for a
+    //    block computes its next block, so the ten Philox rounds run once per ~3 warp iterations with most lanes
+    //    active (per-lane refills ran them every iteration with a quarter of the lanes active: +17 % on M/M/1).
+    SIMB_HD uint64_t& RC(Lane& ln, uint32_t i) { return ln.rc[(size_t)(i & (tab.rng_slots - 1u)) * ln.rc_stride]; }
     SIMB_HD void cache_push(Lane& ln, uint32_t nxt, uint64_t a, uint64_t b) {
-        if (nxt & 1u) a = b;  // odd position (only right after a state load): the block's second half
-        if (ln.ccount == 0) {
-            ln.c0 = a;
-            ln.c1 = b;
+        const bool odd = (nxt & 1u) != 0;  // odd position (only right after a state load): the block's second half
+        if (STATIC) {
+            if (odd) {
+                RC(ln, nxt) = b;
+            } else {
+                RC(ln, nxt) = a;
+                RC(ln, nxt + 1u) = b;
+            }
         } else {
-            ln.c1 = a;
-            ln.c2 = b;
+            if (odd) a = b;
+            if (ln.ccount == 0) {
+                ln.c0 = a;
+                ln.c1 = b;
+            } else {
+                ln.c1 = a;
+                ln.c2 = b;
+            }
         }
-        ln.ccount += (nxt & 1u) ? 1u : 2u;
+        ln.ccount += odd ? 1u : 2u;
     }
     SIMB_HD void philox_refill(Lane& ln) {
         const uint32_t nxt = ln.draw_idx + ln.ccount;
@@ -208,6 +230,16 @@ struct Engine {
         const uint32_t nxt = ln.draw_idx + ln.ccount;
         const U64Pair p = philox_pair_cold(key0(ln), key1(ln), nxt >> 1);
         cache_push(ln, nxt, p.a, p.b);
+    }
+    // the step's converged refill point (every lane of the warp calls it; `live` lanes take part)
+    SIMB_HD void philox_topup(Lane& ln, bool live) {
+        if (STATIC) {
+            if (warp_any(live && ln.ccount <= 1u)) {
+                if (live && ln.ccount + 2u <= tab.rng_slots) philox_refill(ln);
+            }
+        } else if (live && ln.ccount <= 1u) {
+            philox_refill(ln);
+        }
     }
 
     // queue / table storage in global memory, [slot][replication]
@@ -225,10 +257,15 @@ struct Engine {
     // ---- uniform u64 source (RngCore::next_u64 on the shared DynRng, services.rs:25-27) ----------
     SIMB_HD uint64_t next_u64(Lane& ln) {
         if (RNG == 0) {
-            if (ln.ccount == 0) philox_refill_cold(ln);  // rare: the step refills at a warp-uniform point
-            const uint64_t v = ln.c0;
-            ln.c0 = ln.c1;
-            ln.c1 = ln.c2;
+            if (ln.ccount == 0) philox_refill_cold(ln);  // rare: the step tops up at a warp-uniform point
+            uint64_t v;
+            if (STATIC) {
+                v = RC(ln, ln.draw_idx);
+            } else {
+                v = ln.c0;
+                ln.c0 = ln.c1;
+                ln.c1 = ln.c2;
+            }
             ln.ccount--;
             ln.draw_idx++;
             return v;
@@ -1121,10 +1158,8 @@ struct Engine {
             }
         }
         // ---- pay the deferred draws (and top up the Philox prefetch) at this converged point ----
-        if (live) {
-            if (RNG == 0 && ln.ccount <= 1u) philox_refill(ln);
-            flush_draws(ln);
-        }
+        if (RNG == 0) philox_topup(ln, live);
+        if (live) flush_draws(ln);
         // A failed events_ext aborts the step (`?` at :222); the replication freezes.
         const bool go = live && !ln.err;
         // ---- time advance (:225-236) ----

@@ -362,7 +362,7 @@ int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool inst
     // when that costs no occupancy (the ring slots live in L1 between steps).
     uint32_t tile = 256, best_warps = 0;
     for (uint32_t cand = 256; cand >= 32; cand >>= 1) {
-        const uint32_t smem = smem_plan(net, cand).total;
+        const uint32_t smem = smem_plan(net, cand, 0).total;
         if (smem > 227u * 1024u) continue;
         uint32_t ctas = (227u * 1024u) / smem;
         const uint32_t by_regs = 65536u / (64u * cand), by_threads = 2048u / cand;
@@ -382,7 +382,8 @@ int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool inst
         if (t < tile) tile = t;
     }
     if (dims->shape >= 0 && tile != SIMB_SHAPE_TILE) dims->shape = -1;  // baked-shape kernels assume the full tile width
-    SmemPlan sp = smem_plan(net, tile);
+    // baked-shape kernels add their Philox draw cache: SIMB_RNG_CACHE draws per replication on fused launches
+    SmemPlan sp = smem_plan(net, tile, dims->shape >= 0 ? SIMB_RNG_CACHE : 0u);
     if (sp.total > 227u * 1024u) return (int)cudaErrorInvalidConfiguration;
     dims->tile = tile;
     dims->smem_bytes = sp.total;
@@ -409,11 +410,15 @@ int engine_launch_step(const SimbNetDesc& net, const SimbDevState& st, const Sim
     const uint32_t grid = n_tiles ? n_tiles : all - tile0;
     SimbLaunch la = la_in;
     la.tile0 = tile0;
+    const bool streaming = la.k <= SIMB_STREAM_MAX_K;
+    la.rng_slots = dims.shape >= 0 ? (streaming ? 2u : SIMB_RNG_CACHE) : 0u;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(dims.tile);
-    cfg.dynamicSmemBytes = dims.smem_bytes;
+    // streaming launches keep one Philox block per replication instead of SIMB_RNG_CACHE draws: less shared
+    // memory per CTA, one more resident CTA per SM
+    cfg.dynamicSmemBytes = dims.smem_bytes - (dims.shape >= 0 ? (SIMB_RNG_CACHE - la.rng_slots) * 8u * dims.tile : 0u);
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // pairs with griddepcontrol.* in the kernel
@@ -421,7 +426,7 @@ int engine_launch_step(const SimbNetDesc& net, const SimbDevState& st, const Sim
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const uint32_t ca = count_active ? 1u : 0u;
-    return (int)cudaLaunchKernelEx(&cfg, pick_kernel(rng_kind, instrument, dims.shape, la.k <= SIMB_STREAM_MAX_K, dims.rare), net, st,
+    return (int)cudaLaunchKernelEx(&cfg, pick_kernel(rng_kind, instrument, dims.shape, streaming, dims.rare), net, st,
                                    la, ca);
 }
 

@@ -180,6 +180,6 @@ struct SimbLaunch {
     uint32_t epoch;       // step_until call epoch (ctl epoch == epoch => finished in this call)
     uint32_t settle;      // 1 = pay every deferred draw before the state is stored (last launch of an API call)
     uint32_t tile0;       // first tile of this grid (a pass over the batch may be split into concurrent grids)
-    uint32_t reserved;
+    uint32_t rng_slots;   // baked-shape kernels: Philox draws cached per replication in shared memory (0 = none)
     double until;
 };

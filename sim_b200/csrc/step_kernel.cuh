@@ -57,9 +57,10 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // shared memory carve-up (all offsets multiples of 16 B): barrier, reduction scratch, ziggurat x tables, then
 // the state tile (f64 rows followed by u32 rows).
 struct SmemPlan {
-    uint32_t off_bar, off_red, off_expx, off_normx, off_tiles, stage_bytes, d_bytes, total;
+    uint32_t off_bar, off_red, off_expx, off_normx, off_rng, off_tiles, stage_bytes, d_bytes, total;
 };
-__host__ __device__ inline SmemPlan smem_plan(const SimbNetDesc& net, uint32_t tile) {
+// `rng_slots`: Philox draws cached per replication in shared memory (baked-shape kernels; 0 = none)
+__host__ __device__ inline SmemPlan smem_plan(const SimbNetDesc& net, uint32_t tile, uint32_t rng_slots) {
     SmemPlan p;
     uint32_t o = 0;
     p.off_bar = o;  // three mbarriers: one per stage + one for the tables
@@ -71,6 +72,8 @@ __host__ __device__ inline SmemPlan smem_plan(const SimbNetDesc& net, uint32_t t
     p.off_normx = o;
     if (net.uses_normal) o += 2064;
     o = (o + 127u) & ~127u;
+    p.off_rng = o;
+    o += rng_slots * 8u * tile;
     p.off_tiles = o;
     p.d_bytes = net.n_drows * tile * 8u;
     p.stage_bytes = (p.d_bytes + net.n_wrows * tile * 4u + 127u) & ~127u;
@@ -130,7 +133,8 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t tile = SHAPE >= 0 ? SIMB_SHAPE_TILE : blockDim.x;
     const uint32_t tid = threadIdx.x;
-    const SmemPlan sp = smem_plan(net, tile);
+    const uint32_t rng_slots = SHAPE >= 0 ? la.rng_slots : 0u;
+    const SmemPlan sp = smem_plan(net, tile, rng_slots);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + sp.off_bar);
     unsigned long long* s_red = reinterpret_cast<unsigned long long*>(smem + sp.off_red);
     double* s_expx = reinterpret_cast<double*>(smem + sp.off_expx);
@@ -177,6 +181,8 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
     tab.exp_f = ZIG_EXP_F;
     tab.norm_x = s_normx;
     tab.norm_f = ZIG_NORM_F;
+    tab.rng_cache = reinterpret_cast<uint64_t*>(smem + sp.off_rng);
+    tab.rng_slots = rng_slots;
     Engine<RNG, shape_tier<SHAPE>(), RARE> eng(net, net_param, st, tab);
     while (!mbar_try_wait(bar, 0)) {
     }
@@ -185,6 +191,8 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
     Lane ln;
     ln.d = s_d + tid;
     ln.w = s_w + tid;
+    ln.rc = tab.rng_cache + tid;
+    ln.rc_stride = tile;
     ln.stride = tile;
     ln.rep = (uint32_t)(base + tid);
     const uint32_t ctl = eng.lane_load(ln, INSTR);

@@ -30,12 +30,14 @@ struct HS {
     std::vector<uint64_t> ext;
     uint32_t epoch = 0;
     uint64_t settle_every = 0;
+    uint32_t rng_slots = SIMB_RNG_CACHE;  // Philox draws cached by the baked-shape code path (2 = streaming launches)
     int shape = -1;
 };
 
 template <int RNG, bool INSTR, int SM>
 void run(HS* h, int mode, uint64_t k, double until) {
-    Tables tab{ZIG_EXP_X, ZIG_EXP_F, ZIG_NORM_X, ZIG_NORM_F};
+    uint64_t rng_cache[SIMB_RNG_CACHE];  // one lane at a time: its column is the whole cache (lane stride applies)
+    Tables tab{ZIG_EXP_X, ZIG_EXP_F, ZIG_NORM_X, ZIG_NORM_F, rng_cache, h->rng_slots};
     // SM > 0: the literal-index ("baked shape") code path of the interpreter, structure from the host
     // copy of the baked descriptor, values from the lowered network -- as the specialised kernels do
     Engine<RNG, SM> eng(SM > 0 ? *kShapeHost[h->shape] : h->hn.desc, h->hn.desc, h->st, tab);
@@ -45,6 +47,8 @@ void run(HS* h, int mode, uint64_t k, double until) {
         ln.w = h->w.data() + r;
         ln.stride = (uint32_t)h->n;
         ln.rep = (uint32_t)r;
+        ln.rc = rng_cache;
+        ln.rc_stride = 1;
         eng.lane_load(ln, INSTR);
         bool done = false;
         for (uint64_t i = 0; mode == 1 || i < k; i++) {
@@ -163,6 +167,7 @@ void* hs_new(const char* models, const char* connectors, uint64_t n, uint64_t re
 }
 void hs_free(void* h) { delete (HS*)h; }
 void hs_set_reload_every(void* h, uint64_t n) { ((HS*)h)->settle_every = n; }
+void hs_set_rng_slots(void* h, uint32_t n) { ((HS*)h)->rng_slots = n; }
 // select the baked-shape code path when the lowered network matches shape `k` structurally; returns 1 on match
 int hs_use_shape(void* hv, int k) {
     HS* h = (HS*)hv;

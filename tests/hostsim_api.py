@@ -54,6 +54,10 @@ class HostSim:
         """store + reload the lane state every n steps, like consecutive kernel launches of K = n"""
         self.L.hs_set_reload_every(self.h, C.c_uint64(n))
 
+    def set_rng_slots(self, n):
+        """Philox draws cached per replication by the baked-shape code path (8 fused, 2 streaming launches)"""
+        self.L.hs_set_rng_slots(self.h, C.c_uint32(n))
+
     def use_shape(self, k):
         """run through the literal-index (baked shape) code path; False if the network does not match shape k"""
         return bool(self.L.hs_use_shape(self.h, k))

@@ -195,10 +195,18 @@ def test_baked_shape_code_path_equals_generic_and_oracle(shape, name, stat):
     assert not b.use_shape(shape + 7)  # no such baked shape
     assert b.use_shape(shape)
     b.set_reload_every(3)
+    # the baked path prefetches Philox draws into a shared-memory column: 8 slots on fused launches, one block (2)
+    # on streaming launches; the stream consumed must not depend on it
+    c = H.HostSim(models, conns, n=12, seed=5, instrument=False, stat_model_id=stat)
+    assert c.use_shape(shape)
+    c.set_rng_slots(2)
+    c.set_reload_every(1)
     a.step_until(200.0)
     b.step_until(200.0)
+    c.step_until(200.0)
     assert (a.steps() == b.steps()).all() and (a.events() == b.events()).all() and (a.draws() == b.draws()).all()
     assert (a.time() == b.time()).all() and (b.errors() == 0).all()
+    assert (c.steps() == b.steps()).all() and (c.draws() == b.draws()).all() and (c.time() == b.time()).all()
     for m in range(len(models)):
         assert np.array_equal(a.until(m), b.until(m), equal_nan=True)
     for r in (0, 11):
