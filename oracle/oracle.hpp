@@ -272,5 +272,6 @@ std::unique_ptr<ModelBase> make_batcher(const std::string& in, const std::string
 std::unique_ptr<ModelBase> make_passive(const std::string& in);  // sim/tests/custom.rs:18-86
 // state injection used by sim/tests/web.rs:30-46 (Processor `state` block)
 int preload_processor(ModelBase* m, int phase_active, double until_next_event, const std::vector<std::string>& queue);
+int preload_state(ModelBase* m, int phase, double until_next_event, const std::vector<std::string>& jobs);
 
 }  // namespace orc

@@ -153,6 +153,12 @@ int orc_preload_processor(void* hv, const char* id, int active, double until, co
         if (m.id == id) return preload_processor(m.inner.get(), active, until, split_nl(queue_nl));
     return ModelNotFound;
 }
+int orc_preload_state(void* hv, const char* id, int phase, double until, const char* jobs_nl) {
+    Handle* h = (Handle*)hv;
+    for (auto& m : h->staged_models)
+        if (m.id == id) return preload_state(m.inner.get(), phase, until, split_nl(jobs_nl));
+    return ModelNotFound;
+}
 // Simulation::put with fresh clones of the staged models (the reference's replication idiom:
 // reset() + put(models.to_vec(), ..), sim/tests/simulations.rs:162-170)
 int orc_post(void* hv) {

@@ -480,6 +480,8 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
                 std::string ph;
                 if (get_str(*state, "phase", &ph)) p.phase0 = ph == "Closed" ? 1 : ph == "Pass" ? 2 : 0;
                 get_num(*state, "untilNextEvent", &p.u0);
+                get_str_list(*state, "jobs", &p.preload);
+                if (p.preload.size() > p.ring_cap) p.ring_cap = clamp_u32(p.preload.size(), 65535);
             }
         } else if (t == "ExclusiveGateway") {  // exclusive_gateway.rs:20-32
             md.type = MT_EXCLUSIVE_GATEWAY;
@@ -492,6 +494,13 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
             p.ring_cap = tcap;
             p.n_words = 1;
             p.words0 = {0};
+            if (state && state->is_object()) {  // exclusive_gateway.rs:55-78
+                std::string ph;
+                if (get_str(*state, "phase", &ph)) p.phase0 = ph == "Pass" ? 1 : 0;
+                get_num(*state, "untilNextEvent", &p.u0);
+                get_str_list(*state, "jobs", &p.preload);
+                if (p.preload.size() > p.ring_cap) p.ring_cap = clamp_u32(p.preload.size(), 65535);
+            }
         } else if (t == "ParallelGateway") {  // parallel_gateway.rs:19-28
             md.type = MT_PARALLEL_GATEWAY;
             if (!need_ports(true, true) || !get_str_list(*pin, "flowPaths", &hm.ports_in) ||
@@ -547,6 +556,13 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
             p.ring_cap = clamp_u32(2ull * (uint64_t)md.cap + 8ull, 65535);
             p.n_words = 1;
             p.words0 = {0};
+            if (state && state->is_object()) {  // batcher.rs:46-74
+                std::string ph;
+                if (get_str(*state, "phase", &ph)) p.phase0 = ph == "Batching" ? 1 : ph == "Release" ? 2 : 0;
+                get_num(*state, "untilNextEvent", &p.u0);
+                get_str_list(*state, "jobs", &p.preload);
+                if (p.preload.size() > p.ring_cap) p.ring_cap = clamp_u32(p.preload.size(), 65535);
+            }
         } else if (t == "Passive") {  // sim/tests/custom.rs:18-86
             md.type = MT_PASSIVE;
             if (pin && pin->is_object()) port(pin, "job", &hm.ports_in);

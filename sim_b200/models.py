@@ -13,6 +13,9 @@ from .input_modeling import _Variant
 
 class _ModelBody:
     type_name = "?"
+    # optional ``state`` block of the wire form (the reference's models carry `#[serde(default)] state`, e.g.
+    # processor.rs:36-37, gate.rs:26-27): set it as an attribute to inject model state on input (web.rs:30-46)
+    state = None
 
     def fields(self) -> dict:
         raise NotImplementedError
@@ -267,4 +270,6 @@ class Model:
     def to_dict(self) -> dict:
         d = {"id": self.id, "type": self.inner.type_name}
         d.update(self.inner.fields())
+        if "state" not in d and getattr(self.inner, "state", None) is not None:
+            d["state"] = self.inner.state
         return d

@@ -258,6 +258,37 @@ def beta_variables():
     return models, connectors
 
 
+def state_injection(store_records=False):
+    """`state` blocks injected on input (the models' `#[serde(default)] state`, as tests/web.rs:30-46 does for a
+    Processor) for the other queueing models: a Gate, an ExclusiveGateway and a LoadBalancer that start with
+    jobs to pass, a Batcher that starts with a half-built batch and a running timer."""
+    def with_state(body, state):
+        body.state = state
+        return body
+    models = [
+        Model.new("generator", Generator.new(Exp(1.0), None, "job", store_records, None)),
+        Model.new("gate", with_state(Gate.new("job", "activation", "deactivation", "job", store_records),
+                                     {"phase": "Pass", "untilNextEvent": 0.0, "jobs": ["pre 1", "pre 2"], "records": []})),
+        Model.new("exclusive", with_state(ExclusiveGateway.new(["in"], ["a", "b"], IndexRandomVariable.WeightedIndex([1, 1]),
+                                                               store_records, None),
+                                          {"phase": "Pass", "untilNextEvent": 0.0, "jobs": ["x 1", "x 2", "x 3"], "records": []})),
+        Model.new("balancer", with_state(LoadBalancer.new("job", ["p", "q"], store_records),
+                                         {"phase": "LoadBalancing", "untilNextEvent": 0.0, "jobs": ["l 1", "l 2"], "records": []})),
+        Model.new("batcher-p", with_state(Batcher.new("job", "job", 3.0, 3, store_records),
+                                          {"phase": "Batching", "untilNextEvent": 2.5, "jobs": ["b 1", "b 2"], "records": []})),
+        Model.new("batcher-q", Batcher.new("job", "job", 3.0, 3, store_records)),
+        _storage("storage-p", store_records), _storage("storage-q", store_records),
+    ]
+    C = Connector.new
+    connectors = [
+        C("c1", "generator", "gate", "job", "job"), C("c2", "gate", "exclusive", "job", "in"),
+        C("c3", "exclusive", "balancer", "a", "job"), C("c4", "exclusive", "balancer", "b", "job"),
+        C("c5", "balancer", "batcher-p", "p", "job"), C("c6", "balancer", "batcher-q", "q", "job"),
+        C("c7", "batcher-p", "storage-p", "job", "store"), C("c8", "batcher-q", "storage-q", "job", "store"),
+    ]
+    return models, connectors
+
+
 # ---- BASELINE.json configurations (shapes fixed in SURVEY.md 8(d)) -----------------------------------
 def tandem():
     """config 3: generator Exp(1.0) -> load balancer (3 paths) -> 3x stage-1 processor Exp(0.4) cap 8 ->
@@ -384,6 +415,6 @@ ALL = {
     "gate_blocking": gate_blocking, "load_balancer": load_balancer, "parallel_gateway": parallel_gateway,
     "stochastic_gate": stochastic_gate, "batcher": batcher, "stopwatch": stopwatch,
     "processor_from_queue": processor_from_queue, "processor_network": processor_network,
-    "generator_passive": generator_passive, "more_variables": more_variables, "beta_variables": beta_variables, "tandem": tandem, "gateway_network": gateway_network,
+    "generator_passive": generator_passive, "more_variables": more_variables, "beta_variables": beta_variables, "state_injection": state_injection, "tandem": tandem, "gateway_network": gateway_network,
     "large_mixed": large_mixed,
 }

@@ -128,6 +128,14 @@ class OracleSimulation:
             L.orc_add_passive(h, b, _b(i.job_port))
         else:
             raise TypeError(type(i))
+        st = getattr(i, "state", None)
+        if st is not None and not isinstance(i, M.Processor):
+            phases = {M.Gate: ["Open", "Closed", "Pass"], M.Batcher: ["Passive", "Batching", "Release"],
+                      M.ExclusiveGateway: ["Passive", "Pass"], M.LoadBalancer: ["Passive", "LoadBalancing"]}[type(i)]
+            until = st.get("untilNextEvent", float("inf"))
+            until = float("inf") if until is None else float(until)
+            e = L.orc_preload_state(h, b, phases.index(st.get("phase", phases[0])), d(until), _b("\n".join(st.get("jobs", []))))
+            assert e == 0, e
 
     # ---- rng ----
     def set_rng_pcg(self, seed=42):
