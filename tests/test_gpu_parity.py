@@ -214,7 +214,7 @@ def test_status_strings():
     assert sim.get_status("load-balancer-01") == "Listening for requests"
 
 
-@pytest.mark.parametrize("name,stat,shape", [("mm1", "processor-01", "mm1"), ("tandem", None, "generic"),
+@pytest.mark.parametrize("name,stat,shape", [("mm1", "processor-01", "mm1"), ("mm1", None, "mm1_plain"), ("tandem", None, "generic"),
                                              ("gateway_network", None, "generic"), ("large_mixed", None, "generic")])
 @pytest.mark.parametrize("k", [1, 16])
 def test_production_kernels_match_oracle(name, stat, shape, k):

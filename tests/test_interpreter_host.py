@@ -181,7 +181,7 @@ def test_all_passive_network():
     assert hs.time()[0] == float("inf") and np.isnan(hs.until(0)[0])
 
 
-BAKED = [("mm1", "processor-01")]  # tools/gen_shapes.py BASELINE
+BAKED = [("mm1", "processor-01"), ("mm1", None)]  # tools/gen_shapes.py BASELINE (network, statistic model)
 
 
 @pytest.mark.parametrize("shape,name,stat", [(i, n, s) for i, (n, s) in enumerate(BAKED)])
