@@ -295,9 +295,11 @@ StepKernel simb_shape_stream_kernel_2();
 StepKernel simb_shape_stream_kernel_3();
 
 // generic interpreter with the rare continuous variables compiled in (engine_rare.cu)
-StepKernel simb_generic_rare_kernel(int rng_kind, bool instrument);
+StepKernel simb_generic_rare_kernel(int rng_kind, bool instrument, bool narrow);
 
-static StepKernel pick_kernel(int rng_kind, bool instrument, int shape, bool stream = false, bool rare = true) {
+// variant: baked shape -> streaming launch; generic -> narrow tile (see step_kernel.cuh)
+static StepKernel pick_kernel(int rng_kind, bool instrument, int shape, bool stream = false, bool rare = true,
+                              bool narrow = false) {
     if (!instrument && rng_kind == 0) {  // baked shapes exist for the production configuration only
         switch (shape) {
             case 0: return stream ? simb_shape_stream_kernel_0() : simb_shape_kernel_0();
@@ -307,7 +309,8 @@ static StepKernel pick_kernel(int rng_kind, bool instrument, int shape, bool str
             default: break;
         }
     }
-    if (rare) return simb_generic_rare_kernel(rng_kind, instrument);
+    if (rare) return simb_generic_rare_kernel(rng_kind, instrument, narrow);
+    if (narrow && !instrument && rng_kind == 0) return simb_step_kernel<0, false, -1, true, false>;
     if (instrument) {
         if (rng_kind == 0) return simb_step_kernel<0, true, -1, false, false>;
         if (rng_kind == 1) return simb_step_kernel<1, true, -1, false, false>;
@@ -365,7 +368,8 @@ int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool inst
         const uint32_t smem = smem_plan(net, cand, 0).total;
         if (smem > 227u * 1024u) continue;
         uint32_t ctas = (227u * 1024u) / smem;
-        const uint32_t by_regs = 65536u / (64u * cand), by_threads = 2048u / cand;
+        const uint32_t regs = (cand <= 128u && !instrument && rng_kind == 0) ? 96u : 64u;  // narrow-tile variant
+        const uint32_t by_regs = 65536u / (regs * cand), by_threads = 2048u / cand;
         if (ctas > by_regs) ctas = by_regs;
         if (ctas > by_threads) ctas = by_threads;
         if (ctas > 32u) ctas = 32u;
@@ -381,6 +385,10 @@ int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool inst
         while (t < n) t <<= 1;
         if (t < tile) tile = t;
     }
+    if (const char* force = getenv("SIMB_TILE")) {  // A/B switch: force the tile width (32..256, power of two)
+        const uint32_t t = (uint32_t)atoi(force);
+        if (t >= 32u && t <= 256u && (t & (t - 1u)) == 0u && smem_plan(net, t, 0).total <= 227u * 1024u) tile = t;
+    }
     if (dims->shape >= 0 && tile != SIMB_SHAPE_TILE) dims->shape = -1;  // baked-shape kernels assume the full tile width
     // baked-shape kernels add their Philox draw cache: SIMB_RNG_CACHE draws per replication on fused launches
     SmemPlan sp = smem_plan(net, tile, dims->shape >= 0 ? SIMB_RNG_CACHE : 0u);
@@ -391,7 +399,7 @@ int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool inst
         if (*pad) dims->smem_bytes += (uint32_t)atoi(pad);
         if (dims->smem_bytes > 227u * 1024u) dims->smem_bytes = 227u * 1024u;
     }
-    cudaError_t e = cudaFuncSetAttribute((const void*)pick_kernel(rng_kind, instrument, dims->shape, false, dims->rare),
+    cudaError_t e = cudaFuncSetAttribute((const void*)pick_kernel(rng_kind, instrument, dims->shape, false, dims->rare, dims->tile <= 128u),
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dims->smem_bytes);
     if (e != cudaSuccess) return (int)e;
     if (dims->shape >= 0) {
@@ -426,7 +434,7 @@ int engine_launch_step(const SimbNetDesc& net, const SimbDevState& st, const Sim
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const uint32_t ca = count_active ? 1u : 0u;
-    return (int)cudaLaunchKernelEx(&cfg, pick_kernel(rng_kind, instrument, dims.shape, streaming, dims.rare), net, st,
+    return (int)cudaLaunchKernelEx(&cfg, pick_kernel(rng_kind, instrument, dims.shape, streaming, dims.rare, dims.tile <= 128u), net, st,
                                    la, ca);
 }
 

@@ -4,7 +4,8 @@
 #include "step_kernel.cuh"
 
 namespace simb {
-StepKernel simb_generic_rare_kernel(int rng_kind, bool instrument) {
+StepKernel simb_generic_rare_kernel(int rng_kind, bool instrument, bool narrow) {
+    if (narrow && !instrument && rng_kind == 0) return simb_step_kernel<0, false, -1, true, true>;
     if (instrument) {
         if (rng_kind == 0) return simb_step_kernel<0, true, -1, false, true>;
         if (rng_kind == 1) return simb_step_kernel<1, true, -1, false, true>;

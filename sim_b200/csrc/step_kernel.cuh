@@ -124,9 +124,14 @@ __host__ __device__ constexpr int shape_tier() {  // model-count tier of a baked
 // One CTA = one tile of blockDim.x consecutive replications.  Kernels of baked shapes are only launched
 // with SIMB_SHAPE_TILE threads, so their shared-memory row offsets are immediates.
 #define SIMB_SHAPE_TILE 256u
-template <int RNG, bool INSTR, int SHAPE, bool STREAM = false, bool RARE = true>
-__global__ void __launch_bounds__(256, SHAPE >= 0 ? (STREAM ? SIMB_SHAPE_STREAM_MIN_BLOCKS : SIMB_SHAPE_MIN_BLOCKS)
-                                                  : SIMB_MIN_BLOCKS)
+// VARIANT: baked shapes -- true = streaming launch (k <= SIMB_STREAM_MAX_K); generic interpreter -- true = narrow
+// tile (<= 128 replications per CTA: networks whose state column is large), compiled for up to 96 registers: the
+// CTA count of such networks is bounded by shared memory, so the wider register budget is free and removes the
+// spills / rematerialisation of the 64-register build (+10-13 % on the 16- and 32-model networks).
+template <int RNG, bool INSTR, int SHAPE, bool VARIANT = false, bool RARE = true>
+__global__ void __launch_bounds__((SHAPE < 0 && VARIANT) ? 128 : 256,
+                                  SHAPE >= 0 ? (VARIANT ? SIMB_SHAPE_STREAM_MIN_BLOCKS : SIMB_SHAPE_MIN_BLOCKS)
+                                             : (VARIANT ? 5 : SIMB_MIN_BLOCKS))
 simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_constant__ SimbDevState st,
                  const __grid_constant__ SimbLaunch la, const uint32_t count_active) {
     const SimbNetDesc& net = shape_desc<SHAPE>(net_param);
