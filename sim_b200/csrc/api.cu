@@ -56,6 +56,9 @@ struct simb_sim {
     double kernel_ms = 0.0;
     bool instrument = false;
     int rng_kind = 0;
+    uint64_t passes = 0;        // passes issued (parity = sweep direction)
+    bool l2_keep = true;        // SIMB_NO_L2_KEEP = A/B switch
+    bool sweep_reverse = true;  // alternate the sweep direction of consecutive passes (SIMB_NO_REVERSE = A/B switch)
     std::string json;  // result of the last *_json call (handle-owned, see simb.h)
 };
 
@@ -218,7 +221,10 @@ int grids_per_pass(const simb_sim* s) {
 }
 // One pass over the batch: the step kernel on every tile, issued as s->n_lanes concurrent grids.  The side
 // streams must have been forked from s->stream (pass_fork) and are joined back by pass_join.
-int launch_pass(simb_sim* s, const SimbLaunch& la, bool count_active, uint64_t* issued) {
+int launch_pass(simb_sim* s, const SimbLaunch& la_in, bool count_active, uint64_t* issued) {
+    SimbLaunch la = la_in;
+    la.reverse = s->sweep_reverse && (s->passes++ & 1u) ? 1u : 0u;
+    la.l2_keep = s->l2_keep && la.k <= 8u ? 1u : 0u;  // only passes that re-stream the state soon
     const SimbNetDesc& net = s->hn.desc;
     const uint32_t tiles = (uint32_t)(s->st.stride / s->dims.tile);
     const int lanes = grids_per_pass(s);
@@ -423,6 +429,10 @@ int simb_post_json(const char* models_json, const char* connectors_json, const s
     {
         // measured (profiles/r01_pipeline_experiments.txt): two concurrent half-batch grids hide the grid
         // drain / ramp between dependent launches (+12 % at one step per launch); SIMB_STREAMS is the A/B switch
+        const char* nk = getenv("SIMB_NO_L2_KEEP");
+        s->l2_keep = !(nk && *nk);
+        const char* nr = getenv("SIMB_NO_REVERSE");
+        s->sweep_reverse = !(nr && *nr);
         const char* ns = getenv("SIMB_STREAMS");
         int want = ns && *ns ? atoi(ns) : 2;
         s->n_lanes = want < 1 ? 1 : want > simb_sim::MAX_LANES ? simb_sim::MAX_LANES : want;

@@ -181,5 +181,8 @@ struct SimbLaunch {
     uint32_t settle;      // 1 = pay every deferred draw before the state is stored (last launch of an API call)
     uint32_t tile0;       // first tile of this grid (a pass over the batch may be split into concurrent grids)
     uint32_t rng_slots;   // baked-shape kernels: Philox draws cached per replication in shared memory (0 = none)
+    uint32_t reverse;     // 1 = CTA i takes the grid's tile (gridDim.x - 1 - i): consecutive passes sweep the batch in
+                          // opposite directions, so a pass starts on the tiles the previous one left in L2
+    uint32_t l2_keep;     // 1 = the state tile copies carry the L2 evict_last hint (streaming passes)
     double until;
 };

@@ -50,6 +50,25 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
                  "r"(bytes)
                  : "memory");
 }
+// the same copies with an L2 eviction-priority hint (createpolicy): the state tiles of a streaming pass are
+// marked evict_last so that the next pass -- which sweeps the batch in the opposite direction -- finds as much
+// of the state as the 126 MB L2 can hold, while the sparsely touched ring slots take the normal priority
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_hint(void* gmem_dst, const void* smem_src, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gmem_dst),
+                 "r"(smem_u32(smem_src)), "r"(bytes), "l"(pol)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -147,7 +166,8 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
     double* s_d = reinterpret_cast<double*>(smem + sp.off_tiles);
     uint32_t* s_w = reinterpret_cast<uint32_t*>(smem + sp.off_tiles + sp.d_bytes);
     const uint32_t n_rows = net.n_drows + net.n_wrows;
-    const uint64_t base = (uint64_t)(blockIdx.x + la.tile0) * tile;  // first replication (padded index) of this tile
+    const uint32_t tile_in_grid = la.reverse ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
+    const uint64_t base = (uint64_t)(tile_in_grid + la.tile0) * tile;  // first replication (padded index) of this tile
 
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -173,11 +193,15 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
             if (net.uses_normal) bulk_g2s(s_normx, ZIG_NORM_X, ZIG_BYTES, bar);
         }
         __syncwarp();
+        const uint64_t pol = l2_policy_evict_last();
         for (uint32_t r = tid; r < n_rows; r += 32) {
-            if (r < net.n_drows) bulk_g2s(s_d + (size_t)r * tile, st.d + (uint64_t)r * st.stride + base, tile * 8u, bar);
-            else {
+            if (r < net.n_drows) {
+                if (la.l2_keep) bulk_g2s_hint(s_d + (size_t)r * tile, st.d + (uint64_t)r * st.stride + base, tile * 8u, bar, pol);
+                else bulk_g2s(s_d + (size_t)r * tile, st.d + (uint64_t)r * st.stride + base, tile * 8u, bar);
+            } else {
                 const uint32_t rr = r - net.n_drows;
-                bulk_g2s(s_w + (size_t)rr * tile, st.w + (uint64_t)rr * st.stride + base, tile * 4u, bar);
+                if (la.l2_keep) bulk_g2s_hint(s_w + (size_t)rr * tile, st.w + (uint64_t)rr * st.stride + base, tile * 4u, bar, pol);
+                else bulk_g2s(s_w + (size_t)rr * tile, st.w + (uint64_t)rr * st.stride + base, tile * 4u, bar);
             }
         }
     }
@@ -234,11 +258,15 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
     }
     const bool any_stepped = __syncthreads_or(stepped) != 0;
     if (any_stepped && tid < 32) {
+        const uint64_t pol = l2_policy_evict_last();
         for (uint32_t r = tid; r < n_rows; r += 32) {
-            if (r < net.n_drows) bulk_s2g(st.d + (uint64_t)r * st.stride + base, s_d + (size_t)r * tile, tile * 8u);
-            else {
+            if (r < net.n_drows) {
+                if (la.l2_keep) bulk_s2g_hint(st.d + (uint64_t)r * st.stride + base, s_d + (size_t)r * tile, tile * 8u, pol);
+                else bulk_s2g(st.d + (uint64_t)r * st.stride + base, s_d + (size_t)r * tile, tile * 8u);
+            } else {
                 const uint32_t rr = r - net.n_drows;
-                bulk_s2g(st.w + (uint64_t)rr * st.stride + base, s_w + (size_t)rr * tile, tile * 4u);
+                if (la.l2_keep) bulk_s2g_hint(st.w + (uint64_t)rr * st.stride + base, s_w + (size_t)rr * tile, tile * 4u, pol);
+                else bulk_s2g(st.w + (uint64_t)rr * st.stride + base, s_w + (size_t)rr * tile, tile * 4u);
             }
         }
         bulk_commit();
