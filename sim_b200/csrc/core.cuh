@@ -175,7 +175,10 @@ static inline U64Pair philox_pair_cold(uint32_t key0, uint32_t key1, uint32_t ct
 // distribution parameters still come from the launch's descriptor `par`.  SM == 0: generic interpreter.
 // RARE: the less common continuous variables (Beta, Gamma, LogNormal, Weibull) are compiled in.  The generic
 // kernel exists with and without them: they triple its code size, and it is bound by instruction fetch.
-template <int RNG, int SM = 0, bool RARE = true>
+// BASIC: only the Generator / Processor / Storage / LoadBalancer / Passive handlers are compiled in (queueing
+// networks such as M/M/1 and the tandem configuration); the generic kernel exists in this form too, again
+// because its speed follows its code size.
+template <int RNG, int SM = 0, bool RARE = true, bool BASIC = false>
 struct Engine {
     static constexpr bool STATIC = SM > 0;
     const SimbNetDesc& net;  // structure
@@ -796,6 +799,7 @@ struct Engine {
                 break;
             }
             case MT_GATE: {  // gate.rs:180-195
+                if (BASIC) break;
                 if (port == 0) {
                     if (ln.phase(m) != 1) {  // pass_job :127-137
                         ln.set_phase(m, 2);
@@ -818,6 +822,7 @@ struct Engine {
                 break;
             }
             case MT_EXCLUSIVE_GATEWAY: {  // pass_job exclusive_gateway.rs:95-108 (any port)
+                if (BASIC) break;
                 ln.set_phase(m, 1);
                 ln.D(urow) = 0.0;
                 uint32_t slot;
@@ -826,6 +831,7 @@ struct Engine {
                 break;
             }
             case MT_PARALLEL_GATEWAY: {  // parallel_gateway.rs:160-172, increment_collection :100-116
+                if (BASIC) break;
                 if (port == SIMB_PORT_UNKNOWN) { ln.err = 7; break; }
                 uint32_t cnt = ln.W(md.wrow);
                 uint32_t i = 0;
@@ -844,6 +850,7 @@ struct Engine {
                 break;
             }
             case MT_STOCHASTIC_GATE: {  // stochastic_gate.rs:163-172, receive_job :101-122
+                if (BASIC) break;
                 if (port != 0) { ln.err = 7; break; }
                 ln.D(urow) = 0.0;
                 if (ln.dm_int | ln.dm_ext) flush_draws(ln);  // earlier draws of the stream come first
@@ -856,6 +863,7 @@ struct Engine {
                 break;
             }
             case MT_STOPWATCH: {  // stopwatch.rs:271-282
+                if (BASIC) break;
                 if (port == 2) {  // get_job :211-214
                     ln.set_phase(m, 1);
                     ln.D(urow) = 0.0;
@@ -912,6 +920,7 @@ struct Engine {
                 break;
             }
             case MT_BATCHER: {  // batcher.rs:192-206 (any port)
+                if (BASIC) break;
                 uint32_t q = ln.W(md.wrow);
                 uint32_t len = q & 0xFFFFu;
                 bool room = (uint64_t)len + 1ull < (uint64_t)md.cap;
@@ -1023,12 +1032,14 @@ struct Engine {
                 break;
             }
             case MT_GATE: {  // send_jobs gate.rs:149-165
+                if (BASIC) break;
                 ln.set_phase(m, 0);
                 ln.D(urow) = SIMB_INF;
                 release_n<INSTR>(ln, m, md, ln.W(md.wrow) & 0xFFFFu, 0, 0);
                 break;
             }
             case MT_EXCLUSIVE_GATEWAY: {  // exclusive_gateway.rs:153-161
+                if (BASIC) break;
                 ln.D(urow) = SIMB_INF;
                 if (ln.phase(m) == 1) {  // send_jobs :110-134: one draw per firing
                     ln.set_phase(m, 0);
@@ -1041,6 +1052,7 @@ struct Engine {
                 break;
             }
             case MT_PARALLEL_GATEWAY: {  // parallel_gateway.rs:174-182
+                if (BASIC) break;
                 uint32_t cnt = ln.W(md.wrow);
                 uint32_t i = 0;
                 for (; i < cnt; i++)  // canonical choice: earliest-inserted full collection
@@ -1062,6 +1074,7 @@ struct Engine {
                 break;
             }
             case MT_STOCHASTIC_GATE: {  // stochastic_gate.rs:174-183
+                if (BASIC) break;
                 uint32_t len = ln.W(md.wrow) & 0xFFFFu;
                 if (len == 0) {
                     ln.D(urow) = SIMB_INF;
@@ -1079,6 +1092,7 @@ struct Engine {
                 break;
             }
             case MT_STOPWATCH: {  // stopwatch.rs:284-293
+                if (BASIC) break;
                 ln.D(urow) = SIMB_INF;
                 if (ln.phase(m) == 1) {  // release_minimum / release_maximum :216-250
                     ln.set_phase(m, 0);
@@ -1089,6 +1103,7 @@ struct Engine {
                 break;
             }
             case MT_BATCHER: {  // batcher.rs:208-221
+                if (BASIC) break;
                 uint32_t len = ln.W(md.wrow) & 0xFFFFu;
                 bool le = len <= md.cap, ge2 = (uint64_t)len >= 2ull * (uint64_t)md.cap;
                 if (le && ge2) { ln.err = 5; break; }

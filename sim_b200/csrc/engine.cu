@@ -299,7 +299,7 @@ StepKernel simb_generic_rare_kernel(int rng_kind, bool instrument, bool narrow);
 
 // variant: baked shape -> streaming launch; generic -> narrow tile (see step_kernel.cuh)
 static StepKernel pick_kernel(int rng_kind, bool instrument, int shape, bool stream = false, bool rare = true,
-                              bool narrow = false) {
+                              bool narrow = false, bool basic = false) {
     if (!instrument && rng_kind == 0) {  // baked shapes exist for the production configuration only
         switch (shape) {
             case 0: return stream ? simb_shape_stream_kernel_0() : simb_shape_kernel_0();
@@ -309,6 +309,8 @@ static StepKernel pick_kernel(int rng_kind, bool instrument, int shape, bool str
             default: break;
         }
     }
+    if (basic && !rare && !instrument && rng_kind == 0)
+        return narrow ? simb_step_kernel<0, false, -1, true, false, true> : simb_step_kernel<0, false, -1, false, false, true>;
     if (rare) return simb_generic_rare_kernel(rng_kind, instrument, narrow);
     if (narrow && !instrument && rng_kind == 0) return simb_step_kernel<0, false, -1, true, false>;
     if (instrument) {
@@ -319,6 +321,13 @@ static StepKernel pick_kernel(int rng_kind, bool instrument, int shape, bool str
     if (rng_kind == 0) return simb_step_kernel<0, false, -1, false, false>;
     if (rng_kind == 1) return simb_step_kernel<1, false, -1, false, false>;
     return simb_step_kernel<2, false, -1, false, false>;
+}
+static bool only_basic_models(const SimbNetDesc& net) {
+    for (uint32_t m = 0; m < net.n_models; m++) {
+        const uint32_t t = net.models[m].type;
+        if (t != MT_GENERATOR && t != MT_PROCESSOR && t != MT_STORAGE && t != MT_LOAD_BALANCER && t != MT_PASSIVE) return false;
+    }
+    return getenv("SIMB_NO_BASIC") == nullptr || !*getenv("SIMB_NO_BASIC");
 }
 static bool uses_rare_variables(const SimbNetDesc& net) {
     for (uint32_t m = 0; m < net.n_models; m++) {
@@ -359,6 +368,7 @@ const char* engine_shape_name(int shape) { return (shape >= 0 && shape < SIMB_N_
 int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool instrument, EngineDims* dims) {
     dims->shape = engine_match_shape(net, rng_kind, instrument);
     dims->rare = uses_rare_variables(net);
+    dims->basic = only_basic_models(net);
     // Tile width = replications per CTA.  Pick the width that keeps the most warps resident per SM
     // (shared memory 227 KB, 64 registers per thread -> at most 32 warps, at most 32 CTAs); among equals
     // prefer the wider tile (fewer, larger bulk copies), and keep half of the SM's unified storage for L1
@@ -399,7 +409,7 @@ int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool inst
         if (*pad) dims->smem_bytes += (uint32_t)atoi(pad);
         if (dims->smem_bytes > 227u * 1024u) dims->smem_bytes = 227u * 1024u;
     }
-    cudaError_t e = cudaFuncSetAttribute((const void*)pick_kernel(rng_kind, instrument, dims->shape, false, dims->rare, dims->tile <= 128u),
+    cudaError_t e = cudaFuncSetAttribute((const void*)pick_kernel(rng_kind, instrument, dims->shape, false, dims->rare, dims->tile <= 128u, dims->basic),
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dims->smem_bytes);
     if (e != cudaSuccess) return (int)e;
     if (dims->shape >= 0) {
@@ -434,7 +444,7 @@ int engine_launch_step(const SimbNetDesc& net, const SimbDevState& st, const Sim
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const uint32_t ca = count_active ? 1u : 0u;
-    return (int)cudaLaunchKernelEx(&cfg, pick_kernel(rng_kind, instrument, dims.shape, streaming, dims.rare, dims.tile <= 128u), net, st,
+    return (int)cudaLaunchKernelEx(&cfg, pick_kernel(rng_kind, instrument, dims.shape, streaming, dims.rare, dims.tile <= 128u, dims.basic), net, st,
                                    la, ca);
 }
 

@@ -13,6 +13,7 @@ struct EngineDims {
     uint32_t grid;        // reserved (the launch uses one CTA per tile)
     int shape;            // baked shape id whose specialised kernel is used, or -1 (generic interpreter)
     bool rare;            // the network draws from Beta / Gamma / LogNormal / Weibull (generic kernel variant)
+    bool basic;           // only Generator / Processor / Storage / LoadBalancer / Passive models (generic kernel variant)
 };
 int engine_match_shape(const SimbNetDesc& net, int rng_kind, bool instrument);
 const char* engine_shape_name(int shape);

@@ -147,7 +147,7 @@ __host__ __device__ constexpr int shape_tier() {  // model-count tier of a baked
 // tile (<= 128 replications per CTA: networks whose state column is large), compiled for up to 96 registers: the
 // CTA count of such networks is bounded by shared memory, so the wider register budget is free and removes the
 // spills / rematerialisation of the 64-register build (+10-13 % on the 16- and 32-model networks).
-template <int RNG, bool INSTR, int SHAPE, bool VARIANT = false, bool RARE = true>
+template <int RNG, bool INSTR, int SHAPE, bool VARIANT = false, bool RARE = true, bool BASIC = false>
 __global__ void __launch_bounds__((SHAPE < 0 && VARIANT) ? 128 : 256,
                                   SHAPE >= 0 ? (VARIANT ? SIMB_SHAPE_STREAM_MIN_BLOCKS : SIMB_SHAPE_MIN_BLOCKS)
                                              : (VARIANT ? 5 : SIMB_MIN_BLOCKS))
@@ -212,7 +212,7 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
     tab.norm_f = ZIG_NORM_F;
     tab.rng_cache = reinterpret_cast<uint64_t*>(smem + sp.off_rng);
     tab.rng_slots = rng_slots;
-    Engine<RNG, shape_tier<SHAPE>(), RARE> eng(net, net_param, st, tab);
+    Engine<RNG, shape_tier<SHAPE>(), RARE, BASIC> eng(net, net_param, st, tab);
     while (!mbar_try_wait(bar, 0)) {
     }
 
