@@ -550,3 +550,32 @@ def test_device_steady_state_output_matches_host_and_oracle():
     none = _sim(models, conns, 64, seed=29, instrument=False, stat_model_id="processor-3")
     with pytest.raises(SimulationError):
         none.steady_state(0.05)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_streaming_passes_at_full_width(k):
+    """One / two steps per launch over 2^20 replications: every pass is two concurrent half-batch grids, consecutive
+    passes sweep in opposite directions, the state tile copies carry L2 hints and (k <= 2) the 6-CTA instantiation
+    with a one-block Philox cache runs.  None of that may change a single replication."""
+    n, nsteps = 1 << 20, 51
+    models, conns = networks.mm1()
+    sim = _sim(models, conns, n, seed=77, instrument=False, stat_model_id="processor-01", steps_per_launch=k)
+    assert sim.describe()["kernel_shape"] == "mm1" and sim.describe()["grids_per_pass"] == 2
+    sim.step_n(nsteps)
+    steps, events, t = sim.get_steps(), sim.get_events(), sim.get_global_time()
+    s, cnt = sim.get_wait_stats()
+    assert (steps == nsteps).all() and (sim.get_errors() == 0).all()
+    rec = networks.mm1(store_records=True)[0]
+    o = oracle_api.OracleSimulation(rec, conns)
+    for r0 in (0, 254, 256, 524286, 524288, 786432, n - 2):  # tile and half-batch boundaries
+        ref = o.run_batch(77, r0, 2, threads=2, nsteps=nsteps, stat_model_id="processor-01", trace_hash=False)
+        sl = slice(r0, r0 + 2)
+        assert (events[sl] == ref["events"]).all() and _close(t[sl], ref["time"])
+        assert (cnt[sl] == ref["wait_n"]).all() and _close(s[sl], ref["wait_sum"])
+    # the same batch stepped with fused launches ends in the same state
+    fused = _sim(models, conns, n, seed=77, instrument=False, stat_model_id="processor-01")
+    fused.step_n(nsteps)
+    assert np.array_equal(fused.get_global_time(), t) and np.array_equal(fused.get_events(), events)
+    assert np.array_equal(fused.get_draws(), sim.get_draws())
+    for m in models:
+        assert np.array_equal(fused.get_until_next_event(m.id), sim.get_until_next_event(m.id), equal_nan=True)
