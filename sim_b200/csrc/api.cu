@@ -579,7 +579,11 @@ int simb_inject_input(simb_sim* s, const char* target_id, const char* target_por
     uint8_t* d_mask = nullptr;
     if (replica_mask) {
         CUDA_TRY(cudaMalloc((void**)&d_mask, s->st.n));
-        CUDA_TRY(cudaMemcpy(d_mask, replica_mask, s->st.n, cudaMemcpyHostToDevice));
+        const cudaError_t me = cudaMemcpy(d_mask, replica_mask, s->st.n, cudaMemcpyHostToDevice);
+        if (me != cudaSuccess) {
+            cudaFree(d_mask);
+            return fail(SIMB_ERR_CUDA, std::string("mask upload: ") + cudaGetErrorString(me));
+        }
     }
     cudaMemsetAsync(s->d_overflow, 0, sizeof(unsigned long long), s->stream);
     int e = engine_launch_inject(s->hn.desc, s->st, code, rw, d_mask, s->d_overflow, s->stream);
