@@ -81,7 +81,9 @@ struct Tables {
     uint64_t* rng_cache;  // baked shapes: Philox draw cache, [rng_slots][lane] (shared memory on the device)
     uint32_t rng_slots;   // prefetched draws per replication there (power of two >= 2)
 };
+#ifndef SIMB_RNG_CACHE
 #define SIMB_RNG_CACHE 8u /* rng_slots of fused launches (streaming launches keep one block: 2) */
+#endif
 
 // ---- per-lane view of the replication's state tile ----------------------------------------------
 // d/w point at row 0 of this lane's column; consecutive rows are `stride` elements apart
