@@ -51,6 +51,29 @@ def test_step_until_activities():
     assert ci["lower"] < 50.0 < ci["upper"]
 
 
+def _arrival_counts_oracle(reps=10, until=480.0):
+    models, conns = networks.mm1(lam_gen=0.0957, lam_proc=0.1659)
+    sim = O.OracleSimulation(models, conns)
+    counts = []
+    for _ in range(reps):
+        sim.reset()
+        sim.put()
+        e, msgs = sim.step_until(until)
+        assert e == 0
+        counts.append(float(sum(1 for m in msgs if m["target_id"] == "processor-01")))
+    return counts
+
+
+def test_non_stationary_generation():
+    # simulations.rs:181-255 (no thinning despite the name): arrivals in 480 time units over 10 replications on
+    # one shared stream; the CI must overlap the empirical one the reference hard-codes
+    counts = _arrival_counts_oracle()
+    e, ci = O.independent_sample(counts, 0.05)
+    e2, emp = O.independent_sample([47.0, 42.0, 45.0, 34.0, 37.0], 0.05)
+    assert e == 0 and e2 == 0
+    assert ci["lower"] < emp["upper"] and ci["upper"] > emp["lower"]
+
+
 def test_exclusive_gateway_601_steps_200_jobs():
     # simulations.rs:258-379
     sim = O.OracleSimulation(*networks.exclusive_gateway())

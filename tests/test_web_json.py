@@ -209,3 +209,26 @@ def test_yaml_forms_round_trip():
     assert json.loads(a.get_records_json("processor-01")) == []
     a.inject_input_yaml("sourceId: manual\nsourcePort: manual\ntargetId: storage-01\ntargetPort: store\ntime: 0.0\ncontent: x\n")
     assert yaml.safe_load(a.get_messages_yaml())[-1]["content"] == "x"
+
+
+@pytest.mark.gpu
+def test_non_stationary_generation_replication_loop():
+    """non_stationary_generation (simulations.rs:181-255) on the device with the reference's default stream
+    (Pcg64Mcg::new(42)): reset + put per replication, the stream carries on; the arrivals counted from the returned
+    messages of step_until(480) equal the oracle's replication by replication, and the CI overlaps the reference's."""
+    from test_oracle_structural import _arrival_counts_oracle
+    from sim_b200 import output_analysis as oa
+    from sim_b200.simulator import RNG_PCG64MCG, connectors_to_json, models_to_json
+    models, conns = networks.mm1(lam_gen=0.0957, lam_proc=0.1659)
+    mj, cj = models_to_json(models), connectors_to_json(conns)
+    web = _web(models, conns, n=1, replication=0, seed=42, rng_kind=RNG_PCG64MCG)
+    counts = []
+    for _ in range(10):
+        web.reset()
+        web.put_json(mj, cj)
+        msgs = json.loads(web.step_until_json(480.0))
+        counts.append(float(sum(1 for m in msgs if m["targetId"] == "processor-01")))
+    assert counts == _arrival_counts_oracle()
+    ci = oa.IndependentSample.post(counts).confidence_interval_mean(0.05)
+    emp = oa.IndependentSample.post([47.0, 42.0, 45.0, 34.0, 37.0]).confidence_interval_mean(0.05)
+    assert ci.lower() < emp.upper() and ci.upper() > emp.lower()
