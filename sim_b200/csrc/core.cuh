@@ -1204,10 +1204,27 @@ struct Engine {
             }
         } else {
             if (go && !had) {
+                // The full interpreter keeps these loops rolled: it is bound by instruction fetch, so code size costs
+                // more than loop overhead (32-model network +6 %); the small BASIC build gains from unrolling.
                 dt = SIMB_INF;
-                for (uint32_t m = 0; m < M; m++) dt = fmin(dt, ln.D(net.drow_until + m));
+                if (BASIC) {
+                    for (uint32_t m = 0; m < M; m++) dt = fmin(dt, ln.D(net.drow_until + m));
+                } else {
+#pragma unroll 1
+                    for (uint32_t m = 0; m < M; m++) dt = fmin(dt, ln.D(net.drow_until + m));
+                }
             }
-            if (go) {
+            if (go && BASIC) {
+                for (uint32_t m = 0; m < M; m++) {
+                    double u = ln.D(net.drow_until + m);
+                    if (!had && net.models[m].type != MT_PASSIVE) {
+                        u = u - dt;
+                        ln.D(net.drow_until + m) = u;
+                    }
+                    if (u == 0.0) zmask |= 1u << m;
+                }
+            } else if (go) {
+#pragma unroll 1
                 for (uint32_t m = 0; m < M; m++) {
                     double u = ln.D(net.drow_until + m);
                     if (!had && net.models[m].type != MT_PASSIVE) {
