@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/simb.h"
+#include "actions.h"
 #include "engine.cuh"
 #include "json.hpp"
 #include "json_write.hpp"
@@ -116,6 +117,8 @@ void free_device(simb_sim* s) {
     F(s->st.record_count);
     F(s->st.totals);
     F(s->st.series);
+    F((void*)s->st.tab);
+    F((void*)s->st.vtab);
     F(s->d_dinit);
     F(s->d_winit);
     F(s->d_pre_slots);
@@ -139,6 +142,26 @@ int dev_alloc(cudaStream_t stream, T** p, size_t count, bool zero) {
     size_t bytes = (count ? count : 1) * sizeof(T);
     CUDA_TRY(cudaMallocAsync((void**)p, bytes, stream));
     if (zero) CUDA_TRY(cudaMemsetAsync(*p, 0, bytes, stream));
+    return 0;
+}
+
+// model / route / value tables of the generic interpreter (actions.h) for s->hn
+int upload_tables(simb_sim* s) {
+    std::vector<uint32_t> tab(SIMB_TAB_WORDS);
+    std::vector<uint64_t> vtab(SIMB_VTAB_WORDS);
+    build_model_table(s->hn.desc, tab.data(), vtab.data());
+    int r;
+    if (!s->st.tab) {
+        uint32_t* d_tab = nullptr;
+        uint64_t* d_vtab = nullptr;
+        if ((r = dev_alloc(s->stream, &d_tab, tab.size(), false))) return r;
+        if ((r = dev_alloc(s->stream, &d_vtab, vtab.size(), false))) return r;
+        s->st.tab = d_tab;
+        s->st.vtab = d_vtab;
+    }
+    CUDA_TRY(cudaMemcpyAsync((void*)s->st.tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync((void*)s->st.vtab, vtab.data(), vtab.size() * 8, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));  // the staging vectors go out of scope
     return 0;
 }
 
@@ -177,6 +200,7 @@ int build_device(simb_sim* s, uint32_t keep_mask, const simb_sim* old) {
         if ((r = dev_alloc(s->stream, &st.series, (size_t)st.series_cap * stride, false))) return r;
     }
     if ((r = dev_alloc(s->stream, &st.totals, 4, true))) return r;
+    if ((r = upload_tables(s))) return r;
     if ((r = dev_alloc(s->stream, &s->d_dinit, net.n_drows, false))) return r;
     if ((r = dev_alloc(s->stream, &s->d_winit, net.n_wrows, false))) return r;
     CUDA_TRY(cudaMemcpy(s->d_dinit, s->hn.d_init.data(), net.n_drows * sizeof(double), cudaMemcpyHostToDevice));
@@ -486,6 +510,7 @@ int simb_put_json(simb_sim* s, const char* models_json, const char* connectors_j
         return 0;
     }
     s->hn = hn;
+    if ((e = upload_tables(s))) return e;
     CUDA_TRY(cudaMemcpy(s->d_dinit, s->hn.d_init.data(), nw.n_drows * sizeof(double), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(s->d_winit, s->hn.w_init.data(), nw.n_wrows * sizeof(uint32_t), cudaMemcpyHostToDevice));
     if (s->n_pre) {

@@ -12,6 +12,7 @@
 // exactly (mod.rs:239).
 #pragma once
 #include "net.h"
+#include "actions.h"
 
 #include <math.h>
 #include <stdint.h>
@@ -27,6 +28,12 @@
 #define SIMB_ON_DEVICE 1
 #else
 #define SIMB_ON_DEVICE 0
+#endif
+
+#if SIMB_ON_DEVICE
+#define SIMB_LDG(p) __ldg(p)
+#else
+#define SIMB_LDG(p) (*(p))
 #endif
 
 namespace simb {
@@ -109,6 +116,9 @@ struct Lane {
     uint32_t dm_int, dm_ext;  // deferred continuous draws: "until_next_event[m] = sample(dist[m])" still
                               // owed from the previous internal phase / this external phase
     uint32_t traced;
+    // generic interpreter: models whose until_next_event is not +INF / is exactly 0.0 (kept in step with every
+    // write of an until_next_event row, so the time advance and the imminent-model scan visit those only)
+    uint32_t amask, zm;
 
     SIMB_HD double& D(uint32_t row) { return d[(size_t)row * stride]; }
     SIMB_HD uint32_t& W(uint32_t row) { return w[(size_t)row * stride]; }
@@ -169,6 +179,31 @@ static inline U64Pair philox_pair_cold(uint32_t key0, uint32_t key1, uint32_t ct
         else if (SM <= 16) { SIMB_REP16(X) }            \
         else { SIMB_REP32(X) }                          \
     } while (0)
+
+// Distribution parameters of one model, from the launch's descriptor (baked shapes: the model index is a literal,
+// so the reads fold into constant-bank operands) ...
+struct DescP {
+    const SimbModelDesc& d;
+    SIMB_HD double p0() const { return d.p0; }
+    SIMB_HD double p1() const { return d.p1; }
+    SIMB_HD double p2() const { return d.p2; }
+    SIMB_HD uint64_t q0() const { return d.q0; }
+    SIMB_HD uint64_t q1() const { return d.q1; }
+    SIMB_HD uint64_t q2() const { return d.q2; }
+    SIMB_HD uint32_t dist_err() const { return d.dist_err; }
+};
+// ... or from the value table (generic interpreter: lane-varying model index, read through the L1)
+struct TabP {
+    const uint64_t* vt;
+    uint32_t m, derr;
+    SIMB_HD double p0() const { return bits_f64(SIMB_LDG(vt + m)); }
+    SIMB_HD double p1() const { return bits_f64(SIMB_LDG(vt + SIMB_MAX_MODELS + m)); }
+    SIMB_HD double p2() const { return bits_f64(SIMB_LDG(vt + 2 * SIMB_MAX_MODELS + m)); }
+    SIMB_HD uint64_t q0() const { return SIMB_LDG(vt + 3 * SIMB_MAX_MODELS + m); }
+    SIMB_HD uint64_t q1() const { return SIMB_LDG(vt + 4 * SIMB_MAX_MODELS + m); }
+    SIMB_HD uint64_t q2() const { return SIMB_LDG(vt + 5 * SIMB_MAX_MODELS + m); }
+    SIMB_HD uint32_t dist_err() const { return derr; }
+};
 
 // RNG: 0 Philox, 1 Pcg64Mcg, 2 external stream.
 // SM > 0: `net` refers to a compile-time-constant descriptor (a baked network shape, shapes.inc) of at
@@ -341,12 +376,13 @@ struct Engine {
             if (ln.err) return x;
         }
     }
-    SIMB_HD double sample_continuous_rare(Lane& ln, uint32_t dist_kind, const SimbModelDesc& pd) {
+    template <class P>
+    SIMB_HD double sample_continuous_rare(Lane& ln, uint32_t dist_kind, const P& pd) {
         switch (dist_kind) {
             case DK_GAMMA: {  // rand_distr 0.4 Gamma (Marsaglia-Tsang); shape == 1 is lowered to DK_EXP
-                const double d = pd.p0, cc = pd.p1, scale = pd.p2;
+                const double d = pd.p0(), cc = pd.p1(), scale = pd.p2();
                 double u_small = 0.0;
-                if (pd.q0) u_small = open01(ln);  // GammaSmallShape draws its Open01 first
+                if (pd.q0()) u_small = open01(ln);  // GammaSmallShape draws its Open01 first
                 double g = 0.0;
                 for (;;) {
                     const double x = sample_standard_normal(ln);
@@ -364,22 +400,22 @@ struct Engine {
                     }
                     if (ln.err) break;
                 }
-                return pd.q0 ? g * pow(u_small, bits_f64(pd.q1)) : g;
+                return pd.q0() ? g * pow(u_small, bits_f64(pd.q1())) : g;
             }
             case DK_LOGNORMAL: {
                 const double n = sample_standard_normal(ln);
-                return exp(pd.p0 + pd.p1 * n);
+                return exp(pd.p0() + pd.p1() * n);
             }
             case DK_WEIBULL: {  // OpenClosed01, then scale * (-ln x)^(1/shape)
                 const double x = (double)((next_u64(ln) >> 11) + 1ull) * (1.0 / 9007199254740992.0);
-                return pd.p0 * pow(-log(x), pd.p1);
+                return pd.p0() * pow(-log(x), pd.p1());
             }
             case DK_BETA: {  // rand_distr 0.4.3 Beta (Cheng BB / BC); p0 = a, p1 = b, q0 = flags
-                const double aa = pd.p0, bb = pd.p1;
+                const double aa = pd.p0(), bb = pd.p1();
                 const double LN4 = 1.3862943611198906, LN5 = 1.6094379124341003;  // ln 4, ln 5
                 const double alpha = aa + bb;
                 double w = 0.0;
-                if (!(pd.q0 & 1u)) {  // BB
+                if (!(pd.q0() & 1u)) {  // BB
                     const double beta = sqrt((alpha - 2.0) / (2.0 * aa * bb - alpha));
                     const double gamma = aa + 1.0 / beta;
                     for (;;) {
@@ -424,7 +460,7 @@ struct Engine {
                         if (!(alpha * (log(alpha / (bb + w)) + v) - LN4 < log(z))) break;
                     }
                 }
-                if (!(pd.q0 & 2u)) return (w == SIMB_INF) ? 1.0 : w / (bb + w);
+                if (!(pd.q0() & 2u)) return (w == SIMB_INF) ? 1.0 : w / (bb + w);
                 return bb / (bb + w);
             }
             default:
@@ -433,22 +469,23 @@ struct Engine {
     }
     // Continuous::random_variate (random_variable.rs:69-89); parameter errors surface per draw
     SIMB_HD double sample_continuous(Lane& ln, const SimbModelDesc& md, const SimbModelDesc& pd) {
-        return sample_continuous_kind(ln, md.dist_kind, pd);
+        return sample_continuous_kind(ln, md.dist_kind, DescP{pd});
     }
-    SIMB_HD double sample_continuous_kind(Lane& ln, uint32_t dist_kind, const SimbModelDesc& pd) {
-        if (pd.dist_err) {
-            if (!ln.err) ln.err = pd.dist_err;
+    template <class P>
+    SIMB_HD double sample_continuous_kind(Lane& ln, uint32_t dist_kind, const P& pd) {
+        if (pd.dist_err()) {
+            if (!ln.err) ln.err = pd.dist_err();
             return 0.0;
         }
         switch (dist_kind) {
             case DK_EXP:
-                return sample_exp1(ln) * pd.p0;  // Exp1 * lambda_inverse
+                return sample_exp1(ln) * pd.p0();  // Exp1 * lambda_inverse
             case DK_NORMAL: {
                 double n = sample_standard_normal(ln);
-                return pd.p0 + pd.p1 * n;
+                return pd.p0() + pd.p1() * n;
             }
             case DK_TRIANGULAR: {
-                double mn = pd.p0, mx = pd.p1, mode = pd.p2;
+                double mn = pd.p0(), mx = pd.p1(), mode = pd.p2();
                 double f = standard_f64(ln);
                 double diff_mode_min = mode - mn;
                 double range = mx - mn;
@@ -459,7 +496,7 @@ struct Engine {
             case DK_UNIFORM: {  // p0 = low, p1 = scale
                 double value1_2 = bits_f64((next_u64(ln) >> 12) | 0x3FF0000000000000ull);
                 double value0_1 = value1_2 - 1.0;
-                return value0_1 * pd.p1 + pd.p0;
+                return value0_1 * pd.p1() + pd.p0();
             }
             default:
                 return RARE ? sample_continuous_rare(ln, dist_kind, pd) : 0.0;
@@ -476,24 +513,32 @@ struct Engine {
     }
     // Index::random_variate (random_variable.rs:122-130)
     SIMB_HD uint32_t sample_index(Lane& ln, const SimbModelDesc& md, const SimbModelDesc& pd) {
-        if (pd.dist_err) {
-            if (!ln.err) ln.err = pd.dist_err;
+        return sample_index_p(ln, md.flags, md.n_w, md.wtab, DescP{pd});
+    }
+    template <class P>
+    SIMB_HD uint32_t sample_index_p(Lane& ln, uint32_t flags, uint32_t n_w, uint32_t wtab, const P& pd) {
+        if (pd.dist_err()) {
+            if (!ln.err) ln.err = pd.dist_err();
             return 0;
         }
-        uint64_t c = sample_uniform_int(ln, pd.q0, pd.q1, pd.q2);
-        if (!(md.flags & MF_INDEX_WEIGHTED)) return (uint32_t)(c > 0xFFFFFFFFull ? 0xFFFFFFFFull : c);
+        uint64_t c = sample_uniform_int(ln, pd.q0(), pd.q1(), pd.q2());
+        if (!(flags & MF_INDEX_WEIGHTED)) return (uint32_t)(c > 0xFFFFFFFFull ? 0xFFFFFFFFull : c);
         uint32_t idx = 0;  // first cumulative weight strictly greater than the chosen weight
-        while (idx < md.n_w && par.wcum[md.wtab + idx] <= c) idx++;
+        while (idx < n_w && par.wcum[wtab + idx] <= c) idx++;
         return idx;
     }
     // Boolean::random_variate (random_variable.rs:96-101)
     SIMB_HD bool sample_bernoulli(Lane& ln, const SimbModelDesc& md, const SimbModelDesc& pd) {
-        if (pd.dist_err) {
-            if (!ln.err) ln.err = pd.dist_err;
+        return sample_bernoulli_p(ln, md.flags, DescP{pd});
+    }
+    template <class P>
+    SIMB_HD bool sample_bernoulli_p(Lane& ln, uint32_t flags, const P& pd) {
+        if (pd.dist_err()) {
+            if (!ln.err) ln.err = pd.dist_err();
             return false;
         }
-        if (md.flags & MF_BERNOULLI_ALWAYS) return true;  // p == 1.0 consumes no draw
-        return next_u64(ln) < pd.q0;
+        if (flags & MF_BERNOULLI_ALWAYS) return true;  // p == 1.0 consumes no draw
+        return next_u64(ln) < pd.q0();
     }
 
     // ---- deferred continuous draws ------------------------------------------------------------------
@@ -537,7 +582,7 @@ struct Engine {
                         m = (uint32_t)lowest_bit(ln.dm_ext);
                         ln.dm_ext &= ln.dm_ext - 1u;
                     }
-                    ln.D(net.drow_until + m) = sample_continuous_kind(ln, kind, par.models[m]);
+                    ln.D(net.drow_until + m) = sample_continuous_kind(ln, kind, DescP{par.models[m]});
                 }
                 return;
             }
@@ -567,8 +612,10 @@ struct Engine {
                 m = (uint32_t)lowest_bit(ln.dm_ext);
                 ln.dm_ext &= ln.dm_ext - 1u;
             }
-            const double dv = sample_continuous(ln, net.models[m], par.models[m]);
+            // parameter errors were raised when the debt was noted (apply_u), so dist_err is 0 here
+            const double dv = sample_continuous_kind(ln, (TF(TF_WTAB, m) >> 16) & 0xFFu, TabP{st.vtab, m, 0u});
             ln.D(net.drow_until + m) = dv;
+            if (dv == 0.0) ln.zm |= 1u << m;  // a variate of exactly zero makes the model imminent at once
         }
     }
 
@@ -718,9 +765,20 @@ struct Engine {
         ln.dm_int = ln.W(net.wrow_dmask);
         ln.dm_ext = 0;
         ln.tmask = 0;
-        for (uint32_t j = 0; j < ln.npend; j++) {
-            const uint32_t t = ROUTE_TGT(mail_word(ln, j, 1));
-            if (t < SIMB_MAX_MODELS) ln.tmask |= 1u << t;
+        ln.amask = ln.zm = 0;
+        if (STATIC) {
+            for (uint32_t j = 0; j < ln.npend; j++) {
+                const uint32_t t = ROUTE_TGT(mail_word(ln, j, 1));
+                if (t < SIMB_MAX_MODELS) ln.tmask |= 1u << t;
+            }
+        } else {
+            for (uint32_t m = 0; m < net.n_models; m++) {
+                const double u = ln.D(net.drow_until + m);
+                if (u != SIMB_INF) ln.amask |= 1u << m;
+                if (u == 0.0) ln.zm |= 1u << m;
+            }
+            ln.amask |= ln.dm_int;  // a model that owes a draw: its until_next_event row is stale
+            ln.zm &= ~ln.dm_int;
         }
         return ctl;
     }
@@ -1130,6 +1188,463 @@ struct Engine {
     }
 
     // ================================================================================================
+    // Generic interpreter: table-driven handlers (actions.h).  The lane's model index is data, the code
+    // path is the same for every model type, so the lanes of a warp stay converged whatever models
+    // their replications are serving.
+    // ================================================================================================
+    SIMB_HD uint32_t TF(uint32_t field, uint32_t m) const { return SIMB_LDG(st.tab + field * SIMB_MAX_MODELS + m); }
+    SIMB_HD uint32_t ext_lut(uint32_t key) const {
+#if SIMB_ON_DEVICE
+        return __ldg(&kExtLutDev.v[key]);
+#else
+        return kExtLutHost.v[key];
+#endif
+    }
+    SIMB_HD uint32_t int_lut(uint32_t key) const {
+#if SIMB_ON_DEVICE
+        return __ldg(&kIntLutDev.v[key]);
+#else
+        return kIntLutHost.v[key];
+#endif
+    }
+    // until_next_event[m] := 0 / +INF / p0 / "a fresh variate" (deferred, see flush_draws), keeping the
+    // active and imminent masks exact.  false: a distribution parameter error froze the replication.
+    template <bool EXT>
+    SIMB_HD bool apply_u(Lane& ln, uint32_t m, uint32_t ua) {
+        const uint32_t bit = 1u << m;
+        if (ua == UA_DRAW) {
+            const uint32_t de = TF(TF_WTAB, m) >> 24;
+            if (de) {  // parameter errors surface at draw time (random_variable.rs:72-87)
+                if (!ln.err) ln.err = de;
+                return false;
+            }
+            if (EXT) ln.dm_ext |= bit;
+            else ln.dm_int |= bit;
+            ln.amask |= bit;
+            ln.zm &= ~bit;
+            return true;
+        }
+        double v = 0.0;
+        if (ua == UA_INF) v = SIMB_INF;
+        if (ua == UA_P0) v = bits_f64(SIMB_LDG(st.vtab + m));
+        ln.D(net.drow_until + m) = v;
+        if (ua == UA_INF) ln.amask &= ~bit;
+        else ln.amask |= bit;
+        if (v == 0.0) ln.zm |= bit;
+        else ln.zm &= ~bit;
+        return true;
+    }
+
+    // the three models whose events_ext works on a table / draws at arrival
+    template <bool INSTR>
+    SIMB_HD void ext_special(Lane& ln, uint32_t m, uint32_t sp, uint32_t port, uint32_t content, uint32_t tf,
+                             uint32_t rows) {
+        const uint32_t wrow = rows & 0xFFFFu, flags = tf >> 24;
+        const uint32_t rcap = TF(TF_RING_CAP, m), w0 = TF(TF_RING_W0, m), w1 = TF(TF_RING_W1, m);
+        if (sp == XS_SGATE) {  // receive_job stochastic_gate.rs:101-122: Bernoulli draw AT ARRIVAL
+            apply_u<true>(ln, m, UA_ZERO);
+            if (ln.dm_int | ln.dm_ext) flush_draws(ln);  // earlier draws of the stream come first
+            const bool pass = sample_bernoulli_p(ln, flags, TabP{st.vtab, m, TF(TF_WTAB, m) >> 24});
+            if (ln.err) return;
+            const uint32_t q = ln.W(wrow);
+            const uint32_t head = q >> 16, len = q & 0xFFFFu;
+            if (len >= rcap) {
+                ln.err = 32;
+                return;
+            }
+            uint32_t s = head + len;
+            if (s >= rcap) s -= rcap;
+            RW(ln, w0 + s) = content;
+            RW(ln, w1 + s) = pass ? 1u : 0u;
+            ln.W(wrow) = q + 1u;
+            record<INSTR>(ln, m, ACT_ARRIVAL, content);
+            return;
+        }
+        if (sp == XS_PG) {  // parallel_gateway.rs:160-172, increment_collection :100-116
+            if (port == SIMB_PORT_UNKNOWN) {
+                ln.err = 7;
+                return;
+            }
+            const uint32_t cnt = ln.W(wrow);
+            uint32_t i = 0;
+            for (; i < cnt; i++)
+                if (RW(ln, w0 + i) == content) break;
+            if (i < cnt) {
+                RW(ln, w1 + i) += 1u;
+            } else {
+                if (cnt >= rcap) {
+                    ln.err = 32;
+                    return;
+                }
+                RW(ln, w0 + cnt) = content;
+                RW(ln, w1 + cnt) = 1u;
+                ln.W(wrow) = cnt + 1u;
+            }
+            record<INSTR>(ln, m, ACT_ARRIVAL, content, port + 1u);
+            apply_u<true>(ln, m, UA_ZERO);
+            return;
+        }
+        // Stopwatch start / stop (stopwatch.rs:271-282): matching_or_new_job :137-155 on a bounded table of
+        // INCOMPLETE jobs: word0 = entries, word1 = best content, word2 = next insertion seq, word3 = best seq;
+        // entry: c0 = name, c1 = seq<<2 | has_stop<<1 | has_start, d = the time present.
+        const uint32_t rd = TF(TF_RING_D, m), drow = rows >> 16;
+        record<INSTR>(ln, m, port == 0 ? ACT_START : ACT_STOP, content);
+        const uint32_t cnt = ln.W(wrow);
+        uint32_t i = 0;
+        for (; i < cnt; i++)
+            if (RW(ln, w0 + i) == content) break;
+        const uint32_t mine = port == 0 ? 1u : 2u, other = port == 0 ? 2u : 1u;
+        if (i == cnt) {
+            if (cnt >= rcap) {
+                ln.err = 32;
+                return;
+            }
+            const uint32_t seq = ln.W(wrow + 2);
+            ln.W(wrow + 2) = seq + 1u;
+            RW(ln, w0 + cnt) = content;
+            RW(ln, w1 + cnt) = (seq << 2) | mine;
+            RD(ln, rd + cnt) = ln.time;
+            ln.W(wrow) = cnt + 1u;
+            return;
+        }
+        const uint32_t fl = RW(ln, w1 + i);
+        if (!(fl & other)) {  // same side again: overwrite the time
+            RD(ln, rd + i) = ln.time;
+            return;
+        }
+        // both sides now known: duration = stop - start (some_duration :95-100)
+        const double t_other = RD(ln, rd + i);
+        const double dur = port == 0 ? t_other - ln.time : ln.time - t_other;
+        const uint32_t seq = fl >> 2;
+        const uint32_t best_c = ln.W(wrow + 1), best_seq = ln.W(wrow + 3);
+        const double best_d = ln.D(drow);
+        bool better;
+        if (best_c == SIMB_CONTENT_NONE) better = (flags & MF_METRIC_MAX) ? dur > -SIMB_INF : dur < SIMB_INF;
+        else if (flags & MF_METRIC_MAX) better = dur > best_d || (dur == best_d && seq < best_seq);
+        else better = dur < best_d || (dur == best_d && seq < best_seq);
+        if (better) {
+            ln.W(wrow + 1) = content;
+            ln.W(wrow + 3) = seq;
+            ln.D(drow) = dur;
+        }
+        const uint32_t last = cnt - 1u;  // drop the completed entry (swap with last; lookup is by name, order by seq)
+        if (i != last) {
+            RW(ln, w0 + i) = RW(ln, w0 + last);
+            RW(ln, w1 + i) = RW(ln, w1 + last);
+            RD(ln, rd + i) = RD(ln, rd + last);
+        }
+        ln.W(wrow) = last;
+    }
+
+    // events_ext of model m (any type) for one message
+    template <bool INSTR>
+    SIMB_HD void ext2(Lane& ln, uint32_t m, uint32_t port, uint32_t content) {
+        const uint32_t tf = TF(TF_TYPE, m);
+        const uint32_t type = tf & 0xFFu, flags = tf >> 24;
+        const uint32_t rows = TF(TF_ROWS, m);
+        const uint32_t wrow = rows & 0xFFFFu;
+        const uint32_t q = ln.W(wrow);
+        const uint32_t len = q & 0xFFFFu, head = q >> 16;
+        const uint32_t cap = TF(TF_CAP, m);
+        const uint32_t qs = (len == 0u ? XK_EMPTY : 0u) | (len == cap ? XK_FULL : 0u) |
+                            ((uint64_t)len + 1ull >= (uint64_t)cap ? XK_NOROOM : 0u);
+        const uint32_t a = ext_lut(EXT_KEY(type, port < 3u ? port : 3u, ln.phase(m), qs));
+        if (a & 3u) {
+            ln.err = (a & 3u) == 1u ? 7u : 5u;  // InvalidMessage / InvalidModelState
+            return;
+        }
+        if (!BASIC && ((a >> XA_SPECIAL_SHIFT) & 3u)) {
+            ext_special<INSTR>(ln, m, (a >> XA_SPECIAL_SHIFT) & 3u, port, content, tf, rows);
+            return;
+        }
+        if (a & XA_PUSH) {
+            const uint32_t rcap = TF(TF_RING_CAP, m);
+            if (len >= rcap) {
+                ln.err = 32;  // SIMB_ERR_CAPACITY: the reference's Vec is unbounded here
+                return;
+            }
+            uint32_t s = head + len;
+            if (s >= rcap) s -= rcap;
+            RW(ln, TF(TF_RING_W0, m) + s) = content;
+            ln.W(wrow) = q + 1u;
+            if (flags & MF_STAT) RD(ln, TF(TF_RING_D, m) + s) = ln.time;
+        }
+        if (a & XA_STORE) ln.W(wrow) = content;
+        if (a & XA_SETPH) ln.set_phase(m, (a >> XA_PH_SHIFT) & 3u);
+        const uint32_t ua = (a >> XA_U_SHIFT) & 7u;
+        if (ua != UA_KEEP && !apply_u<true>(ln, m, ua)) return;
+        if (INSTR) {
+            const uint32_t r1 = (a >> XA_REC1_SHIFT) & 0xFu, r2 = (a >> XA_REC2_SHIFT) & 0xFu;
+            if (r1 != 0xFu) record<INSTR>(ln, m, r1, content, (a & XA_AUXPORT) ? (port == SIMB_PORT_UNKNOWN ? 0u : port + 1u) : 0u);
+            if (r2 != 0xFu) record<INSTR>(ln, m, r2, content);
+        }
+        if ((a & XA_WAIT0) && (flags & MF_STAT)) wait_sample(ln, ln.time - ln.time);  // Processing Start - Arrival = 0 here
+    }
+
+    // route one outgoing (out-port, content) over every matching connector, in connector order
+    template <bool INSTR>
+    SIMB_HD void emit2(Lane& ln, uint32_t out_port_abs, uint32_t content) {
+        const uint32_t be = SIMB_LDG(st.tab + SIMB_TAB_ROUTE_BEGIN + out_port_abs);
+        for (uint32_t r = be & 0xFFFFu; r < (be >> 16); r++) {
+            if (ln.npend >= net.max_pending) {
+                if (!ln.err) ln.err = 32;  // SIMB_ERR_CAPACITY: mailbox overflow
+                return;
+            }
+            const uint32_t rw = SIMB_LDG(st.tab + SIMB_TAB_ROUTES + r);
+            mail_word(ln, ln.npend, 0) = content;
+            mail_word(ln, ln.npend, 1) = rw;
+            ln.npend++;
+            if (INSTR) {
+                const uint32_t conn = ROUTE_CONN(rw);
+                ln.hash = (ln.hash ^ TRACE_MESSAGE_WORD(conn, content)) * TRACE_HASH_PRIME;
+#if SIMB_ON_DEVICE
+                atomicAdd(&st.conn_count[conn], 1ull);
+#else
+                st.conn_count[conn] += 1ull;
+#endif
+                if (ln.traced) {
+                    uint32_t k = st.trace_count[ln.rep];
+                    if (k < st.trace_cap) {
+                        SimbTraceRec t;
+                        t.step = ln.steps + 1u;
+                        t.meta = conn;
+                        t.content = content;
+                        t.aux = 0;
+                        t.time = ln.time;
+                        st.trace[(uint64_t)ln.rep * st.trace_cap + k] = t;
+                    }
+                    st.trace_count[ln.rep] = k + 1u;
+                }
+            }
+        }
+    }
+
+    // events_int of model m (any type)
+    template <bool INSTR>
+    SIMB_HD void int2(Lane& ln, uint32_t m) {
+        const uint32_t tf = TF(TF_TYPE, m);
+        const uint32_t type = tf & 0xFFu, n_out = (tf >> 16) & 0xFFu, flags = tf >> 24;
+        const uint32_t rows = TF(TF_ROWS, m);
+        const uint32_t wrow = rows & 0xFFFFu;
+        const uint32_t q = ln.W(wrow);
+        const uint32_t len = q & 0xFFFFu, head = q >> 16;
+        const uint32_t cap = TF(TF_CAP, m);
+        const uint32_t ph = ln.phase(m);
+        const uint32_t qs = (len == 0u ? IK_EMPTY : 0u) | (len <= cap ? IK_LE : 0u) |
+                            ((uint64_t)len >= 2ull * (uint64_t)cap ? IK_GE2 : 0u);
+        const uint32_t a = int_lut(INT_KEY(type, ph, qs));
+        if (a & 3u) {
+            ln.err = (a & 3u) == 1u ? 5u : 34u;  // InvalidModelState / a panic of the reference
+            return;
+        }
+        const uint32_t kind = (a >> IA_KIND_SHIFT) & 7u;
+        const uint32_t ob = TF(TF_OUT, m) & 0xFFFFu;
+        const uint32_t rcap = TF(TF_RING_CAP, m), w0 = TF(TF_RING_W0, m);
+        if (!BASIC && kind == KI_PG) {  // parallel_gateway.rs:174-182
+            const uint32_t w1 = TF(TF_RING_W1, m), n_in = (tf >> 8) & 0xFFu;
+            const uint32_t cnt = q;
+            uint32_t i = 0;
+            for (; i < cnt; i++)  // canonical choice: earliest-inserted full collection
+                if (RW(ln, w1 + i) == n_in) break;
+            if (i == cnt) {  // passivate
+                apply_u<false>(ln, m, UA_INF);
+                return;
+            }
+            apply_u<false>(ln, m, UA_ZERO);  // send_job :118-143
+            const uint32_t c = RW(ln, w0 + i);
+            for (uint32_t j = i; j + 1u < cnt; j++) {  // remove, keeping insertion order
+                RW(ln, w0 + j) = RW(ln, w0 + j + 1u);
+                RW(ln, w1 + j) = RW(ln, w1 + j + 1u);
+            }
+            ln.W(wrow) = cnt - 1u;
+            if (INSTR)
+                for (uint32_t p = 0; p < n_out; p++) record<INSTR>(ln, m, ACT_DEPARTURE, c, p + 1u);
+            for (uint32_t p = 0; p < n_out && !ln.err; p++) emit2<INSTR>(ln, ob + p, c);
+            return;
+        }
+        if (a & IA_SETPH) ln.set_phase(m, (a >> IA_PH_SHIFT) & 3u);
+        const uint32_t ua = (a >> IA_U_SHIFT) & 7u;
+        if (ua != UA_KEEP && !apply_u<false>(ln, m, ua)) return;
+        const uint32_t nr = (a >> IA_NREL_SHIFT) & 3u;
+        uint32_t n = nr == NR_ONE ? 1u : nr == NR_ALL ? len : nr == NR_CAP ? cap : 0u;
+        uint32_t port = 0, aux = 0, one = 0;
+        bool from_ring = true;
+        if (kind == KI_LB) {  // send_job load_balancer.rs:95-111 (the index is advanced first)
+            if (n_out == 0u) {
+                ln.err = 34;  // `% 0` panics
+                return;
+            }
+            uint32_t next = ln.W(wrow + 1u) + 1u;
+            if (next >= n_out) next = 0;
+            ln.W(wrow + 1u) = next;
+            port = next;
+            aux = next + 1u;
+        } else if (!BASIC && kind == KI_XGW) {  // send_jobs exclusive_gateway.rs:110-134: one draw per firing
+            if (ln.dm_int | ln.dm_ext) flush_draws(ln);  // earlier draws of the stream come first
+            const uint32_t wt = TF(TF_WTAB, m);
+            const uint32_t idx = sample_index_p(ln, flags, TF(TF_OUT, m) >> 16, wt & 0xFFFFu, TabP{st.vtab, m, wt >> 24});
+            if (ln.err) return;
+            if (idx >= n_out) {
+                ln.err = 34;  // flow_paths[idx] out of bounds panics
+                return;
+            }
+            port = idx;
+            aux = idx + 1u;
+        } else if (kind == KI_GEN) {  // generator.rs:169-177 (the draw was noted first)
+            from_ring = false;
+            if (ph == 1u) {  // release_job :98-123
+                const uint32_t last = q + 1u;
+                if (last >= SIMB_NUM_LITERAL) {
+                    ln.err = 32;  // content code space exhausted
+                    return;
+                }
+                ln.W(wrow) = last;
+                one = TF(TF_PREFIX, m) | last;
+                n = 1;
+                record<INSTR>(ln, m, ACT_GENERATION, one);
+            } else {  // initialize_generation :125-146
+                ln.set_phase(m, 1);
+                record<INSTR>(ln, m, ACT_INITIALIZATION, SIMB_CONTENT_NONE);
+            }
+        } else if (kind == KI_STORED) {  // storage.rs:115-130; stopwatch.rs:216-250
+            from_ring = false;
+            const bool sw = type == MT_STOPWATCH;
+            one = ln.W(wrow + (sw ? 1u : 0u));
+            record<INSTR>(ln, m, !sw ? ACT_DEPARTURE : (flags & MF_METRIC_MAX) ? ACT_MAXIMUM_FETCH : ACT_MINIMUM_FETCH, one);
+            n = one != SIMB_CONTENT_NONE ? 1u : 0u;
+        } else if (kind == KI_PROC_START) {  // process_next processor.rs:160-175
+            record<INSTR>(ln, m, ACT_PROCESSING_START, RW(ln, w0 + head));
+            if (flags & MF_STAT) wait_sample(ln, ln.time - RD(ln, TF(TF_RING_D, m) + head));
+        } else if (!BASIC && kind == KI_SGATE) {  // stochastic_gate.rs:174-183
+            from_ring = false;
+            one = RW(ln, w0 + head);
+            const bool pass = RW(ln, TF(TF_RING_W1, m) + head) != 0u;
+            uint32_t nh = head + 1u;
+            if (nh >= rcap) nh = 0;
+            ln.W(wrow) = (nh << 16) | (len - 1u);
+            record<INSTR>(ln, m, pass ? ACT_PASS : ACT_BLOCK, one);  // pass_job :129-141 / block_job :143-148
+            n = pass ? 1u : 0u;
+        }
+        // All records of one events_int call precede its messages (the reference routes the returned Vec
+        // afterwards, mod.rs:240-263).
+        if (INSTR && from_ring)
+            for (uint32_t i = 0; i < n; i++) {
+                uint32_t s = head + i;
+                if (s >= rcap) s -= rcap;
+                record<INSTR>(ln, m, ACT_DEPARTURE, RW(ln, w0 + s), aux);
+            }
+        for (uint32_t i = 0; i < n && !ln.err; i++) {
+            uint32_t c = one;
+            if (from_ring) {
+                const uint32_t qq = ln.W(wrow);
+                const uint32_t h = qq >> 16;
+                c = RW(ln, w0 + h);
+                uint32_t nh = h + 1u;
+                if (nh >= rcap) nh = 0;
+                ln.W(wrow) = (nh << 16) | ((qq & 0xFFFFu) - 1u);
+            }
+            emit2<INSTR>(ln, ob + port, c);
+        }
+    }
+
+    // Simulation::step for one lane, generic interpreter
+    template <bool INSTR>
+    SIMB_HD void step2(Lane& ln, bool live) {
+        const uint32_t M = net.n_models;
+        const bool had = live && ln.npend > 0;
+        uint32_t nev = 0;
+        // ---- external events: model order, then message order (:202-223) ----
+        if (warp_any(had)) {
+            const uint32_t np = had ? ln.npend : 0u;
+            // slot indices in (target model, slot) order: a nibble list for up to 8 messages, else selection
+            uint32_t order = 0, cnt = 0;
+            if (np == 1u) {
+                cnt = ROUTE_TGT(mail_word(ln, 0, 1)) < M ? 1u : 0u;  // a target id matching no model: dropped
+            } else if (np > 1u) {
+                uint32_t tm = 0;
+                for (uint32_t j = 0; j < np; j++) {
+                    const uint32_t t = ROUTE_TGT(mail_word(ln, j, 1));
+                    if (t < M) {
+                        tm |= 1u << t;
+                        cnt++;
+                    }
+                }
+                if (np <= 8u) {
+                    uint32_t k = 0;
+                    while (tm) {
+                        const uint32_t t = (uint32_t)lowest_bit(tm);
+                        tm &= tm - 1u;
+                        for (uint32_t j = 0; j < np; j++)
+                            if (ROUTE_TGT(mail_word(ln, j, 1)) == t) order |= j << (4u * k++);
+                    }
+                }
+            }
+            uint32_t last_key = 0;  // np > 8: (target + 1) << 8 | slot of the message served last
+            for (uint32_t i = 0; i < cnt && !ln.err; i++) {
+                uint32_t j = (order >> (4u * i)) & 0xFu;
+                if (np > 8u) {
+                    uint32_t best = 0xFFFFFFFFu;
+                    for (uint32_t jj = 0; jj < np; jj++) {
+                        const uint32_t t = ROUTE_TGT(mail_word(ln, jj, 1));
+                        const uint32_t key = ((t + 1u) << 8) | jj;
+                        if (t < M && key > last_key && key < best) best = key;
+                    }
+                    last_key = best;
+                    j = best & 0xFFu;
+                }
+                const uint32_t rw = mail_word(ln, j, 1);
+                nev++;
+                ext2<INSTR>(ln, ROUTE_TGT(rw), ROUTE_PORT(rw), mail_word(ln, j, 0));
+            }
+        }
+        // ---- pay the deferred draws (and top up the Philox prefetch) at this converged point ----
+        if (RNG == 0) philox_topup(ln, live);
+        if (live) flush_draws(ln);
+        // A failed events_ext aborts the step (`?` at :222); the replication freezes.
+        const bool go = live && !ln.err;
+        // ---- time advance (:225-236) over the models whose until_next_event is not +INF ----
+        double dt = 0.0;
+        if (go && !had) {
+            dt = SIMB_INF;
+            for (uint32_t mm = ln.amask; mm; mm &= mm - 1u) dt = fmin(dt, ln.D(net.drow_until + (uint32_t)lowest_bit(mm)));
+            if (dt == SIMB_INF) {
+                // nothing is scheduled: the reference subtracts +INF from every model (NaN) and the clock becomes +INF
+                for (uint32_t m = 0; m < M; m++)
+                    if ((TF(TF_TYPE, m) & 0xFFu) != MT_PASSIVE) {
+                        ln.D(net.drow_until + m) = ln.D(net.drow_until + m) - dt;
+                        ln.amask |= 1u << m;
+                    }
+            } else if (dt != 0.0) {
+                for (uint32_t mm = ln.amask; mm; mm &= mm - 1u) {
+                    const uint32_t m = (uint32_t)lowest_bit(mm);
+                    const double u = ln.D(net.drow_until + m) - dt;
+                    ln.D(net.drow_until + m) = u;
+                    if (u == 0.0) ln.zm |= 1u << m;
+                }
+            }
+        }
+        uint32_t zmk = 0;
+        if (go) {
+            ln.time = ln.time + dt;
+            ln.npend = 0;  // the mailbox is consumed; events_int refills it from slot 0
+            zmk = ln.zm;
+        }
+        // ---- internal events in model order (:237-268) ----
+        while (zmk && !ln.err) {
+            const uint32_t m = (uint32_t)lowest_bit(zmk);
+            zmk &= zmk - 1u;
+            nev++;
+            int2<INSTR>(ln, m);
+        }
+        if (go) {
+            ln.events += nev;
+            if (!ln.err) ln.steps++;
+        } else if (live) {
+            ln.events += nev;
+        }
+    }
+
+    // ================================================================================================
     // Simulation::step (mod.rs:198-272) for one lane.  `live` lanes execute;
     // the others only take part in the warp-level votes.
     // ================================================================================================
@@ -1146,6 +1661,10 @@ struct Engine {
 
     template <bool INSTR>
     SIMB_HD void step(Lane& ln, bool live) {
+        if (!STATIC) {
+            step2<INSTR>(ln, live);
+            return;
+        }
         const uint32_t M = net.n_models;
         const bool had = live && ln.npend > 0;
         uint32_t nev = 0;

@@ -154,6 +154,8 @@ struct SimbDevState {
     uint64_t n;           // real replication count
     uint64_t rep_offset;  // global index of local replication 0
     uint64_t seed;
+    const uint32_t* tab;   // generic interpreter: model / route table (actions.h, SIMB_TAB_WORDS u32)
+    const uint64_t* vtab;  // generic interpreter: distribution value table (SIMB_VTAB_WORDS 64-bit words)
     const uint64_t* ext;  // SIMB_RNG_EXTERNAL: [ext_len][stride]
     uint32_t ext_len;
     uint32_t trace_reps, trace_cap;

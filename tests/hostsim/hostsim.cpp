@@ -28,6 +28,8 @@ struct HS {
     std::vector<SimbTraceRec> trace;
     std::vector<unsigned long long> conn_count, record_count, totals;
     std::vector<uint64_t> ext;
+    std::vector<uint32_t> tab;
+    std::vector<uint64_t> vtab;
     uint32_t epoch = 0;
     uint64_t settle_every = 0;
     uint32_t rng_slots = SIMB_RNG_CACHE;  // Philox draws cached by the baked-shape code path (2 = streaming launches)
@@ -163,6 +165,11 @@ void* hs_new(const char* models, const char* connectors, uint64_t n, uint64_t re
     st.conn_count = h->conn_count.data();
     st.record_count = h->record_count.data();
     st.totals = h->totals.data();
+    h->tab.assign(SIMB_TAB_WORDS, 0u);
+    h->vtab.assign(SIMB_VTAB_WORDS, 0ull);
+    build_model_table(net, h->tab.data(), h->vtab.data());
+    st.tab = h->tab.data();
+    st.vtab = h->vtab.data();
     return h;
 }
 void hs_free(void* h) { delete (HS*)h; }
