@@ -215,8 +215,9 @@ enum {
     TF_COUNT
 };
 #define SIMB_TAB_ROUTE_BEGIN (TF_COUNT * SIMB_MAX_MODELS)                   /* per out-port: begin | end << 16 */
-#define SIMB_TAB_ROUTES (SIMB_TAB_ROUTE_BEGIN + SIMB_MAX_OUT_PORTS)           /* tgt | port << 8 | connector << 16 */
-#define SIMB_TAB_WORDS (SIMB_TAB_ROUTES + SIMB_MAX_ROUTES)
+#define SIMB_TAB_ROUTES (SIMB_TAB_ROUTE_BEGIN + SIMB_MAX_OUT_PORTS)           /* ROUTE_WORD(tgt, port, r, 0) */
+#define SIMB_TAB_CONN (SIMB_TAB_ROUTES + SIMB_MAX_ROUTES)                        /* connector index of route r */
+#define SIMB_TAB_WORDS (SIMB_TAB_CONN + SIMB_MAX_ROUTES)
 // value table: [6][SIMB_MAX_MODELS] 64-bit words: p0, p1, p2 (f64 bits), q0, q1, q2
 #define SIMB_VTAB_WORDS (6 * SIMB_MAX_MODELS)
 
@@ -248,7 +249,10 @@ inline void build_model_table(const SimbNetDesc& net, uint32_t* tab, uint64_t* v
     for (uint32_t p = 0; p < SIMB_MAX_OUT_PORTS; p++)
         tab[SIMB_TAB_ROUTE_BEGIN + p] = net.route_begin[p] | ((uint32_t)net.route_begin[p + 1] << 16);
     for (uint32_t r = 0; r < net.n_routes && r < SIMB_MAX_ROUTES; r++)
-        tab[SIMB_TAB_ROUTES + r] = ROUTE_WORD(net.routes[r].tgt_model, net.routes[r].tgt_port, net.routes[r].connector);
+    {
+        tab[SIMB_TAB_ROUTES + r] = ROUTE_WORD(net.routes[r].tgt_model, net.routes[r].tgt_port, r, 0);
+        tab[SIMB_TAB_CONN + r] = net.routes[r].connector;
+    }
 }
 
 }  // namespace simb

@@ -249,6 +249,10 @@ int launch_pass(simb_sim* s, const SimbLaunch& la_in, bool count_active, uint64_
     SimbLaunch la = la_in;
     la.reverse = s->sweep_reverse && (s->passes++ & 1u) ? 1u : 0u;
     la.l2_keep = s->l2_keep && la.k <= 8u ? 1u : 0u;  // only passes that re-stream the state soon
+    {
+        static const bool lockstep = getenv("SIMB_LOCKSTEP") && *getenv("SIMB_LOCKSTEP");  // A/B switch
+        la.lockstep = lockstep ? 1u : 0u;
+    }
     const SimbNetDesc& net = s->hn.desc;
     const uint32_t tiles = (uint32_t)(s->st.stride / s->dims.tile);
     const int lanes = grids_per_pass(s);
@@ -600,7 +604,7 @@ int simb_inject_input(simb_sim* s, const char* target_id, const char* target_por
     const uint32_t code = s->hn.content_code(content, &overflow);
     if (overflow) return fail(SIMB_ERR_CAPACITY, "content intern table overflow");
     const uint32_t port = tm < 0 ? SIMB_PORT_UNKNOWN : s->hn.resolve_in_port(tm, target_port);
-    const uint32_t rw = ROUTE_WORD(tm < 0 ? 0xFF : tm, port, 0xFFFF);
+    const uint32_t rw = ROUTE_WORD(tm < 0 ? 0xFF : tm, port, ROUTE_INJECTED, 0);  // the kernel adds the sequence number
     uint8_t* d_mask = nullptr;
     if (replica_mask) {
         CUDA_TRY(cudaMalloc((void**)&d_mask, s->st.n));
@@ -670,19 +674,28 @@ int simb_get_messages(simb_sim* s, uint64_t rep, simb_message* out, uint64_t cap
     if ((e = column_d(s, rep, &d))) return e;
     const uint32_t np = CTL_NPEND(w[net.wrow_ctl]);
     *count = np;
-    for (uint32_t j = 0; j < np && j < capacity && out; j++) {
-        uint32_t content, rw;
+    // the mailbox is kept in events_ext order (sorted by target model); the sequence number in the route word
+    // restores the order the reference's Vec<Message> has (emission order, injected messages last)
+    std::vector<std::pair<uint32_t, uint32_t>> mail(np);
+    for (uint32_t j = 0; j < np; j++) {
         if (j < net.pend_tile) {
-            content = w[net.wrow_pend + 2 * j];
-            rw = w[net.wrow_pend + 2 * j + 1];
+            mail[j].first = w[net.wrow_pend + 2 * j];
+            mail[j].second = w[net.wrow_pend + 2 * j + 1];
         } else {
             const uint32_t* base = s->st.mail + (uint64_t)(2u * (j - net.pend_tile)) * s->st.stride + rep;
-            CUDA_TRY(cudaMemcpy(&content, base, 4, cudaMemcpyDeviceToHost));
-            CUDA_TRY(cudaMemcpy(&rw, base + s->st.stride, 4, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(&mail[j].first, base, 4, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(&mail[j].second, base + s->st.stride, 4, cudaMemcpyDeviceToHost));
         }
+    }
+    std::stable_sort(mail.begin(), mail.end(),
+                     [](const std::pair<uint32_t, uint32_t>& a, const std::pair<uint32_t, uint32_t>& b) {
+                         return ROUTE_SEQ(a.second) < ROUTE_SEQ(b.second);
+                     });
+    for (uint32_t j = 0; j < np && j < capacity && out; j++) {
+        const uint32_t content = mail[j].first, rw = mail[j].second;
         simb_message& m = out[j];
         std::memset(&m, 0, sizeof m);
-        const uint32_t conn = ROUTE_CONN(rw);
+        const uint32_t conn = ROUTE_R(rw) == ROUTE_INJECTED ? 0xFFFFu : net.routes[ROUTE_R(rw)].connector;
         if (conn == 0xFFFF) {  // injected: Message::new("manual","manual",..) in the reference's tests
             put_str(m.source_id, sizeof m.source_id, "manual");
             put_str(m.source_port, sizeof m.source_port, "manual");

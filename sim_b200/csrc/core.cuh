@@ -657,7 +657,7 @@ struct Engine {
             }
             SimbRoute rt = net.routes[r];
             mail_word(ln, ln.npend, 0) = content;
-            mail_word(ln, ln.npend, 1) = ROUTE_WORD(rt.tgt_model, rt.tgt_port, rt.connector);
+            mail_word(ln, ln.npend, 1) = ROUTE_WORD(rt.tgt_model, rt.tgt_port, r, ln.npend);
             ln.npend++;
             if (rt.tgt_model < SIMB_MAX_MODELS) ln.tmask |= 1u << rt.tgt_model;
             if (INSTR) {
@@ -779,6 +779,22 @@ struct Engine {
             }
             ln.amask |= ln.dm_int;  // a model that owes a draw: its until_next_event row is stale
             ln.zm &= ~ln.dm_int;
+            // the mailbox must be sorted by target model (inject_input appends; a baked-shape kernel does not sort)
+            for (uint32_t i = 1; i < ln.npend; i++) {
+                const uint32_t c = mail_word(ln, i, 0), rw = mail_word(ln, i, 1);
+                uint32_t j = i;
+                while (j > 0u) {
+                    const uint32_t prev = mail_word(ln, j - 1u, 1);
+                    if (ROUTE_TGT(prev) <= ROUTE_TGT(rw)) break;
+                    mail_word(ln, j, 0) = mail_word(ln, j - 1u, 0);
+                    mail_word(ln, j, 1) = prev;
+                    j--;
+                }
+                if (j != i) {
+                    mail_word(ln, j, 0) = c;
+                    mail_word(ln, j, 1) = rw;
+                }
+            }
         }
         return ctl;
     }
@@ -1242,8 +1258,7 @@ struct Engine {
         const uint32_t wrow = rows & 0xFFFFu, flags = tf >> 24;
         const uint32_t rcap = TF(TF_RING_CAP, m), w0 = TF(TF_RING_W0, m), w1 = TF(TF_RING_W1, m);
         if (sp == XS_SGATE) {  // receive_job stochastic_gate.rs:101-122: Bernoulli draw AT ARRIVAL
-            apply_u<true>(ln, m, UA_ZERO);
-            if (ln.dm_int | ln.dm_ext) flush_draws(ln);  // earlier draws of the stream come first
+            apply_u<true>(ln, m, UA_ZERO);  // (ext2 made sure that no earlier draw of the stream is still owed)
             const bool pass = sample_bernoulli_p(ln, flags, TabP{st.vtab, m, TF(TF_WTAB, m) >> 24});
             if (ln.err) return;
             const uint32_t q = ln.W(wrow);
@@ -1336,9 +1351,10 @@ struct Engine {
         ln.W(wrow) = last;
     }
 
-    // events_ext of model m (any type) for one message
+    // events_ext of model m (any type) for one message.  false: nothing was done because the handler draws inline
+    // (StochasticGate) while earlier draws of the stream are still owed -- pay them (flush_draws) and call again.
     template <bool INSTR>
-    SIMB_HD void ext2(Lane& ln, uint32_t m, uint32_t port, uint32_t content) {
+    SIMB_HD bool ext2(Lane& ln, uint32_t m, uint32_t port, uint32_t content) {
         const uint32_t tf = TF(TF_TYPE, m);
         const uint32_t type = tf & 0xFFu, flags = tf >> 24;
         const uint32_t rows = TF(TF_ROWS, m);
@@ -1351,17 +1367,19 @@ struct Engine {
         const uint32_t a = ext_lut(EXT_KEY(type, port < 3u ? port : 3u, ln.phase(m), qs));
         if (a & 3u) {
             ln.err = (a & 3u) == 1u ? 7u : 5u;  // InvalidMessage / InvalidModelState
-            return;
+            return true;
         }
         if (!BASIC && ((a >> XA_SPECIAL_SHIFT) & 3u)) {
-            ext_special<INSTR>(ln, m, (a >> XA_SPECIAL_SHIFT) & 3u, port, content, tf, rows);
-            return;
+            const uint32_t sp = (a >> XA_SPECIAL_SHIFT) & 3u;
+            if (sp == XS_SGATE && (ln.dm_int | ln.dm_ext)) return false;
+            ext_special<INSTR>(ln, m, sp, port, content, tf, rows);
+            return true;
         }
         if (a & XA_PUSH) {
             const uint32_t rcap = TF(TF_RING_CAP, m);
             if (len >= rcap) {
                 ln.err = 32;  // SIMB_ERR_CAPACITY: the reference's Vec is unbounded here
-                return;
+                return true;
             }
             uint32_t s = head + len;
             if (s >= rcap) s -= rcap;
@@ -1372,13 +1390,14 @@ struct Engine {
         if (a & XA_STORE) ln.W(wrow) = content;
         if (a & XA_SETPH) ln.set_phase(m, (a >> XA_PH_SHIFT) & 3u);
         const uint32_t ua = (a >> XA_U_SHIFT) & 7u;
-        if (ua != UA_KEEP && !apply_u<true>(ln, m, ua)) return;
+        if (ua != UA_KEEP && !apply_u<true>(ln, m, ua)) return true;
         if (INSTR) {
             const uint32_t r1 = (a >> XA_REC1_SHIFT) & 0xFu, r2 = (a >> XA_REC2_SHIFT) & 0xFu;
             if (r1 != 0xFu) record<INSTR>(ln, m, r1, content, (a & XA_AUXPORT) ? (port == SIMB_PORT_UNKNOWN ? 0u : port + 1u) : 0u);
             if (r2 != 0xFu) record<INSTR>(ln, m, r2, content);
         }
         if ((a & XA_WAIT0) && (flags & MF_STAT)) wait_sample(ln, ln.time - ln.time);  // Processing Start - Arrival = 0 here
+        return true;
     }
 
     // route one outgoing (out-port, content) over every matching connector, in connector order
@@ -1390,12 +1409,21 @@ struct Engine {
                 if (!ln.err) ln.err = 32;  // SIMB_ERR_CAPACITY: mailbox overflow
                 return;
             }
-            const uint32_t rw = SIMB_LDG(st.tab + SIMB_TAB_ROUTES + r);
-            mail_word(ln, ln.npend, 0) = content;
-            mail_word(ln, ln.npend, 1) = rw;
+            const uint32_t rw = SIMB_LDG(st.tab + SIMB_TAB_ROUTES + r) | (ln.npend << 24);
+            // keep the mailbox sorted by target model (stable): the order events_ext runs in (mod.rs:203-221)
+            uint32_t j = ln.npend;
+            while (j > 0u) {
+                const uint32_t prev = mail_word(ln, j - 1u, 1);
+                if (ROUTE_TGT(prev) <= ROUTE_TGT(rw)) break;
+                mail_word(ln, j, 0) = mail_word(ln, j - 1u, 0);
+                mail_word(ln, j, 1) = prev;
+                j--;
+            }
+            mail_word(ln, j, 0) = content;
+            mail_word(ln, j, 1) = rw;
             ln.npend++;
             if (INSTR) {
-                const uint32_t conn = ROUTE_CONN(rw);
+                const uint32_t conn = SIMB_LDG(st.tab + SIMB_TAB_CONN + r);
                 ln.hash = (ln.hash ^ TRACE_MESSAGE_WORD(conn, content)) * TRACE_HASH_PRIME;
 #if SIMB_ON_DEVICE
                 atomicAdd(&st.conn_count[conn], 1ull);
@@ -1419,9 +1447,10 @@ struct Engine {
         }
     }
 
-    // events_int of model m (any type)
+    // events_int of model m (any type).  false: nothing was done because the handler draws inline
+    // (ExclusiveGateway) while earlier draws of the stream are still owed -- pay them and call again.
     template <bool INSTR>
-    SIMB_HD void int2(Lane& ln, uint32_t m) {
+    SIMB_HD bool int2(Lane& ln, uint32_t m) {
         const uint32_t tf = TF(TF_TYPE, m);
         const uint32_t type = tf & 0xFFu, n_out = (tf >> 16) & 0xFFu, flags = tf >> 24;
         const uint32_t rows = TF(TF_ROWS, m);
@@ -1435,9 +1464,10 @@ struct Engine {
         const uint32_t a = int_lut(INT_KEY(type, ph, qs));
         if (a & 3u) {
             ln.err = (a & 3u) == 1u ? 5u : 34u;  // InvalidModelState / a panic of the reference
-            return;
+            return true;
         }
         const uint32_t kind = (a >> IA_KIND_SHIFT) & 7u;
+        if (!BASIC && kind == KI_XGW && (ln.dm_int | ln.dm_ext)) return false;
         const uint32_t ob = TF(TF_OUT, m) & 0xFFFFu;
         const uint32_t rcap = TF(TF_RING_CAP, m), w0 = TF(TF_RING_W0, m);
         if (!BASIC && kind == KI_PG) {  // parallel_gateway.rs:174-182
@@ -1448,7 +1478,7 @@ struct Engine {
                 if (RW(ln, w1 + i) == n_in) break;
             if (i == cnt) {  // passivate
                 apply_u<false>(ln, m, UA_INF);
-                return;
+                return true;
             }
             apply_u<false>(ln, m, UA_ZERO);  // send_job :118-143
             const uint32_t c = RW(ln, w0 + i);
@@ -1460,11 +1490,11 @@ struct Engine {
             if (INSTR)
                 for (uint32_t p = 0; p < n_out; p++) record<INSTR>(ln, m, ACT_DEPARTURE, c, p + 1u);
             for (uint32_t p = 0; p < n_out && !ln.err; p++) emit2<INSTR>(ln, ob + p, c);
-            return;
+            return true;
         }
         if (a & IA_SETPH) ln.set_phase(m, (a >> IA_PH_SHIFT) & 3u);
         const uint32_t ua = (a >> IA_U_SHIFT) & 7u;
-        if (ua != UA_KEEP && !apply_u<false>(ln, m, ua)) return;
+        if (ua != UA_KEEP && !apply_u<false>(ln, m, ua)) return true;
         const uint32_t nr = (a >> IA_NREL_SHIFT) & 3u;
         uint32_t n = nr == NR_ONE ? 1u : nr == NR_ALL ? len : nr == NR_CAP ? cap : 0u;
         uint32_t port = 0, aux = 0, one = 0;
@@ -1472,7 +1502,7 @@ struct Engine {
         if (kind == KI_LB) {  // send_job load_balancer.rs:95-111 (the index is advanced first)
             if (n_out == 0u) {
                 ln.err = 34;  // `% 0` panics
-                return;
+                return true;
             }
             uint32_t next = ln.W(wrow + 1u) + 1u;
             if (next >= n_out) next = 0;
@@ -1480,13 +1510,12 @@ struct Engine {
             port = next;
             aux = next + 1u;
         } else if (!BASIC && kind == KI_XGW) {  // send_jobs exclusive_gateway.rs:110-134: one draw per firing
-            if (ln.dm_int | ln.dm_ext) flush_draws(ln);  // earlier draws of the stream come first
             const uint32_t wt = TF(TF_WTAB, m);
             const uint32_t idx = sample_index_p(ln, flags, TF(TF_OUT, m) >> 16, wt & 0xFFFFu, TabP{st.vtab, m, wt >> 24});
-            if (ln.err) return;
+            if (ln.err) return true;
             if (idx >= n_out) {
                 ln.err = 34;  // flow_paths[idx] out of bounds panics
-                return;
+                return true;
             }
             port = idx;
             aux = idx + 1u;
@@ -1496,7 +1525,7 @@ struct Engine {
                 const uint32_t last = q + 1u;
                 if (last >= SIMB_NUM_LITERAL) {
                     ln.err = 32;  // content code space exhausted
-                    return;
+                    return true;
                 }
                 ln.W(wrow) = last;
                 one = TF(TF_PREFIX, m) | last;
@@ -1545,102 +1574,122 @@ struct Engine {
             }
             emit2<INSTR>(ln, ob + port, c);
         }
+        return true;
     }
 
-    // Simulation::step for one lane, generic interpreter
+    // ---- Simulation::step for one lane, generic interpreter -----------------------------------------
+    // Replications are independent, so the lanes of a warp need not agree on WHICH step they are in: the
+    // warp runs `micro` in a loop, and in each iteration every lane advances its own step by at most one
+    // external event, the time advance, and one internal event.  A replication whose step delivers one
+    // message and fires one model completes a whole step per iteration; one with a burst (a fan-out, a
+    // batch release) takes more iterations for that step while the other lanes move on to their next
+    // steps.  The cost of a launch is then the maximum over lanes of the SUM of their work, not the sum
+    // over steps of the maximum (what step-level lockstep pays).
+    struct Prog {
+        uint32_t stage;   // 0 = at a step boundary, 1 = external phase, 2 = internal phase
+        uint32_t np, ei;  // messages in the mailbox at the start of the step, delivered so far
+        uint32_t zmk;     // imminent models not yet fired in this step
+        uint32_t nev;
+        bool flush;       // a handler that draws inline is waiting for the deferred draws to be paid
+    };
+    SIMB_HD void prog_init(Prog& pg) {
+        pg.stage = 0;
+        pg.np = pg.ei = 0;
+        pg.zmk = 0;
+        pg.nev = 0;
+        pg.flush = false;
+    }
+    // One iteration for a lane that is `act`ive (others fall through).  Returns true when the lane has just
+    // completed a step (its stage is 0 again).
+    template <bool INSTR>
+    SIMB_HD bool micro(Lane& ln, Prog& pg, bool act) {
+        const uint32_t M = net.n_models;
+        // ---- step begin (:199-201); the mailbox is sorted by target model, unknown targets (0xFF) last ----
+        if (act && pg.stage == 0u) {
+            pg.stage = 1u;
+            pg.nev = 0;
+            pg.ei = 0;
+            pg.np = ln.npend;
+        }
+        // ---- one external event: model order, then message order (:202-223) ----
+        if (act && pg.stage == 1u && pg.ei < pg.np && !ln.err) {
+            const uint32_t rw = mail_word(ln, pg.ei, 1);
+            if (ROUTE_TGT(rw) < M) {
+                if (ext2<INSTR>(ln, ROUTE_TGT(rw), ROUTE_PORT(rw), mail_word(ln, pg.ei, 0))) {
+                    pg.ei++;
+                    pg.nev++;
+                } else {
+                    pg.flush = true;
+                }
+            } else {
+                pg.ei = pg.np;  // a target id matching no model: never delivered
+            }
+        }
+        // ---- every message delivered (or a failed events_ext, `?` at :222): pay the deferred draws, advance ----
+        // ---- the ONE place where deferred draws are paid: at the end of the external phase, and for a handler
+        // that is waiting to draw inline ----
+        const bool ext_done = act && pg.stage == 1u && (pg.ei >= pg.np || ln.err);
+        if (ext_done || (act && pg.flush)) {
+            pg.flush = false;
+            if (RNG == 0 && ln.ccount <= 1u) philox_refill(ln);
+            flush_draws(ln);
+        }
+        if (ext_done) {
+            pg.stage = 2u;
+            pg.zmk = 0;
+            if (!ln.err) {
+                // time advance (:225-236) over the models whose until_next_event is not +INF
+                double dt = 0.0;
+                if (pg.np == 0u) {
+                    dt = SIMB_INF;
+                    for (uint32_t mm = ln.amask; mm; mm &= mm - 1u)
+                        dt = fmin(dt, ln.D(net.drow_until + (uint32_t)lowest_bit(mm)));
+                    if (dt == SIMB_INF) {
+                        // nothing is scheduled: the reference subtracts +INF from every model (NaN), the clock becomes +INF
+                        for (uint32_t m = 0; m < M; m++)
+                            if ((TF(TF_TYPE, m) & 0xFFu) != MT_PASSIVE) {
+                                ln.D(net.drow_until + m) = ln.D(net.drow_until + m) - dt;
+                                ln.amask |= 1u << m;
+                            }
+                    } else if (dt != 0.0) {
+                        for (uint32_t mm = ln.amask; mm; mm &= mm - 1u) {
+                            const uint32_t m = (uint32_t)lowest_bit(mm);
+                            const double u = ln.D(net.drow_until + m) - dt;
+                            ln.D(net.drow_until + m) = u;
+                            if (u == 0.0) ln.zm |= 1u << m;
+                        }
+                    }
+                }
+                ln.time = ln.time + dt;
+                ln.npend = 0;  // the mailbox is consumed; events_int refills it from slot 0
+                pg.zmk = ln.zm;
+            }
+        }
+        // ---- one internal event, in model order (:237-268) ----
+        if (act && pg.stage == 2u && pg.zmk && !ln.err) {
+            const uint32_t m = (uint32_t)lowest_bit(pg.zmk);
+            if (int2<INSTR>(ln, m)) {
+                pg.zmk &= pg.zmk - 1u;
+                pg.nev++;
+            } else {
+                pg.flush = true;
+            }
+        }
+        // ---- step end ----
+        if (act && pg.stage == 2u && (pg.zmk == 0u || ln.err)) {
+            pg.stage = 0u;
+            ln.events += pg.nev;
+            if (!ln.err) ln.steps++;
+            return true;
+        }
+        return false;
+    }
     template <bool INSTR>
     SIMB_HD void step2(Lane& ln, bool live) {
-        const uint32_t M = net.n_models;
-        const bool had = live && ln.npend > 0;
-        uint32_t nev = 0;
-        // ---- external events: model order, then message order (:202-223) ----
-        if (warp_any(had)) {
-            const uint32_t np = had ? ln.npend : 0u;
-            // slot indices in (target model, slot) order: a nibble list for up to 8 messages, else selection
-            uint32_t order = 0, cnt = 0;
-            if (np == 1u) {
-                cnt = ROUTE_TGT(mail_word(ln, 0, 1)) < M ? 1u : 0u;  // a target id matching no model: dropped
-            } else if (np > 1u) {
-                uint32_t tm = 0;
-                for (uint32_t j = 0; j < np; j++) {
-                    const uint32_t t = ROUTE_TGT(mail_word(ln, j, 1));
-                    if (t < M) {
-                        tm |= 1u << t;
-                        cnt++;
-                    }
-                }
-                if (np <= 8u) {
-                    uint32_t k = 0;
-                    while (tm) {
-                        const uint32_t t = (uint32_t)lowest_bit(tm);
-                        tm &= tm - 1u;
-                        for (uint32_t j = 0; j < np; j++)
-                            if (ROUTE_TGT(mail_word(ln, j, 1)) == t) order |= j << (4u * k++);
-                    }
-                }
-            }
-            uint32_t last_key = 0;  // np > 8: (target + 1) << 8 | slot of the message served last
-            for (uint32_t i = 0; i < cnt && !ln.err; i++) {
-                uint32_t j = (order >> (4u * i)) & 0xFu;
-                if (np > 8u) {
-                    uint32_t best = 0xFFFFFFFFu;
-                    for (uint32_t jj = 0; jj < np; jj++) {
-                        const uint32_t t = ROUTE_TGT(mail_word(ln, jj, 1));
-                        const uint32_t key = ((t + 1u) << 8) | jj;
-                        if (t < M && key > last_key && key < best) best = key;
-                    }
-                    last_key = best;
-                    j = best & 0xFFu;
-                }
-                const uint32_t rw = mail_word(ln, j, 1);
-                nev++;
-                ext2<INSTR>(ln, ROUTE_TGT(rw), ROUTE_PORT(rw), mail_word(ln, j, 0));
-            }
-        }
-        // ---- pay the deferred draws (and top up the Philox prefetch) at this converged point ----
-        if (RNG == 0) philox_topup(ln, live);
-        if (live) flush_draws(ln);
-        // A failed events_ext aborts the step (`?` at :222); the replication freezes.
-        const bool go = live && !ln.err;
-        // ---- time advance (:225-236) over the models whose until_next_event is not +INF ----
-        double dt = 0.0;
-        if (go && !had) {
-            dt = SIMB_INF;
-            for (uint32_t mm = ln.amask; mm; mm &= mm - 1u) dt = fmin(dt, ln.D(net.drow_until + (uint32_t)lowest_bit(mm)));
-            if (dt == SIMB_INF) {
-                // nothing is scheduled: the reference subtracts +INF from every model (NaN) and the clock becomes +INF
-                for (uint32_t m = 0; m < M; m++)
-                    if ((TF(TF_TYPE, m) & 0xFFu) != MT_PASSIVE) {
-                        ln.D(net.drow_until + m) = ln.D(net.drow_until + m) - dt;
-                        ln.amask |= 1u << m;
-                    }
-            } else if (dt != 0.0) {
-                for (uint32_t mm = ln.amask; mm; mm &= mm - 1u) {
-                    const uint32_t m = (uint32_t)lowest_bit(mm);
-                    const double u = ln.D(net.drow_until + m) - dt;
-                    ln.D(net.drow_until + m) = u;
-                    if (u == 0.0) ln.zm |= 1u << m;
-                }
-            }
-        }
-        uint32_t zmk = 0;
-        if (go) {
-            ln.time = ln.time + dt;
-            ln.npend = 0;  // the mailbox is consumed; events_int refills it from slot 0
-            zmk = ln.zm;
-        }
-        // ---- internal events in model order (:237-268) ----
-        while (zmk && !ln.err) {
-            const uint32_t m = (uint32_t)lowest_bit(zmk);
-            zmk &= zmk - 1u;
-            nev++;
-            int2<INSTR>(ln, m);
-        }
-        if (go) {
-            ln.events += nev;
-            if (!ln.err) ln.steps++;
-        } else if (live) {
-            ln.events += nev;
+        if (!live) return;
+        Prog pg;
+        prog_init(pg);
+        while (!micro<INSTR>(ln, pg, true)) {
         }
     }
 

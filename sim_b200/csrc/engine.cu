@@ -84,6 +84,7 @@ __global__ void simb_inject_kernel(const __grid_constant__ SimbNetDesc net, cons
         atomicAdd(overflow, 1ull);
         return;
     }
+    route_word |= np << 24;  // sequence number: after everything already pending (the step kernel sorts by target)
     if (np < net.pend_tile) {
         st.w[(uint64_t)(net.wrow_pend + 2u * np) * st.stride + r] = content;
         st.w[(uint64_t)(net.wrow_pend + 2u * np + 1u) * st.stride + r] = route_word;

@@ -7,7 +7,7 @@
 #include <stdint.h>
 
 #define SIMB_MAX_MODELS 32
-#define SIMB_MAX_ROUTES 160
+#define SIMB_MAX_ROUTES 160     /* < 255: a route index is one byte of the mailbox route word */
 #define SIMB_MAX_OUT_PORTS 96   /* total out-ports over all models */
 #define SIMB_MAX_WEIGHTS 64     /* total cumulative-weight entries over all ExclusiveGateways */
 #define SIMB_MAX_NAMES 255      /* content prefix / literal intern table */
@@ -115,11 +115,18 @@ struct SimbNetDesc {
 #define CTL_MAKE(err, epoch, npend, absent) \
     (((uint32_t)(err) & 0xFFu) | (((uint32_t)(epoch) & 0xFFu) << 8) | (((uint32_t)(npend) & 0xFFu) << 16) | (((uint32_t)(absent) & 1u) << 24))
 
-// route word in a mailbox slot
-#define ROUTE_WORD(tgt, port, conn) (((uint32_t)(tgt) & 0xFFu) | (((uint32_t)(port) & 0xFFu) << 8) | (((uint32_t)(conn) & 0xFFFFu) << 16))
+// route word in a mailbox slot: target model (0xFF = no such model), index among the target's input ports,
+// route index (into SimbNetDesc.routes; ROUTE_INJECTED for Simulation::inject_input) and the emission sequence
+// number within the step.  The generic interpreter keeps the mailbox SORTED by target model (stable), which is
+// the order events_ext is called in (mod.rs:203-221); the sequence number restores the reference's message
+// order for get_messages.
+#define ROUTE_INJECTED 0xFFu
+#define ROUTE_WORD(tgt, port, r, seq) \
+    (((uint32_t)(tgt) & 0xFFu) | (((uint32_t)(port) & 0xFFu) << 8) | (((uint32_t)(r) & 0xFFu) << 16) | (((uint32_t)(seq) & 0xFFu) << 24))
 #define ROUTE_TGT(w) ((w) & 0xFFu)
 #define ROUTE_PORT(w) (((w) >> 8) & 0xFFu)
-#define ROUTE_CONN(w) (((w) >> 16) & 0xFFFFu)
+#define ROUTE_R(w) (((w) >> 16) & 0xFFu)
+#define ROUTE_SEQ(w) ((w) >> 24)
 
 // trace word (shared definition with the oracle, DESIGN.md "trace hash")
 #define TRACE_RECORD_WORD(model, action, aux, content) \
@@ -186,5 +193,8 @@ struct SimbLaunch {
     uint32_t reverse;     // 1 = CTA i takes the grid's tile (gridDim.x - 1 - i): consecutive passes sweep the batch in
                           // opposite directions, so a pass starts on the tiles the previous one left in L2
     uint32_t l2_keep;     // 1 = the state tile copies carry the L2 evict_last hint (streaming passes)
+    uint32_t lockstep;    // generic interpreter, A/B switch: 1 = the lanes of a warp wait for each other at every step
+                          // boundary (0 = each lane runs through its own steps)
+    uint32_t reserved;
     double until;
 };

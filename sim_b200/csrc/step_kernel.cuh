@@ -230,12 +230,31 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
     // ---- 3. up to K lockstep steps (each warp runs on its own; no block barrier per step) ----
     bool done = absent || (la.mode == 1 && CTL_EPOCH(ctl) == la.epoch);
     bool stepped = false;
-    for (uint32_t k = 0; k < la.k; k++) {
-        const bool live = !done && ln.err == 0;
-        if (__ballot_sync(0xFFFFFFFFu, live) == 0u) break;  // every replication of this warp is finished
-        stepped = true;
-        eng.template step<INSTR>(ln, live);
-        if (live && la.mode == 1 && !(ln.time < la.until)) done = true;  // step_until: mod.rs:281-285
+    if (SHAPE < 0) {
+        // generic interpreter: the lanes advance through their own steps, one micro-iteration at a time (core.cuh)
+        typename Engine<RNG, shape_tier<SHAPE>(), RARE, BASIC>::Prog pg;
+        eng.prog_init(pg);
+        uint32_t k_left = la.k;
+        bool act = !done && ln.err == 0 && k_left > 0u;
+        bool parked = false;  // lockstep mode: this lane has finished the step the others are still in
+        while (__ballot_sync(0xFFFFFFFFu, act) != 0u) {  // until every replication of this warp has done its steps
+            stepped = true;
+            if (eng.template micro<INSTR>(ln, pg, act && !parked)) {
+                k_left--;
+                if (la.mode == 1 && !(ln.time < la.until)) done = true;  // step_until: mod.rs:281-285
+                act = !done && ln.err == 0 && k_left > 0u;
+                parked = la.lockstep != 0u;
+            }
+            if (la.lockstep && __ballot_sync(0xFFFFFFFFu, act && !parked) == 0u) parked = false;
+        }
+    } else {
+        for (uint32_t k = 0; k < la.k; k++) {
+            const bool live = !done && ln.err == 0;
+            if (__ballot_sync(0xFFFFFFFFu, live) == 0u) break;  // every replication of this warp is finished
+            stepped = true;
+            eng.template step<INSTR>(ln, live);
+            if (live && la.mode == 1 && !(ln.time < la.until)) done = true;  // step_until: mod.rs:281-285
+        }
     }
     // last launch of an API call: pay the deferred draws so the stored state is observable as is
     if (la.settle && !absent && (ln.dm_int | ln.dm_ext)) {

@@ -212,11 +212,12 @@ int hs_inject(void* hv, const char* tgt, const char* port, const char* content) 
     bool ov = false;
     uint32_t code = h->hn.content_code(content, &ov);
     uint32_t pidx = tm < 0 ? SIMB_PORT_UNKNOWN : h->hn.resolve_in_port(tm, port);
-    uint32_t rw = ROUTE_WORD(tm < 0 ? 0xFF : tm, pidx, 0xFFFF);
+    uint32_t rw0 = ROUTE_WORD(tm < 0 ? 0xFF : tm, pidx, ROUTE_INJECTED, 0);
     for (uint64_t r = 0; r < h->n; r++) {
         uint32_t& ctl = h->w[(size_t)net.wrow_ctl * h->n + r];
         uint32_t np = CTL_NPEND(ctl);
         if (np >= net.max_pending) return 32;
+        const uint32_t rw = rw0 | (np << 24);
         if (np < net.pend_tile) {
             h->w[(size_t)(net.wrow_pend + 2 * np) * h->n + r] = code;
             h->w[(size_t)(net.wrow_pend + 2 * np + 1) * h->n + r] = rw;

@@ -161,5 +161,5 @@ class HostSim:
         out = []
         for i in range(n):
             self.L.hs_pending_get(self.h, C.c_uint64(rep), i, o)
-            out.append((self.render(o[0]), o[1] & 0xFF, (o[1] >> 8) & 0xFF, o[1] >> 16))
-        return out
+            out.append((self.render(o[0]), o[1] & 0xFF, (o[1] >> 8) & 0xFF, (o[1] >> 16) & 0xFF, o[1] >> 24))
+        return sorted(out, key=lambda p: p[4])  # emission order (the mailbox itself is sorted by target model)
