@@ -119,6 +119,11 @@ struct Lane {
     // generic interpreter: models whose until_next_event is not +INF / is exactly 0.0 (kept in step with every
     // write of an until_next_event row, so the time advance and the imminent-model scan visit those only)
     uint32_t amask, zm;
+    // ... and the smallest non-zero until_next_event among them, so that most time advances need no search:
+    // it is folded forward whenever a value is written and by the subtraction pass itself; `dirty` (a running
+    // timer was overwritten, or the state was just loaded) forces one search
+    double nmin;
+    bool dirty;
 
     SIMB_HD double& D(uint32_t row) { return d[(size_t)row * stride]; }
     SIMB_HD uint32_t& W(uint32_t row) { return w[(size_t)row * stride]; }
@@ -616,6 +621,7 @@ struct Engine {
             const double dv = sample_continuous_kind(ln, (TF(TF_WTAB, m) >> 16) & 0xFFu, TabP{st.vtab, m, 0u});
             ln.D(net.drow_until + m) = dv;
             if (dv == 0.0) ln.zm |= 1u << m;  // a variate of exactly zero makes the model imminent at once
+            else ln.nmin = fmin(ln.nmin, dv);
         }
     }
 
@@ -766,6 +772,8 @@ struct Engine {
         ln.dm_ext = 0;
         ln.tmask = 0;
         ln.amask = ln.zm = 0;
+        ln.nmin = SIMB_INF;
+        ln.dirty = true;
         if (STATIC) {
             for (uint32_t j = 0; j < ln.npend; j++) {
                 const uint32_t t = ROUTE_TGT(mail_word(ln, j, 1));
@@ -1223,11 +1231,32 @@ struct Engine {
         return kIntLutHost.v[key];
 #endif
     }
+    struct Prog {
+        uint32_t stage;   // 0 = at a step boundary, 1 = external phase, 2 = internal phase
+        uint32_t np, ei;  // messages in the mailbox at the start of the step, delivered so far
+        uint32_t zmk;     // imminent models not yet fired in this step
+        uint32_t nev;
+        bool flush;       // a handler that draws inline is waiting for the deferred draws to be paid
+        // release in progress (events_int of a queueing model): jobs left | REL_* flags, model | absolute out-port << 8,
+        // and the job content when it does not come from the model's ring
+        uint32_t rel, rel_mp, rel_one;
+    };
+#define REL_RING 0x10000u
+#define REL_PORTS 0x20000u
+    SIMB_HD void prog_init(Prog& pg) {
+        pg.stage = 0;
+        pg.np = pg.ei = 0;
+        pg.zmk = 0;
+        pg.nev = 0;
+        pg.flush = false;
+        pg.rel = pg.rel_mp = pg.rel_one = 0;
+    }
     // until_next_event[m] := 0 / +INF / p0 / "a fresh variate" (deferred, see flush_draws), keeping the
     // active and imminent masks exact.  false: a distribution parameter error froze the replication.
     template <bool EXT>
     SIMB_HD bool apply_u(Lane& ln, uint32_t m, uint32_t ua) {
         const uint32_t bit = 1u << m;
+        if ((ln.amask & ~ln.zm) & bit) ln.dirty = true;  // a running timer is overwritten (Batcher): nmin may be stale
         if (ua == UA_DRAW) {
             const uint32_t de = TF(TF_WTAB, m) >> 24;
             if (de) {  // parameter errors surface at draw time (random_variable.rs:72-87)
@@ -1246,8 +1275,12 @@ struct Engine {
         ln.D(net.drow_until + m) = v;
         if (ua == UA_INF) ln.amask &= ~bit;
         else ln.amask |= bit;
-        if (v == 0.0) ln.zm |= bit;
-        else ln.zm &= ~bit;
+        if (v == 0.0) {
+            ln.zm |= bit;
+        } else {
+            ln.zm &= ~bit;
+            ln.nmin = fmin(ln.nmin, v);  // (+INF leaves it alone)
+        }
         return true;
     }
 
@@ -1450,7 +1483,7 @@ struct Engine {
     // events_int of model m (any type).  false: nothing was done because the handler draws inline
     // (ExclusiveGateway) while earlier draws of the stream are still owed -- pay them and call again.
     template <bool INSTR>
-    SIMB_HD bool int2(Lane& ln, uint32_t m) {
+    SIMB_HD bool int2(Lane& ln, Prog& pg, uint32_t m) {
         const uint32_t tf = TF(TF_TYPE, m);
         const uint32_t type = tf & 0xFFu, n_out = (tf >> 16) & 0xFFu, flags = tf >> 24;
         const uint32_t rows = TF(TF_ROWS, m);
@@ -1489,7 +1522,9 @@ struct Engine {
             ln.W(wrow) = cnt - 1u;
             if (INSTR)
                 for (uint32_t p = 0; p < n_out; p++) record<INSTR>(ln, m, ACT_DEPARTURE, c, p + 1u);
-            for (uint32_t p = 0; p < n_out && !ln.err; p++) emit2<INSTR>(ln, ob + p, c);
+            pg.rel = n_out ? (n_out | REL_PORTS) : 0u;
+            pg.rel_mp = m | (ob << 8);
+            pg.rel_one = c;
             return true;
         }
         if (a & IA_SETPH) ln.set_phase(m, (a >> IA_PH_SHIFT) & 3u);
@@ -1562,19 +1597,30 @@ struct Engine {
                 if (s >= rcap) s -= rcap;
                 record<INSTR>(ln, m, ACT_DEPARTURE, RW(ln, w0 + s), aux);
             }
-        for (uint32_t i = 0; i < n && !ln.err; i++) {
-            uint32_t c = one;
-            if (from_ring) {
-                const uint32_t qq = ln.W(wrow);
-                const uint32_t h = qq >> 16;
-                c = RW(ln, w0 + h);
-                uint32_t nh = h + 1u;
-                if (nh >= rcap) nh = 0;
-                ln.W(wrow) = (nh << 16) | ((qq & 0xFFFFu) - 1u);
-            }
-            emit2<INSTR>(ln, ob + port, c);
-        }
+        // the jobs leave one per micro-iteration (release_one), so a batch does not hold up the other lanes
+        pg.rel = n ? (n | (from_ring ? REL_RING : 0u)) : 0u;
+        pg.rel_mp = m | ((ob + port) << 8);
+        pg.rel_one = one;
         return true;
+    }
+    // one job of the release in progress: pop it (unless the content is given) and route it
+    template <bool INSTR>
+    SIMB_HD void release_one(Lane& ln, Prog& pg) {
+        uint32_t c = pg.rel_one;
+        const uint32_t m = pg.rel_mp & 0xFFu;
+        if (pg.rel & REL_RING) {
+            const uint32_t wrow = TF(TF_ROWS, m) & 0xFFFFu, rcap = TF(TF_RING_CAP, m);
+            const uint32_t qq = ln.W(wrow);
+            const uint32_t h = qq >> 16;
+            c = RW(ln, TF(TF_RING_W0, m) + h);
+            uint32_t nh = h + 1u;
+            if (nh >= rcap) nh = 0;
+            ln.W(wrow) = (nh << 16) | ((qq & 0xFFFFu) - 1u);
+        }
+        emit2<INSTR>(ln, pg.rel_mp >> 8, c);
+        if (pg.rel & REL_PORTS) pg.rel_mp += 1u << 8;  // ParallelGateway: the same job on the next output port
+        pg.rel--;
+        if ((pg.rel & 0xFFFFu) == 0u) pg.rel = 0;
     }
 
     // ---- Simulation::step for one lane, generic interpreter -----------------------------------------
@@ -1585,20 +1631,6 @@ struct Engine {
     // batch release) takes more iterations for that step while the other lanes move on to their next
     // steps.  The cost of a launch is then the maximum over lanes of the SUM of their work, not the sum
     // over steps of the maximum (what step-level lockstep pays).
-    struct Prog {
-        uint32_t stage;   // 0 = at a step boundary, 1 = external phase, 2 = internal phase
-        uint32_t np, ei;  // messages in the mailbox at the start of the step, delivered so far
-        uint32_t zmk;     // imminent models not yet fired in this step
-        uint32_t nev;
-        bool flush;       // a handler that draws inline is waiting for the deferred draws to be paid
-    };
-    SIMB_HD void prog_init(Prog& pg) {
-        pg.stage = 0;
-        pg.np = pg.ei = 0;
-        pg.zmk = 0;
-        pg.nev = 0;
-        pg.flush = false;
-    }
     // One iteration for a lane that is `act`ive (others fall through).  Returns true when the lane has just
     // completed a step (its stage is 0 again).
     template <bool INSTR>
@@ -1629,7 +1661,7 @@ struct Engine {
         // ---- the ONE place where deferred draws are paid: at the end of the external phase, and for a handler
         // that is waiting to draw inline ----
         const bool ext_done = act && pg.stage == 1u && (pg.ei >= pg.np || ln.err);
-        if (ext_done || (act && pg.flush)) {
+        if (ext_done || pg.flush) {  // (pg.flush without act: the settle pass at the end of a launch)
             pg.flush = false;
             if (RNG == 0 && ln.ccount <= 1u) philox_refill(ln);
             flush_draws(ln);
@@ -1641,9 +1673,14 @@ struct Engine {
                 // time advance (:225-236) over the models whose until_next_event is not +INF
                 double dt = 0.0;
                 if (pg.np == 0u) {
-                    dt = SIMB_INF;
-                    for (uint32_t mm = ln.amask; mm; mm &= mm - 1u)
-                        dt = fmin(dt, ln.D(net.drow_until + (uint32_t)lowest_bit(mm)));
+                    if (ln.dirty) {  // search the smallest non-zero value (zeros are exactly the bits of zm)
+                        double nm = SIMB_INF;
+                        for (uint32_t mm = ln.amask & ~ln.zm; mm; mm &= mm - 1u)
+                            nm = fmin(nm, ln.D(net.drow_until + (uint32_t)lowest_bit(mm)));
+                        ln.nmin = nm;
+                        ln.dirty = false;
+                    }
+                    dt = ln.zm ? fmin(ln.nmin, 0.0) : ln.nmin;
                     if (dt == SIMB_INF) {
                         // nothing is scheduled: the reference subtracts +INF from every model (NaN), the clock becomes +INF
                         for (uint32_t m = 0; m < M; m++)
@@ -1652,12 +1689,17 @@ struct Engine {
                                 ln.amask |= 1u << m;
                             }
                     } else if (dt != 0.0) {
+                        double nm = SIMB_INF;
+                        uint32_t z = 0;
                         for (uint32_t mm = ln.amask; mm; mm &= mm - 1u) {
                             const uint32_t m = (uint32_t)lowest_bit(mm);
                             const double u = ln.D(net.drow_until + m) - dt;
                             ln.D(net.drow_until + m) = u;
-                            if (u == 0.0) ln.zm |= 1u << m;
+                            if (u == 0.0) z |= 1u << m;
+                            else nm = fmin(nm, u);
                         }
+                        ln.zm = z;
+                        ln.nmin = nm;
                     }
                 }
                 ln.time = ln.time + dt;
@@ -1666,18 +1708,21 @@ struct Engine {
             }
         }
         // ---- one internal event, in model order (:237-268) ----
-        if (act && pg.stage == 2u && pg.zmk && !ln.err) {
+        if (act && pg.stage == 2u && pg.zmk && pg.rel == 0u && !ln.err) {
             const uint32_t m = (uint32_t)lowest_bit(pg.zmk);
-            if (int2<INSTR>(ln, m)) {
+            if (int2<INSTR>(ln, pg, m)) {
                 pg.zmk &= pg.zmk - 1u;
                 pg.nev++;
             } else {
                 pg.flush = true;
             }
         }
+        // ---- one outgoing job of that event ----
+        if (act && pg.rel != 0u && !ln.err) release_one<INSTR>(ln, pg);
         // ---- step end ----
-        if (act && pg.stage == 2u && (pg.zmk == 0u || ln.err)) {
+        if (act && pg.stage == 2u && ((pg.zmk == 0u && pg.rel == 0u) || ln.err)) {
             pg.stage = 0u;
+            pg.rel = 0;
             ln.events += pg.nev;
             if (!ln.err) ln.steps++;
             return true;

@@ -194,6 +194,7 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
         }
         __syncwarp();
         const uint64_t pol = l2_policy_evict_last();
+#pragma unroll 1
         for (uint32_t r = tid; r < n_rows; r += 32) {
             if (r < net.n_drows) {
                 if (la.l2_keep) bulk_g2s_hint(s_d + (size_t)r * tile, st.d + (uint64_t)r * st.stride + base, tile * 8u, bar, pol);
@@ -247,6 +248,13 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
             }
             if (la.lockstep && __ballot_sync(0xFFFFFFFFu, act && !parked) == 0u) parked = false;
         }
+        // last launch of an API call: pay the deferred draws so the stored state is observable as is -- through the
+        // loop's own flush site (one more pass of micro with no lane active)
+        pg.flush = la.settle && !absent && (ln.dm_int | ln.dm_ext) != 0u;
+        if (__ballot_sync(0xFFFFFFFFu, pg.flush) != 0u) {
+            stepped = true;
+            eng.template micro<INSTR>(ln, pg, false);
+        }
     } else {
         for (uint32_t k = 0; k < la.k; k++) {
             const bool live = !done && ln.err == 0;
@@ -257,7 +265,7 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
         }
     }
     // last launch of an API call: pay the deferred draws so the stored state is observable as is
-    if (la.settle && !absent && (ln.dm_int | ln.dm_ext)) {
+    if (SHAPE >= 0 && la.settle && !absent && (ln.dm_int | ln.dm_ext)) {
         eng.flush_draws(ln);
         stepped = true;
     }
@@ -278,6 +286,7 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
     const bool any_stepped = __syncthreads_or(stepped) != 0;
     if (any_stepped && tid < 32) {
         const uint64_t pol = l2_policy_evict_last();
+#pragma unroll 1
         for (uint32_t r = tid; r < n_rows; r += 32) {
             if (r < net.n_drows) {
                 if (la.l2_keep) bulk_s2g_hint(st.d + (uint64_t)r * st.stride + base, s_d + (size_t)r * tile, tile * 8u, pol);
