@@ -85,6 +85,8 @@ struct Tables {
     const double* exp_f;
     const double* norm_x;
     const double* norm_f;
+    const uint32_t* mt;   // generic interpreter: model / route table (actions.h; shared memory on the device)
+    const uint64_t* vt;   // generic interpreter: distribution value table
     uint64_t* rng_cache;  // baked shapes: Philox draw cache, [rng_slots][lane] (shared memory on the device)
     uint32_t rng_slots;   // prefetched draws per replication there (power of two >= 2)
 };
@@ -197,16 +199,16 @@ struct DescP {
     SIMB_HD uint64_t q2() const { return d.q2; }
     SIMB_HD uint32_t dist_err() const { return d.dist_err; }
 };
-// ... or from the value table (generic interpreter: lane-varying model index, read through the L1)
+// ... or from the value table (generic interpreter: lane-varying model index; a copy in shared memory)
 struct TabP {
     const uint64_t* vt;
     uint32_t m, derr;
-    SIMB_HD double p0() const { return bits_f64(SIMB_LDG(vt + m)); }
-    SIMB_HD double p1() const { return bits_f64(SIMB_LDG(vt + SIMB_MAX_MODELS + m)); }
-    SIMB_HD double p2() const { return bits_f64(SIMB_LDG(vt + 2 * SIMB_MAX_MODELS + m)); }
-    SIMB_HD uint64_t q0() const { return SIMB_LDG(vt + 3 * SIMB_MAX_MODELS + m); }
-    SIMB_HD uint64_t q1() const { return SIMB_LDG(vt + 4 * SIMB_MAX_MODELS + m); }
-    SIMB_HD uint64_t q2() const { return SIMB_LDG(vt + 5 * SIMB_MAX_MODELS + m); }
+    SIMB_HD double p0() const { return bits_f64(vt[m]); }
+    SIMB_HD double p1() const { return bits_f64(vt[SIMB_MAX_MODELS + m]); }
+    SIMB_HD double p2() const { return bits_f64(vt[2 * SIMB_MAX_MODELS + m]); }
+    SIMB_HD uint64_t q0() const { return vt[3 * SIMB_MAX_MODELS + m]; }
+    SIMB_HD uint64_t q1() const { return vt[4 * SIMB_MAX_MODELS + m]; }
+    SIMB_HD uint64_t q2() const { return vt[5 * SIMB_MAX_MODELS + m]; }
     SIMB_HD uint32_t dist_err() const { return derr; }
 };
 
@@ -618,7 +620,7 @@ struct Engine {
                 ln.dm_ext &= ln.dm_ext - 1u;
             }
             // parameter errors were raised when the debt was noted (apply_u), so dist_err is 0 here
-            const double dv = sample_continuous_kind(ln, (TF(TF_WTAB, m) >> 16) & 0xFFu, TabP{st.vtab, m, 0u});
+            const double dv = sample_continuous_kind(ln, (TF(TF_WTAB, m) >> 16) & 0xFFu, TabP{tab.vt, m, 0u});
             ln.D(net.drow_until + m) = dv;
             if (dv == 0.0) ln.zm |= 1u << m;  // a variate of exactly zero makes the model imminent at once
             else ln.nmin = fmin(ln.nmin, dv);
@@ -1216,7 +1218,7 @@ struct Engine {
     // path is the same for every model type, so the lanes of a warp stay converged whatever models
     // their replications are serving.
     // ================================================================================================
-    SIMB_HD uint32_t TF(uint32_t field, uint32_t m) const { return SIMB_LDG(st.tab + field * SIMB_MAX_MODELS + m); }
+    SIMB_HD uint32_t TF(uint32_t field, uint32_t m) const { return tab.mt[field * SIMB_MAX_MODELS + m]; }
     SIMB_HD uint32_t ext_lut(uint32_t key) const {
 #if SIMB_ON_DEVICE
         return __ldg(&kExtLutDev.v[key]);
@@ -1271,7 +1273,7 @@ struct Engine {
         }
         double v = 0.0;
         if (ua == UA_INF) v = SIMB_INF;
-        if (ua == UA_P0) v = bits_f64(SIMB_LDG(st.vtab + m));
+        if (ua == UA_P0) v = bits_f64(tab.vt[m]);
         ln.D(net.drow_until + m) = v;
         if (ua == UA_INF) ln.amask &= ~bit;
         else ln.amask |= bit;
@@ -1284,6 +1286,22 @@ struct Engine {
         return true;
     }
 
+    // first i < cnt with ring_w[base + i] == key (cnt if none).  The table lives in global memory: four entries are
+    // requested at once so that a short scan costs one memory round trip instead of one per entry.
+    SIMB_HD uint32_t ring_find(Lane& ln, uint32_t base, uint32_t cnt, uint32_t key) {
+        for (uint32_t b = 0; b < cnt; b += 4u) {
+            const uint32_t v0 = RW(ln, base + b);
+            const uint32_t v1 = b + 1u < cnt ? RW(ln, base + b + 1u) : ~key;
+            const uint32_t v2 = b + 2u < cnt ? RW(ln, base + b + 2u) : ~key;
+            const uint32_t v3 = b + 3u < cnt ? RW(ln, base + b + 3u) : ~key;
+            if (v0 == key) return b;
+            if (v1 == key) return b + 1u;
+            if (v2 == key) return b + 2u;
+            if (v3 == key) return b + 3u;
+        }
+        return cnt;
+    }
+
     // the three models whose events_ext works on a table / draws at arrival
     template <bool INSTR>
     SIMB_HD void ext_special(Lane& ln, uint32_t m, uint32_t sp, uint32_t port, uint32_t content, uint32_t tf,
@@ -1292,7 +1310,7 @@ struct Engine {
         const uint32_t rcap = TF(TF_RING_CAP, m), w0 = TF(TF_RING_W0, m), w1 = TF(TF_RING_W1, m);
         if (sp == XS_SGATE) {  // receive_job stochastic_gate.rs:101-122: Bernoulli draw AT ARRIVAL
             apply_u<true>(ln, m, UA_ZERO);  // (ext2 made sure that no earlier draw of the stream is still owed)
-            const bool pass = sample_bernoulli_p(ln, flags, TabP{st.vtab, m, TF(TF_WTAB, m) >> 24});
+            const bool pass = sample_bernoulli_p(ln, flags, TabP{tab.vt, m, TF(TF_WTAB, m) >> 24});
             if (ln.err) return;
             const uint32_t q = ln.W(wrow);
             const uint32_t head = q >> 16, len = q & 0xFFFFu;
@@ -1314,9 +1332,7 @@ struct Engine {
                 return;
             }
             const uint32_t cnt = ln.W(wrow);
-            uint32_t i = 0;
-            for (; i < cnt; i++)
-                if (RW(ln, w0 + i) == content) break;
+            const uint32_t i = ring_find(ln, w0, cnt, content);
             if (i < cnt) {
                 RW(ln, w1 + i) += 1u;
             } else {
@@ -1338,9 +1354,7 @@ struct Engine {
         const uint32_t rd = TF(TF_RING_D, m), drow = rows >> 16;
         record<INSTR>(ln, m, port == 0 ? ACT_START : ACT_STOP, content);
         const uint32_t cnt = ln.W(wrow);
-        uint32_t i = 0;
-        for (; i < cnt; i++)
-            if (RW(ln, w0 + i) == content) break;
+        const uint32_t i = ring_find(ln, w0, cnt, content);
         const uint32_t mine = port == 0 ? 1u : 2u, other = port == 0 ? 2u : 1u;
         if (i == cnt) {
             if (cnt >= rcap) {
@@ -1436,13 +1450,13 @@ struct Engine {
     // route one outgoing (out-port, content) over every matching connector, in connector order
     template <bool INSTR>
     SIMB_HD void emit2(Lane& ln, uint32_t out_port_abs, uint32_t content) {
-        const uint32_t be = SIMB_LDG(st.tab + SIMB_TAB_ROUTE_BEGIN + out_port_abs);
+        const uint32_t be = tab.mt[SIMB_TAB_ROUTE_BEGIN + out_port_abs];
         for (uint32_t r = be & 0xFFFFu; r < (be >> 16); r++) {
             if (ln.npend >= net.max_pending) {
                 if (!ln.err) ln.err = 32;  // SIMB_ERR_CAPACITY: mailbox overflow
                 return;
             }
-            const uint32_t rw = SIMB_LDG(st.tab + SIMB_TAB_ROUTES + r) | (ln.npend << 24);
+            const uint32_t rw = tab.mt[SIMB_TAB_ROUTES + r] | (ln.npend << 24);
             // keep the mailbox sorted by target model (stable): the order events_ext runs in (mod.rs:203-221)
             uint32_t j = ln.npend;
             while (j > 0u) {
@@ -1506,9 +1520,7 @@ struct Engine {
         if (!BASIC && kind == KI_PG) {  // parallel_gateway.rs:174-182
             const uint32_t w1 = TF(TF_RING_W1, m), n_in = (tf >> 8) & 0xFFu;
             const uint32_t cnt = q;
-            uint32_t i = 0;
-            for (; i < cnt; i++)  // canonical choice: earliest-inserted full collection
-                if (RW(ln, w1 + i) == n_in) break;
+            const uint32_t i = ring_find(ln, w1, cnt, n_in);  // canonical choice: earliest-inserted full collection
             if (i == cnt) {  // passivate
                 apply_u<false>(ln, m, UA_INF);
                 return true;
@@ -1546,7 +1558,7 @@ struct Engine {
             aux = next + 1u;
         } else if (!BASIC && kind == KI_XGW) {  // send_jobs exclusive_gateway.rs:110-134: one draw per firing
             const uint32_t wt = TF(TF_WTAB, m);
-            const uint32_t idx = sample_index_p(ln, flags, TF(TF_OUT, m) >> 16, wt & 0xFFFFu, TabP{st.vtab, m, wt >> 24});
+            const uint32_t idx = sample_index_p(ln, flags, TF(TF_OUT, m) >> 16, wt & 0xFFFFu, TabP{tab.vt, m, wt >> 24});
             if (ln.err) return true;
             if (idx >= n_out) {
                 ln.err = 34;  // flow_paths[idx] out of bounds panics

@@ -376,7 +376,7 @@ int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool inst
     // when that costs no occupancy (the ring slots live in L1 between steps).
     uint32_t tile = 256, best_warps = 0;
     for (uint32_t cand = 256; cand >= 32; cand >>= 1) {
-        const uint32_t smem = smem_plan(net, cand, 0).total;
+        const uint32_t smem = smem_plan(net, cand, 0, true).total;
         if (smem > 227u * 1024u) continue;
         uint32_t ctas = (227u * 1024u) / smem;
         const uint32_t regs = (cand <= 128u && !instrument && rng_kind == 0) ? 96u : 64u;  // narrow-tile variant
@@ -385,7 +385,9 @@ int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool inst
         if (ctas > by_threads) ctas = by_threads;
         if (ctas > 32u) ctas = 32u;
         const uint32_t warps = ctas * cand / 32u;
-        if (warps > best_warps) {
+        // among equals prefer the wider tile (fewer, larger bulk copies) -- except that 128 beats 256: the narrow-tile
+        // instantiation has 96 registers and does not spill (gateway network: 3.7e9 vs 2.8e9 replication-steps/s)
+        if (warps > best_warps || (warps == best_warps && cand == 128u && tile == 256u)) {
             best_warps = warps;
             tile = cand;
         }
@@ -398,11 +400,11 @@ int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool inst
     }
     if (const char* force = getenv("SIMB_TILE")) {  // A/B switch: force the tile width (32..256, power of two)
         const uint32_t t = (uint32_t)atoi(force);
-        if (t >= 32u && t <= 256u && (t & (t - 1u)) == 0u && smem_plan(net, t, 0).total <= 227u * 1024u) tile = t;
+        if (t >= 32u && t <= 256u && (t & (t - 1u)) == 0u && smem_plan(net, t, 0, true).total <= 227u * 1024u) tile = t;
     }
     if (dims->shape >= 0 && tile != SIMB_SHAPE_TILE) dims->shape = -1;  // baked-shape kernels assume the full tile width
     // baked-shape kernels add their Philox draw cache: SIMB_RNG_CACHE draws per replication on fused launches
-    SmemPlan sp = smem_plan(net, tile, dims->shape >= 0 ? SIMB_RNG_CACHE : 0u);
+    SmemPlan sp = smem_plan(net, tile, dims->shape >= 0 ? SIMB_RNG_CACHE : 0u, dims->shape < 0);
     if (sp.total > 227u * 1024u) return (int)cudaErrorInvalidConfiguration;
     dims->tile = tile;
     dims->smem_bytes = sp.total;

@@ -76,10 +76,13 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // shared memory carve-up (all offsets multiples of 16 B): barrier, reduction scratch, ziggurat x tables, then
 // the state tile (f64 rows followed by u32 rows).
 struct SmemPlan {
-    uint32_t off_bar, off_red, off_expx, off_normx, off_rng, off_tiles, stage_bytes, d_bytes, total;
+    uint32_t off_bar, off_red, off_expx, off_normx, off_tab, off_vtab, off_rng, off_tiles, stage_bytes, d_bytes, total;
 };
+// generic interpreter: the model / route table without the connector column (instrumented handles read that one
+// from global memory) and the value table are copied to shared memory at the start of a launch
+#define SIMB_TAB_SMEM_WORDS SIMB_TAB_CONN
 // `rng_slots`: Philox draws cached per replication in shared memory (baked-shape kernels; 0 = none)
-__host__ __device__ inline SmemPlan smem_plan(const SimbNetDesc& net, uint32_t tile, uint32_t rng_slots) {
+__host__ __device__ inline SmemPlan smem_plan(const SimbNetDesc& net, uint32_t tile, uint32_t rng_slots, bool tables) {
     SmemPlan p;
     uint32_t o = 0;
     p.off_bar = o;  // three mbarriers: one per stage + one for the tables
@@ -90,6 +93,12 @@ __host__ __device__ inline SmemPlan smem_plan(const SimbNetDesc& net, uint32_t t
     if (net.uses_exp) o += 2064;
     p.off_normx = o;
     if (net.uses_normal) o += 2064;
+    o = (o + 15u) & ~15u;
+    p.off_tab = o;
+    if (tables) o += SIMB_TAB_SMEM_WORDS * 4u;
+    o = (o + 15u) & ~15u;
+    p.off_vtab = o;
+    if (tables) o += SIMB_VTAB_WORDS * 8u;
     o = (o + 127u) & ~127u;
     p.off_rng = o;
     o += rng_slots * 8u * tile;
@@ -158,7 +167,7 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
     const uint32_t tile = SHAPE >= 0 ? SIMB_SHAPE_TILE : blockDim.x;
     const uint32_t tid = threadIdx.x;
     const uint32_t rng_slots = SHAPE >= 0 ? la.rng_slots : 0u;
-    const SmemPlan sp = smem_plan(net, tile, rng_slots);
+    const SmemPlan sp = smem_plan(net, tile, rng_slots, SHAPE < 0);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + sp.off_bar);
     unsigned long long* s_red = reinterpret_cast<unsigned long long*>(smem + sp.off_red);
     double* s_expx = reinterpret_cast<double*>(smem + sp.off_expx);
@@ -207,6 +216,15 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
         }
     }
     Tables tab;
+    tab.mt = reinterpret_cast<const uint32_t*>(smem + sp.off_tab);
+    tab.vt = reinterpret_cast<const uint64_t*>(smem + sp.off_vtab);
+    if (SHAPE < 0) {  // the tables are written at post / put, long before this launch
+        uint32_t* s_mt = reinterpret_cast<uint32_t*>(smem + sp.off_tab);
+        uint64_t* s_vt = reinterpret_cast<uint64_t*>(smem + sp.off_vtab);
+        for (uint32_t i = tid; i < SIMB_TAB_SMEM_WORDS; i += tile) s_mt[i] = __ldg(st.tab + i);
+        for (uint32_t i = tid; i < SIMB_VTAB_WORDS; i += tile) s_vt[i] = __ldg(st.vtab + i);
+        __syncthreads();
+    }
     tab.exp_x = s_expx;
     tab.exp_f = ZIG_EXP_F;
     tab.norm_x = s_normx;

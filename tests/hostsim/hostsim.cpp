@@ -39,7 +39,7 @@ struct HS {
 template <int RNG, bool INSTR, int SM>
 void run(HS* h, int mode, uint64_t k, double until) {
     uint64_t rng_cache[SIMB_RNG_CACHE];  // one lane at a time: its column is the whole cache (lane stride applies)
-    Tables tab{ZIG_EXP_X, ZIG_EXP_F, ZIG_NORM_X, ZIG_NORM_F, rng_cache, h->rng_slots};
+    Tables tab{ZIG_EXP_X, ZIG_EXP_F, ZIG_NORM_X, ZIG_NORM_F, h->tab.data(), h->vtab.data(), rng_cache, h->rng_slots};
     // SM > 0: the literal-index ("baked shape") code path of the interpreter, structure from the host
     // copy of the baked descriptor, values from the lowered network -- as the specialised kernels do
     Engine<RNG, SM> eng(SM > 0 ? *kShapeHost[h->shape] : h->hn.desc, h->hn.desc, h->st, tab);
