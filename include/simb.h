@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SIMB_ABI_VERSION 1
+#define SIMB_ABI_VERSION 2 /* 2: simb_counters.ring_bytes */
 
 /* ---- status codes: SimulationError variants (sim/src/utils/errors.rs:5-97) keep their names ---- */
 typedef enum simb_status {
@@ -138,6 +138,9 @@ typedef struct simb_counters {
     double kernel_ms;        /* device time of those launches (CUDA events on the handle's stream) */
     uint64_t state_bytes_per_replication; /* bytes of the SoA state tile one launch loads (= stores) */
     uint64_t failed;         /* replications holding a sticky error */
+    uint64_t ring_bytes;     /* bytes of queue / table slots (and mailbox overflow) the step kernels touched in
+                                global memory since the last simb_reset_counters: counted on the device, the
+                                second term of a launch's algorithmic bytes next to 2 x state bytes */
 } simb_counters;
 
 /* SteadyStateOutput of one replication (sim/src/output_analysis/mod.rs:205-345) */

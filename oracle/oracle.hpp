@@ -164,6 +164,7 @@ struct Tracer {
     bool enabled = false, store = false;
     uint64_t hash = 0xcbf29ce484222325ull;
     uint64_t count = 0;
+    uint64_t record_count[32 * 14] = {0};  // [model][action]: would-be ModelRecords (test instrumentation)
     std::vector<TraceEvent> events;
     std::vector<std::string> names;  // prefix / literal intern table
     uint32_t intern(const std::string& s);

@@ -404,11 +404,27 @@ void orc_zig_table(int which, double out[257]) {
 // Per-replication outputs (any pointer may be null): final global time, trace hash, steps,
 // events (ext+int), waiting-time sum / count of `stat_model_id` (needs store_records on it).
 // totals[0..2] = steps, ext events, int events over all replications.
+// out_conn[n_connectors] / out_records[n_models][14]: totals over the batch of routed messages per connector and of
+// would-be ModelRecords per (model, action) (trace_hash must be on for the latter).
+int orc_run_batch_counts(void* hv, uint64_t seed, uint64_t rep0, uint64_t nreps, int threads, int mode, double until,
+                         uint64_t nsteps, const char* stat_model_id, int trace_hash, uint64_t* totals, double* out_time,
+                         uint64_t* out_hash, uint64_t* out_steps, uint64_t* out_events, double* out_wait_sum,
+                         uint64_t* out_wait_n, uint64_t* out_conn, uint64_t* out_records);
 int orc_run_batch(void* hv, uint64_t seed, uint64_t rep0, uint64_t nreps, int threads, int mode, double until,
                   uint64_t nsteps, const char* stat_model_id, int trace_hash, uint64_t* totals, double* out_time,
                   uint64_t* out_hash, uint64_t* out_steps, uint64_t* out_events, double* out_wait_sum,
                   uint64_t* out_wait_n) {
+    return orc_run_batch_counts(hv, seed, rep0, nreps, threads, mode, until, nsteps, stat_model_id, trace_hash, totals,
+                                out_time, out_hash, out_steps, out_events, out_wait_sum, out_wait_n, nullptr, nullptr);
+}
+int orc_run_batch_counts(void* hv, uint64_t seed, uint64_t rep0, uint64_t nreps, int threads, int mode, double until,
+                         uint64_t nsteps, const char* stat_model_id, int trace_hash, uint64_t* totals, double* out_time,
+                         uint64_t* out_hash, uint64_t* out_steps, uint64_t* out_events, double* out_wait_sum,
+                         uint64_t* out_wait_n, uint64_t* out_conn, uint64_t* out_records) {
     Handle* h = (Handle*)hv;
+    const size_t n_conn = h->staged_connectors.size(), n_mod = h->staged_models.size();
+    std::vector<uint64_t> conn_t((size_t)(threads < 1 ? 1 : threads) * (n_conn + 1), 0);
+    std::vector<uint64_t> rec_t((size_t)(threads < 1 ? 1 : threads) * 32 * 14, 0);
     if (threads < 1) threads = 1;
     std::atomic<uint64_t> next{0};
     std::atomic<int> first_err{0};
@@ -434,6 +450,9 @@ int orc_run_batch(void* hv, uint64_t seed, uint64_t rep0, uint64_t nreps, int th
                 tot[3 * t + 0] += sim.n_steps;
                 tot[3 * t + 1] += sim.n_ext;
                 tot[3 * t + 2] += sim.n_int;
+                for (size_t c = 0; c < n_conn && c < sim.connector_messages.size(); c++)
+                    conn_t[(size_t)t * (n_conn + 1) + c] += sim.connector_messages[c];
+                for (size_t k = 0; k < 32 * 14; k++) rec_t[(size_t)t * 32 * 14 + k] += sim.tracer.record_count[k];
                 if (out_time) out_time[i] = sim.services.global_time;
                 if (out_hash) out_hash[i] = sim.tracer.hash;
                 if (out_steps) out_steps[i] = sim.n_steps;
@@ -458,6 +477,17 @@ int orc_run_batch(void* hv, uint64_t seed, uint64_t rep0, uint64_t nreps, int th
         for (int t = 0; t < threads; t++)
             for (int k = 0; k < 3; k++) totals[k] += tot[3 * t + k];
     }
+    if (out_conn)
+        for (size_t c = 0; c < n_conn; c++) {
+            out_conn[c] = 0;
+            for (int t = 0; t < threads; t++) out_conn[c] += conn_t[(size_t)t * (n_conn + 1) + c];
+        }
+    if (out_records)
+        for (size_t m = 0; m < n_mod && m < 32; m++)
+            for (size_t a = 0; a < 14; a++) {
+                out_records[m * 14 + a] = 0;
+                for (int t = 0; t < threads; t++) out_records[m * 14 + a] += rec_t[(size_t)t * 32 * 14 + m * 14 + a];
+            }
     return first_err.load();
 }
 

@@ -199,7 +199,7 @@ int build_device(simb_sim* s, uint32_t keep_mask, const simb_sim* old) {
         st.series_cap = s->cfg.series_capacity;
         if ((r = dev_alloc(s->stream, &st.series, (size_t)st.series_cap * stride, false))) return r;
     }
-    if ((r = dev_alloc(s->stream, &st.totals, 4, true))) return r;
+    if ((r = dev_alloc(s->stream, &st.totals, 5, true))) return r;
     if ((r = upload_tables(s))) return r;
     if ((r = dev_alloc(s->stream, &s->d_dinit, net.n_drows, false))) return r;
     if ((r = dev_alloc(s->stream, &s->d_winit, net.n_wrows, false))) return r;
@@ -786,6 +786,8 @@ int simb_get_counters(simb_sim* s, simb_counters* out) {
     uint32_t nb = 0;
     CUDA_TRY(engine_launch_reduce(net, s->st, 2, 0.0, s->d_psum, s->d_pcnt, &nb, s->stream));
     std::vector<unsigned long long> a(nb), b(nb);
+    unsigned long long ring_bytes = 0;
+    CUDA_TRY(cudaMemcpyAsync(&ring_bytes, s->st.totals + 4, 8, cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaMemcpyAsync(a.data(), s->d_psum, nb * 8, cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaMemcpyAsync(b.data(), s->d_pcnt, nb * 8, cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -797,6 +799,7 @@ int simb_get_counters(simb_sim* s, simb_counters* out) {
     out->launches = s->launches;
     out->kernel_ms = s->kernel_ms;
     out->state_bytes_per_replication = (uint64_t)net.n_drows * 8 + (uint64_t)net.n_wrows * 4;
+    out->ring_bytes = ring_bytes;
     std::vector<uint32_t> ctl(s->st.n);
     CUDA_TRY(cudaMemcpy(ctl.data(), s->st.w + (uint64_t)net.wrow_ctl * s->st.stride, s->st.n * 4, cudaMemcpyDeviceToHost));
     for (uint64_t r = 0; r < s->st.n; r++) out->failed += CTL_ERR(ctl[r]) ? 1 : 0;
@@ -806,6 +809,9 @@ int simb_reset_counters(simb_sim* s) {
     if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");
     s->launches = 0;
     s->kernel_ms = 0.0;
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    CUDA_TRY(cudaMemsetAsync(s->st.totals + 4, 0, sizeof(unsigned long long), s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
     return 0;
 }
 

@@ -118,6 +118,8 @@ struct Lane {
     uint32_t dm_int, dm_ext;  // deferred continuous draws: "until_next_event[m] = sample(dist[m])" still
                               // owed from the previous internal phase / this external phase
     uint32_t traced;
+    uint32_t rb;  // bytes of queue / table slots (and mailbox overflow) this lane touched in global memory in this
+                  // launch: the counted part of the launch's algorithmic bytes (simb_counters.ring_bytes)
     // generic interpreter: models whose until_next_event is not +INF / is exactly 0.0 (kept in step with every
     // write of an until_next_event row, so the time advance and the imminent-model scan visit those only)
     uint32_t amask, zm;
@@ -290,14 +292,21 @@ struct Engine {
     }
 
     // queue / table storage in global memory, [slot][replication]
-    SIMB_HD uint32_t& RW(Lane& ln, uint32_t slot) { return st.ring_w[(uint64_t)slot * st.stride + ln.rep]; }
-    SIMB_HD double& RD(Lane& ln, uint32_t slot) { return st.ring_d[(uint64_t)slot * st.stride + ln.rep]; }
+    SIMB_HD uint32_t& RW(Lane& ln, uint32_t slot) {
+        ln.rb += 4u;
+        return st.ring_w[(uint64_t)slot * st.stride + ln.rep];
+    }
+    SIMB_HD double& RD(Lane& ln, uint32_t slot) {
+        ln.rb += 8u;
+        return st.ring_d[(uint64_t)slot * st.stride + ln.rep];
+    }
 
     // mailbox slot j: word 0 = content, word 1 = route.  The first net.pend_tile slots are rows of the
     // state tile (shared memory); deeper slots -- reached only by rare bursts -- stay in global memory.
     SIMB_HD uint32_t& mail_word(Lane& ln, uint32_t j, uint32_t which) {
         // no overflow area when the whole mailbox fits the tile (folds away for baked shapes)
         if (net.pend_tile == net.max_pending || j < net.pend_tile) return ln.W(net.wrow_pend + 2u * j + which);
+        ln.rb += 4u;
         return st.mail[(uint64_t)(2u * (j - net.pend_tile) + which) * st.stride + ln.rep];
     }
 
@@ -770,6 +779,7 @@ struct Engine {
         ln.c0 = ln.c1 = ln.c2 = 0;
         ln.ccount = 0;
         ln.traced = instr && ln.rep < st.trace_reps;
+        ln.rb = 0;
         ln.dm_int = ln.W(net.wrow_dmask);
         ln.dm_ext = 0;
         ln.tmask = 0;

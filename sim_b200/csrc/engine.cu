@@ -301,7 +301,7 @@ StepKernel simb_generic_rare_kernel(int rng_kind, bool instrument, bool narrow);
 // variant: baked shape -> streaming launch; generic -> narrow tile (see step_kernel.cuh)
 static StepKernel pick_kernel(int rng_kind, bool instrument, int shape, bool stream = false, bool rare = true,
                               bool narrow = false, bool basic = false) {
-    if (!instrument && rng_kind == 0) {  // baked shapes exist for the production configuration only
+    if (rng_kind == 0) {  // baked shapes exist for Philox streams only (engine_match_shape pairs the instrument flag)
         switch (shape) {
             case 0: return stream ? simb_shape_stream_kernel_0() : simb_shape_kernel_0();
             case 1: return stream ? simb_shape_stream_kernel_1() : simb_shape_kernel_1();
@@ -349,14 +349,16 @@ static void strip_values(SimbNetDesc* d) {
     memset(d->wcum, 0, sizeof d->wcum);
 }
 int engine_match_shape(const SimbNetDesc& net, int rng_kind, bool instrument) {
-    if (instrument || rng_kind != 0) return -1;
+    if (rng_kind != 0) return -1;
     const char* off = getenv("SIMB_NO_SHAPES");  // A/B switch: a non-empty value forces the generic interpreter
     if (off && *off) return -1;
     static_assert(SIMB_N_SHAPES <= 4, "extend shape_desc<> / pick_kernel / the Makefile for more baked shapes");
     SimbNetDesc a;
     memcpy(&a, &net, sizeof a);
     strip_values(&a);
+    static const int shape_is_instr[] = SIMB_SHAPE_INSTR;
     for (int i = 0; i < SIMB_N_SHAPES; i++) {
+        if ((shape_is_instr[i] != 0) != instrument) continue;
         SimbNetDesc b;
         memcpy(&b, kShapeHost[i], sizeof b);
         strip_values(&b);
@@ -393,6 +395,7 @@ int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool inst
         }
     }
     if (best_warps == 0) return (int)cudaErrorInvalidConfiguration;
+    if (dims->shape >= 0) tile = SIMB_SHAPE_TILE;  // a baked shape's kernel is compiled for the full tile width
     if (n && n < tile) {
         uint32_t t = 32;
         while (t < n) t <<= 1;

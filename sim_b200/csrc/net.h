@@ -170,7 +170,7 @@ struct SimbDevState {
     uint32_t* trace_count;        // [trace_reps]
     unsigned long long* conn_count;    // [n_connectors]        (instrumented)
     unsigned long long* record_count;  // [n_models][ACT_COUNT] (instrumented)
-    unsigned long long* totals;        // [4]: steps, events, still-active replications, failed
+    unsigned long long* totals;        // [5]: steps, events, still-active replications, failed, ring bytes touched
     double* series;       // waiting-time series of the MF_STAT processor, [series_cap][stride], or null
     uint32_t series_cap;  // samples kept per replication (simb_config.series_capacity)
     uint32_t reserved;

@@ -26,11 +26,12 @@ static void pd(double v) {
 
 int main(int argc, char** argv) {
     if (argc < 3) {
-        std::fprintf(stderr, "usage: shape_dump models.json connectors.json [stat_model_id]\n");
+        std::fprintf(stderr, "usage: shape_dump models.json connectors.json [stat_model_id|-] [instr]\n");
         return 2;
     }
     LowerOptions opt;
-    if (argc > 3) opt.stat_model_id = argv[3];
+    if (argc > 3 && std::strcmp(argv[3], "-") != 0) opt.stat_model_id = argv[3];
+    if (argc > 4 && std::strcmp(argv[4], "instr") == 0) opt.instrument = true;
     HostNet hn;
     std::string err;
     int e = lower_network(slurp(argv[1]).c_str(), slurp(argv[2]).c_str(), opt, &hn, &err);

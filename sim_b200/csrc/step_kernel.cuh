@@ -149,6 +149,12 @@ __host__ __device__ constexpr int shape_tier() {  // model-count tier of a baked
     return SHAPE < 0 ? 0 : tiers[SHAPE < 0 ? 0 : SHAPE];
 }
 
+template <int SHAPE>
+__host__ __device__ constexpr bool shape_instr() {  // baked shape lowered for an instrumented handle
+    constexpr int flags[] = SIMB_SHAPE_INSTR;
+    return SHAPE < 0 ? false : flags[SHAPE < 0 ? 0 : SHAPE] != 0;
+}
+
 // One CTA = one tile of blockDim.x consecutive replications.  Kernels of baked shapes are only launched
 // with SIMB_SHAPE_TILE threads, so their shared-memory row offsets are immediates.
 #define SIMB_SHAPE_TILE 256u
@@ -182,6 +188,7 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
         mbar_init(bar, 1);
         s_red[0] = 0ull;
         s_red[1] = 0ull;
+        s_red[2] = 0ull;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();  // make the barrier init visible to the async proxy
     }
@@ -293,6 +300,10 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
         eng.lane_store(ln, INSTR, (la.mode == 1 && done) ? la.epoch : 0u, absent ? 1u : 0u);
         fence_proxy_async();  // generic-proxy writes -> visible to the bulk (async proxy) stores
     }
+    {  // queue / table bytes this launch touched in global memory (the counted term of the algorithmic bytes)
+        const uint32_t wsum = __reduce_add_sync(0xFFFFFFFFu, ln.rb);
+        if ((tid & 31u) == 0 && wsum) atomicAdd(&s_red[2], (unsigned long long)wsum);
+    }
     if (count_active) {
         const uint32_t act = __popc(__ballot_sync(0xFFFFFFFFu, !done && ln.err == 0));
         const uint32_t bad = __popc(__ballot_sync(0xFFFFFFFFu, !absent && ln.err != 0));
@@ -318,6 +329,7 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
         bulk_commit();
         bulk_wait_read_all();  // the stores must have read shared memory before the CTA exits
     }
+    if (tid == 0 && s_red[2]) atomicAdd(&st.totals[4], s_red[2]);
     if (count_active && tid == 0) {
         if (s_red[0]) atomicAdd(&st.totals[2], s_red[0]);
         if (s_red[1]) atomicAdd(&st.totals[3], s_red[1]);

@@ -60,7 +60,7 @@ class _TraceEvent(C.Structure):
 
 class _Counters(C.Structure):
     _fields_ = [("steps", C.c_uint64), ("events", C.c_uint64), ("launches", C.c_uint64), ("kernel_ms", C.c_double),
-                ("state_bytes_per_replication", C.c_uint64), ("failed", C.c_uint64)]
+                ("state_bytes_per_replication", C.c_uint64), ("failed", C.c_uint64), ("ring_bytes", C.c_uint64)]
 
 
 class _SteadyState(C.Structure):

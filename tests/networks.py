@@ -320,13 +320,15 @@ def tandem():
 
 
 def gateway_network():
-    """config 4 (16 models): generator Exp(2) -> parallel split (1->3) -> {processor Exp; stochastic gate p=.9 ->
-    processor Normal(1,.1); exclusive [6,3,1] -> 3 processors -> (merge)} ... -> batcher(10,10) -> storage, with a
-    stopwatch across the network and a gate on the exclusive branch."""
+    """config 4 (16 models, SURVEY.md 8(d)): generator Exp(2) -> parallel split (1 -> 4) -> {processor Exp;
+    stochastic gate p=.9 -> processor Normal; exclusive [6,3,1] -> 3 processors, with a gate on that branch} and a
+    parallel JOIN (2 -> 1) of the split's fourth output with the first branch's departures, upstream of the
+    batcher(10, 10) -> storage; a stopwatch across the first branch.  The join collects every job twice (at the
+    split and when proc-p releases it), so exactly one collection fills per departure (App. F)."""
     T = ContinuousRandomVariable
     models = [
         Model.new("generator", Generator.new(Exp(2.0), None, "job", False, None)),
-        Model.new("split", ParallelGateway.new(["in"], ["p", "q", "r"], False)),
+        Model.new("split", ParallelGateway.new(["in"], ["p", "q", "r", "j"], False)),
         Model.new("proc-p", Processor.new(Exp(4.0), None, "job", "done", False, None)),
         Model.new("sgate-q", StochasticGate.new(BooleanRandomVariable.Bernoulli(0.9), "job", "job", False, None)),
         Model.new("proc-q", Processor.new(T.Normal(0.25, 0.02), 16, "job", "done", False, None)),
@@ -336,7 +338,7 @@ def gateway_network():
         Model.new("proc-y", Processor.new(T.Triangular(0.1, 0.5, 0.2), 16, "job", "done", False, None)),
         Model.new("proc-z", Processor.new(T.Uniform(0.1, 0.4), 16, "job", "done", False, None)),
         Model.new("gate-r", Gate.new("job", "activation", "deactivation", "job", False)),
-        Model.new("lb", LoadBalancer.new("job", ["one", "two"], False)),
+        Model.new("join", ParallelGateway.new(["early", "late"], ["out"], False)),
         Model.new("batcher", Batcher.new("job", "job", 10.0, 10, False)),
         Model.new("stopwatch", Stopwatch.new("start", "stop", "metric", "job", Metric.Minimum, False)),
         _storage("storage-p"), _storage("storage-q"), _storage("storage-r"),
@@ -351,10 +353,10 @@ def gateway_network():
         C("c06", "proc-p", "storage-p", "done", "store"),
         C("c07", "proc-p", "stopwatch", "done", "stop"),
         C("c08", "sgate-q", "proc-q", "job", "job"),
-        C("c09", "proc-q", "lb", "done", "job"),
-        C("c10", "lb", "batcher", "one", "job"),
-        C("c11", "lb", "storage-q", "two", "store"),
-        C("c12", "batcher", "storage-q", "job", "store"),
+        C("c09", "proc-q", "storage-q", "done", "store"),
+        C("c10", "split", "join", "j", "early"),
+        C("c11", "proc-p", "join", "done", "late"),
+        C("c12", "join", "batcher", "out", "job"),
         C("c13", "xgw-r", "proc-x", "x", "job"),
         C("c14", "xgw-r", "proc-y", "y", "job"),
         C("c15", "xgw-r", "proc-z", "z", "job"),
@@ -363,6 +365,7 @@ def gateway_network():
         C("c18", "proc-z", "gate-r", "done", "deactivation"),
         C("c19", "proc-y", "storage-r", "done", "store"),
         C("c20", "gate-r", "storage-r", "job", "store"),
+        C("c21", "batcher", "storage-q", "job", "store"),
     ]
     return models, connectors
 
@@ -391,8 +394,9 @@ def large_mixed():
                                             c.target_port))
 
     g_models, g_conn = gateway_network()
-    # trim each gateway sub-network to 11 models: drop the three storages and the stopwatch (and their connectors)
-    drop = {"storage-p", "storage-q", "stopwatch", "lb"}
+    # trim each gateway sub-network to 11 models: drop the three storages and the stopwatch (and their connectors);
+    # split -> ... -> join -> batcher stays whole
+    drop = {"storage-p", "storage-q", "storage-r", "stopwatch"}
     gm = [m for m in g_models if m.id not in drop]
     gc = [c for c in g_conn if c.source_id not in drop and c.target_id not in drop]
     sub("a/", gm, gc, "g1", "split", "in")

@@ -259,13 +259,16 @@ class OracleSimulation:
         ws = np.zeros(nreps, np.float64)
         wn = np.zeros(nreps, np.uint64)
         tot = (C.c_uint64 * 3)()
+        conn = np.zeros(max(1, len(self.connectors)), np.uint64)
+        recs = np.zeros((len(self.models), 14), np.uint64)
         p = lambda a, ty: a.ctypes.data_as(C.POINTER(ty))
-        e = self.L.orc_run_batch(self.h, C.c_uint64(seed), C.c_uint64(rep0), C.c_uint64(nreps), int(threads),
+        e = self.L.orc_run_batch_counts(self.h, C.c_uint64(seed), C.c_uint64(rep0), C.c_uint64(nreps), int(threads),
                                  0 if until is not None else 1, C.c_double(until or 0.0), C.c_uint64(nsteps or 0),
                                  _b(stat_model_id) if stat_model_id else None, int(trace_hash), tot,
                                  p(t, C.c_double), p(hsh, C.c_uint64), p(st, C.c_uint64), p(ev, C.c_uint64),
-                                 p(ws, C.c_double), p(wn, C.c_uint64))
+                                 p(ws, C.c_double), p(wn, C.c_uint64), p(conn, C.c_uint64), p(recs, C.c_uint64))
         return dict(err=e, time=t, hash=hsh, steps=st, events=ev, wait_sum=ws, wait_n=wn,
+                    conn=conn[:len(self.connectors)], records=recs,
                     totals=dict(steps=tot[0], ext=tot[1], int=tot[2]))
 
 

@@ -22,13 +22,13 @@ def test_exports_every_declared_symbol():
     lib = C.CDLL(os.path.join(ROOT, "sim_b200", "libsimb200.so"))
     missing = [n for n in sorted(names) if not hasattr(lib, n)]
     assert not missing, missing
-    assert lib.simb_abi_version() == 1
+    assert lib.simb_abi_version() == 2
 
 
 def test_struct_layout_matches_header():
     from sim_b200.simulator import SimbConfig, _CI, _Counters, _Message, _Record, _TraceEvent
     assert C.sizeof(SimbConfig) == 88 and C.sizeof(_Message) == 248 and C.sizeof(_Record) == 136
-    assert C.sizeof(_TraceEvent) == 24 and C.sizeof(_Counters) == 48 and C.sizeof(_CI) == 40
+    assert C.sizeof(_TraceEvent) == 24 and C.sizeof(_Counters) == 56 and C.sizeof(_CI) == 40
 
 
 def test_host_only_entry_points():

@@ -3,6 +3,8 @@ oracle on identical per-replication uniform streams.  Discrete results (event or
 record counts, step / event / draw counts) must match bit-exactly -- they are compared through the
 per-replication trace hash and, for traced replications, event by event -- and f64 clocks within
 1e-12 relative (north_star)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -237,10 +239,22 @@ def test_production_kernels_match_oracle(name, stat, shape, k):
     if stat:
         s, cnt = sim.get_wait_stats()
         assert (cnt == ref["wait_n"]).all() and _close(s, ref["wait_sum"])
+    # the instrumented handle of a baked shape runs the SAME specialised code path with the trace compiled in
     gen = _sim(models, conns, n, seed=5, instrument=True, stat_model_id=stat, steps_per_launch=k)
-    assert gen.describe()["kernel_shape"] == "generic"
+    assert gen.describe()["kernel_shape"] == (shape + "_instr" if shape != "generic" else "generic")
     gen.step_until(until)
     assert (gen.get_trace_hash() == ref["hash"]).all()
+    if shape != "generic":  # ... and agrees with the generic interpreter's trace, message and record counts
+        os.environ["SIMB_NO_SHAPES"] = "1"
+        try:
+            itp = _sim(models, conns, n, seed=5, instrument=True, stat_model_id=stat, steps_per_launch=k)
+        finally:
+            del os.environ["SIMB_NO_SHAPES"]
+        assert itp.describe()["kernel_shape"] == "generic"
+        itp.step_until(until)
+        assert (itp.get_trace_hash() == gen.get_trace_hash()).all()
+        assert (itp.get_message_counts() == gen.get_message_counts()).all()
+        assert (itp.get_record_counts() == gen.get_record_counts()).all()
     assert (gen.get_draws() == sim.get_draws()).all()
     for m in models:
         assert _close(gen.get_until_next_event(m.id), sim.get_until_next_event(m.id)), m.id
@@ -315,6 +329,50 @@ def test_full_size_sampled_replications_match_oracle(full_mm1):
         assert (steps[sl] == ref["steps"]).all() and (events[sl] == ref["events"]).all()
         assert (cnt[sl] == ref["wait_n"]).all()
         assert _close(t[sl], ref["time"]) and _close(s[sl], ref["wait_sum"])
+
+
+@pytest.mark.parametrize("stat", ["processor-01", None])
+def test_full_size_baked_kernel_trace(full_mm1, stat):
+    """north_star test 1 for the kernel that produces the headline number: the baked M/M/1 code path with the trace
+    compiled in (shapes mm1_instr / mm1_plain_instr: the same template instantiation plus record<> / emit<>
+    instrumentation) at 2^20 replications over the full horizon.  Event order (per-replication FNV trace hash),
+    per-connector message counts and per-(model, action) record counts against the oracle on replications sampled
+    across the batch; totals against the identities of the M/M/1 cadence; and the production (uninstrumented)
+    kernel agrees with it in everything it can observe on all 2^20 replications."""
+    models, conns = networks.mm1()
+    sim = _sim(models, conns, FULL_N, seed=42, instrument=True, stat_model_id=stat, trace_replications=0)
+    assert sim.describe()["kernel_shape"] == ("mm1_instr" if stat else "mm1_plain_instr")
+    sim.step_until(FULL_UNTIL)
+    assert (sim.get_errors() == 0).all()
+    h, steps, events = sim.get_trace_hash(), sim.get_steps(), sim.get_events()
+    rec_models, _ = networks.mm1(store_records=True)
+    o = oracle_api.OracleSimulation(rec_models, conns)
+    for r0 in (0, 255, 256, 65535, 300001, 524288, 777777, FULL_N - 4):
+        ref = o.run_batch(42, r0, 4, threads=4, until=FULL_UNTIL, stat_model_id=stat)
+        sl = slice(r0, r0 + 4)
+        assert (h[sl] == ref["hash"]).all() and (steps[sl] == ref["steps"]).all() and (events[sl] == ref["events"]).all()
+    # message / record totals over the batch: exact identities of this network (generator.rs:98-123,
+    # processor.rs:119-196, storage.rs:106-113)
+    mc = sim.get_message_counts()
+    rc = sim.get_record_counts().reshape(len(models), -1)
+    A = {n: i for i, n in enumerate(("Initialization", "Generation", "Arrival", "Processing Start", "Drop", "Departure"))}
+    assert rc[0, A["Initialization"]] == FULL_N and rc[0, A["Generation"]] == mc[0]        # one message per generated job
+    # every job arrives or is dropped, processed jobs reach the storage -- up to the one message a replication
+    # may hold in flight when it crosses the horizon
+    assert 0 <= int(mc[0]) - int(rc[1, A["Arrival"]] + rc[1, A["Drop"]]) <= FULL_N
+    assert rc[1, A["Departure"]] == mc[1] and 0 <= int(mc[1]) - int(rc[2, A["Arrival"]]) <= FULL_N
+    assert 0 <= rc[1, A["Processing Start"]] - rc[1, A["Departure"]] <= FULL_N             # at most one job in service each
+    # the oracle's totals on a contiguous block agree with a second instrumented handle posted on that block
+    blk = _sim(models, conns, 512, seed=42, instrument=True, stat_model_id=stat, replication_offset=4096)
+    blk.step_until(FULL_UNTIL)
+    ref = o.run_batch(42, 4096, 512, threads=8, until=FULL_UNTIL, stat_model_id=stat)
+    assert (blk.get_trace_hash() == ref["hash"]).all() and (blk.get_trace_hash() == h[4096:4608]).all()
+    assert (blk.get_message_counts() == np.array(ref["conn"], np.uint64)).all()
+    assert (np.asarray(blk.get_record_counts()).reshape(-1) == np.array(ref["records"], np.uint64).reshape(-1)).all()
+    if stat:  # the production kernel of the headline bench (fixture) saw the same replications
+        assert np.array_equal(full_mm1.get_steps(), steps) and np.array_equal(full_mm1.get_events(), events)
+        assert np.array_equal(full_mm1.get_global_time(), sim.get_global_time())
+        assert np.array_equal(full_mm1.get_draws(), sim.get_draws())
 
 
 def test_full_size_statistic_and_sharding_invariance(full_mm1):

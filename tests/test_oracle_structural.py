@@ -252,3 +252,19 @@ def test_all_passive_network_goes_to_infinity():
     assert sim.step()[0] == 0
     assert sim.get_global_time() == float("inf")
     assert np.isnan(sim.until_next_event("storage-01"))
+
+
+def test_gateway_network_join_fires_once_per_departure():
+    """BASELINE config 4 as benchmarked: the ParallelGateway JOIN upstream of the batcher completes
+    one collection per proc-p departure (parallel_gateway.rs:100-143), and the batcher releases in tens."""
+    models, conns = networks.gateway_network()
+    o = O.OracleSimulation(models, conns)
+    o.set_rng_philox(42, 0)
+    e, _ = o.step_n(20000, collect=False)
+    assert e == 0
+    per = dict(zip([c.id for c in conns], o.connector_messages()))
+    assert per["c10"] > 100 and per["c11"] > 100
+    assert per["c10"] == per["c03"]            # every job of the split reaches the join early ...
+    assert per["c11"] == per["c06"]            # ... and late, when proc-p releases it
+    assert per["c12"] == per["c11"]            # one full collection per departure -> one job to the batcher
+    assert 0 < per["c21"] <= per["c12"]        # released by the batcher in tens (or on its timer)
