@@ -13,6 +13,14 @@ replications (Simulation::reset + put) and run step_until(T) on every replicatio
   python bench.py --gpus N --steps K --warmup W            # this engine (one rank per GPU under torchrun)
   python bench.py --impl reference --gpus N --steps K ...  # the CPU path (oracle port) on the host cores
 
+Besides the headline (weak scaling: 2^20 M/M/1 replications per GPU) the same line carries
+  hbm_streaming_k1  one Simulation::step per launch at 2^20 (state 101 MB: L2-assisted) and 2^22 replications
+                    (403 MB: streams from HBM), algorithmic GB/s beside the ncu-measured DRAM GB/s,
+  configs           BASELINE configs[2..4] at their named sizes (tandem 2^22, gateway network 2^20, the 32-model
+                    network 2^23 per GPU) with a bounded horizon each,
+  strong_scaling    fixed-total jobs split over the ranks: configs[4] with 2^26 replications in total and
+                    M/M/1 with 2^20 in total.
+
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions of `roofline`,
 `cpu_baseline` and `e2e`.
 """
@@ -28,8 +36,21 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-METRIC = "simulated events/sec (replications x events), M/M/1 batched step_until(10000)"
 UNIT = "events/s"
+WORKLOADS = {
+    "mm1": "M/M/1 batched (BASELINE configs[1]): Generator Exp(0.5) -> Processor Exp(0.333333) cap 14 -> Storage",
+    "tandem": "Tandem 3-stage queue (BASELINE configs[2]): Generator -> LoadBalancer -> 3 x Processor cap 8 -> Processor "
+              "-> Processor -> Storage, steady-state batch means of the last stage",
+    "gateway_network": "Gateway network (BASELINE configs[3]): 16-model DAG with ExclusiveGateway, ParallelGateway split "
+                       "and join, StochasticGate, Gate, Batcher, Stopwatch",
+    "large_mixed": "Large mixed network (BASELINE configs[4]): 32 models, two gateway sub-networks and the tandem behind one split",
+}
+
+
+def metric_name(network, until):
+    short = {"mm1": "M/M/1 batched", "tandem": "tandem queue", "gateway_network": "gateway network",
+             "large_mixed": "32-model mixed network"}.get(network, network)
+    return "simulated events/sec (replications x events), %s step_until(%g)" % (short, until)
 
 
 def parse():
@@ -46,13 +67,17 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-k1", action="store_true", help="skip the one-step-per-launch (HBM streaming) section")
+    p.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configurations")
+    p.add_argument("--no-strong", action="store_true", help="skip the fixed-total (strong scaling) jobs")
+    p.add_argument("--strong-total-log2", type=int, default=26, help="replications of the fixed-total configs[4] job (log2)")
+    p.add_argument("--sub-batch-log2", type=int, default=23, help="largest shard of the 32-model network posted at once (log2)")
     return p.parse_args()
 
 
 def workload(name):
     import networks
     models, conns = networks.ALL[name]()
-    stat = {"mm1": "processor-01", "tandem": "processor-3"}.get(name)
+    stat = {"mm1": "processor-01", "tandem": "processor-3"}.get(name)  # waiting-time statistic of that Processor
     return models, conns, stat
 
 
@@ -126,6 +151,14 @@ def cpu_sample(args, threads, nreps):
     return ev, dt, r["totals"]["steps"]
 
 
+def job_config(network, replications_per_gpu, until):
+    """The `config` object of the JSON line: what the job IS (identical in both arms; how each arm runs it is
+    described in `engine` / `cpu_baseline.sample`)."""
+    return {"workload": WORKLOADS.get(network, network), "replications_per_gpu": replications_per_gpu, "until": until,
+            "rng": "philox4x32-10, key = (global replication index, seed 42)",
+            "parallelism": "independent replications, contiguous index blocks per GPU, no data-path collective"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  The Rust engine cannot be
     built in this image (no cargo/rustc), so this times the C++ oracle port with every host thread,
@@ -147,13 +180,12 @@ def run_reference(args):
     v = tot_ev / tot_dt
     sample = "%d replications x step_until(%g) per step, %d threads" % (nreps, args.until, cores)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(args.network, args.until), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_dt / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "M/M/1 batched (BASELINE configs[1]): Generator Exp(0.5) -> Processor Exp(0.333333) cap 14 -> Storage"
-                   if args.network == "mm1" else args.network,
-                   "replications_per_step": nreps, "until": args.until, "sample": sample,
-                   "implementation": "C++ oracle port of the reference engine (the Rust crate cannot be built in this image)"},
+        "config": job_config(args.network, args.replications, args.until),
+        "implementation": "C++ oracle port of the reference engine (the Rust crate cannot be built in this image); "
+                          "each step is a bounded sample of the job: " + sample,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -164,7 +196,7 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
-    import numpy as np
+    import numpy as np  # noqa: F401
     import torch
     import torch.distributed as dist
 
@@ -186,12 +218,63 @@ def main():
     sim = Simulation.post_json(mj, cj, n, seed=42, replication_offset=rank * n, device=local_rank,
                                steps_per_launch=args.k, stat_model_id=stat)
     desc = sim.describe()
+    peak, peak_src = peaks()
+    ncu = {}
+    ncu_path = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(ncu_path):
+        with open(ncu_path) as f:
+            ncu = json.load(f)
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(xs):
+        t = torch.tensor([float(x) for x in xs], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
+    def roofline_of(desc_, ctr_, wall_s, tag):
+        """Dominant kernel (simb_step_kernel) of a timed region: algorithmic bytes per launch / mean launch time.
+        Algorithmic bytes = every state word of the launch's replications read once and written once (2 x state
+        bytes x replications of the grid) + the queue / table bytes the launches touched in global memory, COUNTED
+        on the device (simb_counters.ring_bytes)."""
+        state_b = desc_["state_bytes_per_replication"]
+        launches_ = max(1, ctr_["launches"])
+        # a pass over the batch is issued as `grids` concurrent grids on their own streams, each covering
+        # 1/grids of the replications; launch_ms is the device time of the calls divided by the launches
+        grids = max(1, int(desc_.get("grids_per_pass", 1)))
+        ring_per_launch = ctr_["ring_bytes"] / launches_
+        alg = desc_["stride"] * (2.0 * state_b) / grids + ring_per_launch
+        launch_ms_ = ctr_["kernel_ms"] / launches_
+        ach = alg / (launch_ms_ * 1e-3) / 1e9 if launch_ms_ > 0 else 0.0
+        cap = ncu.get(tag, {})
+        r = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+             "traffic": cap.get("dram_bytes_per_launch"), "kernel": "simb_step_kernel<%s>" % desc_["kernel_shape"],
+             "launches": ctr_["launches"], "grids_per_pass": grids, "launch_ms": launch_ms_,
+             "algorithmic_bytes_per_launch": alg, "ring_bytes_per_launch_counted": ring_per_launch,
+             "steps_per_launch": desc_["steps_per_launch"], "state_bytes_per_replication": state_b,
+             "peak_source": peak_src, "kernel_share_of_step": ctr_["kernel_ms"] * 1e-3 / wall_s if wall_s > 0 else None}
+        if cap:
+            # DRAM bytes of the committed ncu capture of this configuration (tools/ncu_summary.py) over the launch
+            # time measured live here: the fraction of the HBM peak that really came from DRAM
+            r["traffic_source"] = "profiles/ncu_summary.json[%s] (ncu --set full capture of the same configuration, %s)" % (
+                tag, cap.get("source"))
+            if launch_ms_ > 0 and cap.get("dram_bytes_per_launch"):
+                r["dram_gbs"] = cap["dram_bytes_per_launch"] / (launch_ms_ * 1e-3) / 1e9
+                r["dram_frac"] = r["dram_gbs"] / peak
+            r["l2_hit_pct"] = cap.get("l2_hit_pct")
+            r["ncu"] = cap
+        return r
 
     def one_step():
         sim.reset()                 # Simulation::reset + put: fresh models, the RNG streams continue
@@ -215,92 +298,34 @@ def main():
         steps_done += c["steps"]
     barrier()
     dt = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
     ctr = sim.get_counters()
 
     # max over ranks of the elapsed time, sum over ranks of the work
-    tmax = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    work = torch.tensor([float(ev_done), float(steps_done)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(work, op=dist.ReduceOp.SUM)
-    dt_max = float(tmax.item())
-    events_total, rsteps_total = float(work[0].item()), float(work[1].item())
+    dt_max = reduce_max(dt)
+    events_total, rsteps_total = reduce_sum([ev_done, steps_done])
     value = events_total / dt_max
 
     # statistics: the only collective of the path -- all-reduce of (n, sum) then of the squared deviations
     s_sum, s_n = sim.stat_partial() if stat else (0.0, 0)
-    red = torch.tensor([s_sum, float(s_n)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(red, op=dist.ReduceOp.SUM)
+    red = reduce_sum([s_sum, s_n])
     ci = None
-    if stat and red[1].item() > 0:
-        mean = float(red[0].item() / red[1].item())
-        sq = torch.tensor([sim.stat_partial_sqdev(mean)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(sq, op=dist.ReduceOp.SUM)
+    if stat and red[1] > 0:
+        mean = red[0] / red[1]
+        sq = reduce_sum([sim.stat_partial_sqdev(mean)])[0]
         from sim_b200.simulator import _CI, load_library
         import ctypes as C
         out = _CI()
-        load_library().simb_oa_confidence_interval(mean, float(sq.item() / red[1].item()), int(red[1].item()), 0.05, C.byref(out))
+        load_library().simb_oa_confidence_interval(mean, sq / red[1], int(red[1]), 0.05, C.byref(out))
         ci = {"mean": out.mean, "lower": out.lower, "upper": out.upper, "n": out.n}
-
-    # roofline of the dominant kernel (simb_step_kernel): algorithmic bytes per launch / mean launch time
-    peak, peak_src = peaks()
-    ncu = {}
-    ncu_path = os.path.join(ROOT, "profiles", "ncu_summary.json")
-    if os.path.exists(ncu_path):
-        with open(ncu_path) as f:
-            ncu = json.load(f)
-
-    def roofline_of(desc_, ctr_, rsteps_local, wall_s, tag):
-        state_b = desc_["state_bytes_per_replication"]
-        launches_ = max(1, ctr_["launches"])
-        # ring touches per replication-step for this network: ~0.4 slots of 4 B (+8 B arrival time)
-        ring_b = 0.4 * (4 + (8 if stat else 0)) if desc_["ring_u32_slots"] else 0.0
-        # a pass over the batch is issued as `grids` concurrent grids on their own streams, each covering
-        # 1/grids of the replications; launch_ms is the device time of the call divided by the launches
-        grids = max(1, int(desc_.get("grids_per_pass", 1)))
-        alg = desc_["stride"] * (2.0 * state_b) / grids + (rsteps_local / launches_) * ring_b
-        launch_ms_ = ctr_["kernel_ms"] / launches_
-        ach = alg / (launch_ms_ * 1e-3) / 1e9 if launch_ms_ > 0 else 0.0
-        cap = ncu.get(tag, {})
-        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": cap.get("dram_bytes_per_launch"), "kernel": "simb_step_kernel<%s>" % desc_["kernel_shape"],
-                "launches": ctr_["launches"], "grids_per_pass": grids, "launch_ms": launch_ms_,
-                "algorithmic_bytes_per_launch": alg,
-                "steps_per_launch": desc_["steps_per_launch"], "state_bytes_per_replication": state_b,
-                "peak_source": peak_src, "kernel_share_of_step": ctr_["kernel_ms"] * 1e-3 / wall_s if wall_s > 0 else None,
-                "ncu": cap or None}
 
     k_eff = desc["steps_per_launch"]
     launches = ctr["launches"]
-    roofline = roofline_of(desc, ctr, rsteps_total / world, dt, "fused")
+    roofline = roofline_of(desc, ctr, dt, "fused")
     roofline["note"] = ("fused steps: the state is loaded once per %d steps, so the kernel sits far below the HBM roof "
                         "and is bound by instruction issue (ncu issue-active in roofline.ncu); the HBM-streaming "
                         "formulation (one step per launch, Simulation::step granularity) is reported in hbm_streaming_k1" % k_eff)
 
-    # the same workload with ONE step per launch (API-faithful Simulation::step granularity): every launch
-    # streams the whole state through HBM; bounded to a quarter of the horizon to keep the run short
-    k1 = None
-    if rank == 0 and world == 1 and not args.no_k1:
-        s1 = Simulation.post_json(mj, cj, n, seed=42, device=local_rank, steps_per_launch=1, stat_model_id=stat)
-        s1.step_until(args.until / 16.0)
-        s1.reset_counters()
-        c0 = s1.get_counters()
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        s1.step_until(args.until / 4.0)
-        torch.cuda.synchronize()
-        w1 = time.perf_counter() - t1
-        c1 = s1.get_counters()
-        r1 = roofline_of(s1.describe(), c1, c1["steps"] - c0["steps"], w1, "k1")
-        k1 = {"value": (c1["events"] - c0["events"]) / w1, "unit": UNIT,
-              "replication_steps_per_s": (c1["steps"] - c0["steps"]) / w1, "roofline": r1,
-              "sample": "step_until(%g) -> step_until(%g), steps_per_launch=1" % (args.until / 16.0, args.until / 4.0)}
-        s1.close()
-
-    # end to end through the public API with host buffers: post (JSON in), run, waits read back to the host
+    # ---- end to end through the public API with host buffers: post (JSON in), run, waits read back to the host ----
     e2e = None
     if not args.no_e2e:
         barrier()
@@ -317,13 +342,103 @@ def main():
             e_ev += s2.get_counters()["events"]
             s2.close()
         barrier()
-        e_dt = time.perf_counter() - t1
-        ev_t = torch.tensor([float(e_ev)], dtype=torch.float64, device="cuda")
-        tt = torch.tensor([e_dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(ev_t, op=dist.ReduceOp.SUM)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": float(ev_t.item() / tt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+        e_dt = reduce_max(time.perf_counter() - t1)
+        e2e = {"value": reduce_sum([e_ev])[0] / e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+    clocks = sampler.stop() if rank == 0 else None
+    sim.close()
+
+    # ---- the same workload with ONE step per launch (API-faithful Simulation::step granularity): every launch
+    # streams the whole state through the memory system.  2^20 replications = 101 MB of state, which the 126 MB L2
+    # largely holds between passes (reverse sweeps + evict_last hints): an L2-assisted number.  2^22 replications =
+    # 403 MB: the state genuinely streams from HBM.  Bounded to a slice of the horizon. ----
+    k1 = None
+    if rank == 0 and world == 1 and not args.no_k1:
+        k1 = []
+        for log2n, tag in ((20, "k1"), (22, "k1_2p22")):
+            nn = 1 << log2n
+            s1 = Simulation.post_json(mj, cj, nn, seed=42, device=local_rank, steps_per_launch=1, stat_model_id=stat)
+            s1.step_until(args.until / 16.0)
+            c0 = s1.get_counters()
+            s1.reset_counters()
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            s1.step_until(args.until / 8.0)
+            torch.cuda.synchronize()
+            w1 = time.perf_counter() - t1
+            c1 = s1.get_counters()
+            d1 = s1.describe()
+            r1 = roofline_of(d1, c1, w1, tag)
+            state_mb = d1["stride"] * d1["state_bytes_per_replication"] / 1e6
+            k1.append({"replications": nn, "value": (c1["events"] - c0["events"]) / w1, "unit": UNIT,
+                       "replication_steps_per_s": (c1["steps"] - c0["steps"]) / w1, "roofline": r1,
+                       "state_mb": state_mb,
+                       "l2": ("state %.0f MB < 126 MB L2: consecutive passes are L2-assisted, compare dram_frac" % state_mb) if state_mb < 126.0
+                             else ("state %.0f MB > 126 MB L2: the state streams from HBM every pass" % state_mb),
+                       "sample": "step_until(%g) -> step_until(%g), steps_per_launch=1" % (args.until / 16.0, args.until / 8.0)})
+            s1.close()
+
+    # ---- the other BASELINE configurations at their named sizes, bounded horizons ----
+    def run_job(network, per_rank, until, offset0, sub=None, **post_kw):
+        """Every rank runs `per_rank` replications of `network` (global indices offset0 + rank * per_rank ...) to
+        `until`, in sub-batches of at most `sub` replications posted one after the other.  Timed like the
+        headline: barrier + synchronize on both sides, max over ranks."""
+        m_, c_, stat_ = workload(network)
+        mj_, cj_ = models_to_json(m_), connectors_to_json(c_)
+        sub = min(per_rank, sub or per_rank)
+        tot = {"events": 0, "steps": 0, "launches": 0, "kernel_ms": 0.0, "ring_bytes": 0, "failed": 0}
+        d_ = None
+        # warm-up: one small batch through the same kernels (first-use module load, pool growth)
+        w = Simulation.post_json(mj_, cj_, min(sub, 1 << 16), seed=42, device=local_rank, stat_model_id=stat_, **post_kw)
+        w.step_until(until)
+        w.close()
+        barrier()
+        t1 = time.perf_counter()
+        done = 0
+        while done < per_rank:
+            cnt = min(sub, per_rank - done)
+            h = Simulation.post_json(mj_, cj_, cnt, seed=42, replication_offset=offset0 + rank * per_rank + done,
+                                     device=local_rank, stat_model_id=stat_, **post_kw)
+            h.step_until(until)
+            c_ = h.get_counters()
+            for k_ in tot:
+                tot[k_] += c_[k_]
+            d_ = h.describe()
+            h.close()
+            done += cnt
+        barrier()
+        wall = time.perf_counter() - t1
+        wall_max = reduce_max(wall)
+        ev, st = reduce_sum([tot["events"], tot["steps"]])
+        r_ = roofline_of(d_, tot, wall, "cfg_" + network)
+        return {"metric": metric_name(network, until), "config": job_config(network, per_rank, until),
+                "value": ev / wall_max, "unit": UNIT, "replication_steps_per_s": st / wall_max,
+                "replications_total": per_rank * world, "sub_batch": sub, "ms": 1e3 * wall_max,
+                "kernel_replication_steps_per_s_per_gpu": tot["steps"] / (tot["kernel_ms"] * 1e-3) if tot["kernel_ms"] else None,
+                "failed_replications": int(reduce_sum([tot["failed"]])[0]), "roofline": r_}
+
+    configs = None
+    if not args.no_configs and args.network == "mm1":
+        configs = []
+        sub = 1 << args.sub_batch_log2
+        for network, per_rank, until, kw in (("tandem", 1 << 22, 250.0, {"batch_warmup": 50, "batch_size": 5}),
+                                             ("gateway_network", 1 << 20, 100.0, {}),
+                                             ("large_mixed", 1 << 23, 4.0, {})):
+            r_ = run_job(network, per_rank, until, 0, sub=sub, **kw)
+            r_["scaling"] = "weak"
+            configs.append(r_)
+
+    # ---- fixed-total jobs split over the ranks (strong scaling): configs[4] with 2^26 replications in total,
+    # processed by each rank in shards of at most 2^23, and M/M/1 with 2^20 in total ----
+    strong = None
+    if not args.no_strong and args.network == "mm1":
+        strong = []
+        total = 1 << args.strong_total_log2
+        r_ = run_job("large_mixed", total // world, 4.0, 0, sub=1 << args.sub_batch_log2)
+        r_["scaling"] = "strong"
+        strong.append(r_)
+        r_ = run_job("mm1", (1 << 20) // world, args.until, 0)
+        r_["scaling"] = "strong"
+        strong.append(r_)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -337,21 +452,19 @@ def main():
 
     if rank == 0:
         print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * dt_max / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+            "metric": metric_name(args.network, args.until), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt_max / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "M/M/1 batched (BASELINE configs[1]): Generator Exp(0.5) -> Processor Exp(0.333333) cap 14 -> Storage"
-                       if args.network == "mm1" else args.network,
-                       "replications_per_gpu": n, "until": args.until, "steps_per_launch": k_eff,
-                       "rng": "philox4x32-10 per replication", "tile": desc["tile"],
-                       "l2": "state %.0f MB + rings %.0f MB per GPU vs 126 MB L2 (inputs larger than L2; no flush)" % (
-                           desc["stride"] * desc["state_bytes_per_replication"] / 1e6,
-                           desc["stride"] * (desc["ring_u32_slots"] * 4 + desc["ring_f64_slots"] * 8) / 1e6),
-                       "parallelism": "replications sharded, %d per GPU" % n},
+            "config": job_config(args.network, n, args.until),
+            "engine": {"steps_per_launch": k_eff, "tile": desc["tile"], "kernel": roofline["kernel"],
+                       "l2": "state %.0f MB + queue rings %.0f MB per GPU vs 126 MB L2; %d steps are fused per state load, so the "
+                             "timed kernel is not a streaming kernel (no flush needed); see hbm_streaming_k1 for the streaming form" % (
+                                 desc["stride"] * desc["state_bytes_per_replication"] / 1e6,
+                                 desc["stride"] * (desc["ring_u32_slots"] * 4 + desc["ring_f64_slots"] * 8) / 1e6, k_eff)},
             "replication_steps_per_s": rsteps_total / dt_max,
             "gpu_launches": int(launches * world + 2 * args.steps * world),
-            "clocks": clocks, "roofline": roofline, "hbm_streaming_k1": k1, "cpu_baseline": cpu, "e2e": e2e,
-            "statistic": ci,
+            "clocks": clocks, "roofline": roofline, "hbm_streaming_k1": k1, "configs": configs, "strong_scaling": strong,
+            "cpu_baseline": cpu, "e2e": e2e, "statistic": ci,
         }))
     if world > 1:
         dist.destroy_process_group()
