@@ -253,6 +253,32 @@ int simb_step_n_json(simb_sim* sim, uint64_t n, uint64_t replication, const char
 int simb_step_until_json(simb_sim* sim, double until, uint64_t replication, const char** json);
 int simb_format_f64(double value, char* out, uint64_t capacity);
 
+/* ---- whole-simulation documents and checkpoints ------------------------------------------------
+ * simb_get_json  <- WebSimulation::get_json (web.rs:43-45): serde_json::to_string_pretty of the Simulation
+ *                   { models (each with its live `state` block), connectors, messages, services.globalTime }
+ *                   (mod.rs:37-45) of ONE replication of the batch.  The models and connectors of the document can
+ *                   be posted again (simb_post_json); like the reference's, the document does not carry the RNG.
+ * simb_get_yaml  <- get_yaml (web.rs:69-71), the same document in serde_yaml 0.8 layout.
+ * simb_post_yaml <- post_yaml (web.rs:56-64), simb_put_yaml <- put_yaml (web.rs:66-67).
+ * simb_yaml_to_json / simb_json_to_yaml: the converters behind the other *_yaml forms of web.rs:91-215
+ *                   (get_messages_yaml, get_records_yaml, inject_input_yaml, step*_yaml); *needed receives the
+ *                   size of the result including the terminator.
+ * simb_state_size / simb_get_state / simb_put_state: the device state of the WHOLE batch (state rows, queue rings,
+ *                   mailboxes, RNG positions, statistics, trace buffers, counters) as one opaque blob for exact
+ *                   checkpoint / resume: a handle posted with the same models, connectors and simb_config continues
+ *                   bit for bit after simb_put_state.  (The reference's serde form skips the RNG, services.rs:11;
+ *                   the counter-based streams make the exact form cheap here.)
+ */
+int simb_get_json(simb_sim* sim, uint64_t replication, const char** json);
+int simb_get_yaml(simb_sim* sim, uint64_t replication, const char** yaml);
+int simb_post_yaml(const char* models_yaml, const char* connectors_yaml, const simb_config* config, simb_sim** out);
+int simb_put_yaml(simb_sim* sim, const char* models_yaml, const char* connectors_yaml);
+int simb_yaml_to_json(const char* yaml, char* out, uint64_t capacity, uint64_t* needed);
+int simb_json_to_yaml(const char* json, char* out, uint64_t capacity, uint64_t* needed);
+int simb_state_size(simb_sim* sim, uint64_t* bytes);
+int simb_get_state(simb_sim* sim, void* out, uint64_t capacity, uint64_t* written);
+int simb_put_state(simb_sim* sim, const void* data, uint64_t bytes);
+
 /* ---- output_analysis (sim/src/output_analysis/mod.rs) ------------------------------------------
  * Device side: per-replication waiting-time accumulators of `stat_model_id` (the statistic of
  * sim/tests/web.rs:571-597: Processing Start - Arrival per job) and their reduction.

@@ -274,5 +274,9 @@ std::unique_ptr<ModelBase> make_passive(const std::string& in);  // sim/tests/cu
 // state injection used by sim/tests/web.rs:30-46 (Processor `state` block)
 int preload_processor(ModelBase* m, int phase_active, double until_next_event, const std::vector<std::string>& queue);
 int preload_state(ModelBase* m, int phase, double until_next_event, const std::vector<std::string>& jobs);
+int preload_parallel_gateway(ModelBase* m, double until_next_event, const std::vector<std::string>& names, const uint64_t* counts);
+int preload_stochastic_gate(ModelBase* m, double until_next_event, const std::vector<std::string>& contents, const uint8_t* pass);
+int preload_stopwatch(ModelBase* m, int job_fetch, double until_next_event, const std::vector<std::string>& names,
+                      const double* start, const double* stop);
 
 }  // namespace orc

@@ -159,6 +159,25 @@ int orc_preload_state(void* hv, const char* id, int phase, double until, const c
         if (m.id == id) return preload_state(m.inner.get(), phase, until, split_nl(jobs_nl));
     return ModelNotFound;
 }
+int orc_preload_parallel_gateway(void* hv, const char* id, double until, const char* names_nl, const uint64_t* counts) {
+    Handle* h = (Handle*)hv;
+    for (auto& m : h->staged_models)
+        if (m.id == id) return preload_parallel_gateway(m.inner.get(), until, split_nl(names_nl), counts);
+    return ModelNotFound;
+}
+int orc_preload_stochastic_gate(void* hv, const char* id, double until, const char* contents_nl, const uint8_t* pass) {
+    Handle* h = (Handle*)hv;
+    for (auto& m : h->staged_models)
+        if (m.id == id) return preload_stochastic_gate(m.inner.get(), until, split_nl(contents_nl), pass);
+    return ModelNotFound;
+}
+int orc_preload_stopwatch(void* hv, const char* id, int job_fetch, double until, const char* names_nl, const double* start,
+                          const double* stop) {
+    Handle* h = (Handle*)hv;
+    for (auto& m : h->staged_models)
+        if (m.id == id) return preload_stopwatch(m.inner.get(), job_fetch, until, split_nl(names_nl), start, stop);
+    return ModelNotFound;
+}
 // Simulation::put with fresh clones of the staged models (the reference's replication idiom:
 // reset() + put(models.to_vec(), ..), sim/tests/simulations.rs:162-170)
 int orc_post(void* hv) {

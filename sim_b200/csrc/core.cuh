@@ -986,8 +986,9 @@ struct Engine {
                     break;
                 }
                 uint32_t fl = RW(ln, md.ring_w1 + i);
-                if (!(fl & other)) {  // same side again: overwrite the time
+                if (!(fl & other)) {  // same side again (or an entry injected with neither side): overwrite the time
                     RD(ln, md.ring_d + i) = ln.time;
+                    if (!(fl & mine)) RW(ln, md.ring_w1 + i) = fl | mine;
                     break;
                 }
                 // both sides now known: duration = stop - start (some_duration :95-100)
@@ -1380,8 +1381,9 @@ struct Engine {
             return;
         }
         const uint32_t fl = RW(ln, w1 + i);
-        if (!(fl & other)) {  // same side again: overwrite the time
+        if (!(fl & other)) {  // same side again (or an entry injected with neither side): overwrite the time
             RD(ln, rd + i) = ln.time;
+            if (!(fl & mine)) RW(ln, w1 + i) = fl | mine;
             return;
         }
         // both sides now known: duration = stop - start (some_duration :95-100)

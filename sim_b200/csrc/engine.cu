@@ -58,7 +58,13 @@ __global__ void simb_init_kernel(const __grid_constant__ SimbNetDesc net, const 
         st.w[(uint64_t)net.wrow_hash * st.stride + r] = (uint32_t)TRACE_HASH_INIT;
         st.w[(uint64_t)(net.wrow_hash + 1) * st.stride + r] = (uint32_t)(TRACE_HASH_INIT >> 32);
     }
-    for (uint32_t k = 0; k < n_pre; k++) st.ring_w[(uint64_t)pre_slots[k] * st.stride + r] = pre_vals[k];
+    for (uint32_t k = 0; k < n_pre; k++) {
+        const uint32_t slot = pre_slots[k];
+        if (slot & 0x80000000u)  // RING_PRELOAD_F64 (lower.hpp): one half of an f64 slot of ring_d
+            reinterpret_cast<uint32_t*>(st.ring_d)[2u * ((uint64_t)(slot & 0x3FFFFFFFu) * st.stride + r) + ((slot >> 30) & 1u)] = pre_vals[k];
+        else
+            st.ring_w[(uint64_t)slot * st.stride + r] = pre_vals[k];
+    }
 }
 
 __global__ void simb_reset_kernel(const __grid_constant__ SimbNetDesc net, const __grid_constant__ SimbDevState st,

@@ -331,6 +331,12 @@ struct PendingModel {
     uint32_t phase0 = 0;
     std::vector<uint32_t> words0;
     std::vector<std::string> preload;  // queue contents from `state`
+    std::vector<uint32_t> preload1;    // second u32 channel of those entries (collection count / pass flag / seq|flags)
+    std::vector<double> preload_d;     // f64 channel of those entries (Stopwatch: the time present)
+    bool has_best = false;             // Stopwatch `state.jobs` held completed jobs: (name, duration, seq) of the best
+    std::string best_name;
+    double best_dur = 0.0;
+    uint32_t best_seq = 0;
     uint32_t preload_next_port = 0;
 };
 
@@ -510,6 +516,18 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
             p.ring_cap = qcap;
             p.n_words = 1;  // entries
             p.words0 = {0};
+            if (state && state->is_object()) {  // parallel_gateway.rs:47-53: collections in the order of the document
+                get_num(*state, "untilNextEvent", &p.u0);
+                if (const Value* col = state->get("collections")) {
+                    if (!col->is_object()) return c.fail(13, hm.id + ": state.collections must be an object");
+                    for (auto& kv : col->obj) {
+                        if (!kv.second.is_uint) return c.fail(13, hm.id + ": state.collections values must be unsigned integers");
+                        p.preload.push_back(kv.first);
+                        p.preload1.push_back(clamp_u32(kv.second.u, 0xFFFFFFFFu));
+                    }
+                    if (p.preload.size() > p.ring_cap) p.ring_cap = clamp_u32(p.preload.size(), 65535);
+                }
+            }
         } else if (t == "StochasticGate") {  // stochastic_gate.rs:19-31
             md.type = MT_STOCHASTIC_GATE;
             if (!need_ports(true, true) || !port(pin, "job", &hm.ports_in) || !port(pout, "job", &hm.ports_out))
@@ -528,6 +546,21 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
             p.ring_cap = tcap;
             p.n_words = 1;
             p.words0 = {0};
+            if (state && state->is_object()) {  // stochastic_gate.rs:50-73: jobs: [{content, pass}]
+                get_num(*state, "untilNextEvent", &p.u0);
+                if (const Value* jobs = state->get("jobs")) {
+                    if (!jobs->is_array()) return c.fail(13, hm.id + ": state.jobs must be an array");
+                    for (auto& jb : jobs->arr) {
+                        std::string content;
+                        const Value* ps = jb.get("pass");
+                        if (!jb.is_object() || !get_str(jb, "content", &content) || !ps || ps->kind != Value::Bool)
+                            return c.fail(13, hm.id + ": state.jobs entries need `content` and `pass`");
+                        p.preload.push_back(content);
+                        p.preload1.push_back(ps->b ? 1u : 0u);
+                    }
+                    if (p.preload.size() > p.ring_cap) p.ring_cap = clamp_u32(p.preload.size(), 65535);
+                }
+            }
         } else if (t == "Stopwatch") {  // stopwatch.rs:21-32
             md.type = MT_STOPWATCH;
             if (!need_ports(true, true) || !port(pin, "start", &hm.ports_in) || !port(pin, "stop", &hm.ports_in) ||
@@ -543,6 +576,44 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
             p.n_words = 4;  // entries, best content, next seq, best seq
             p.words0 = {0, SIMB_CONTENT_NONE, 0, 0};
             p.n_dwords = 1;  // best duration
+            if (state && state->is_object()) {  // stopwatch.rs:66-93: jobs: [{name, start, stop}] (null = None)
+                std::string ph;
+                if (get_str(*state, "phase", &ph)) p.phase0 = ph == "JobFetch" ? 1 : 0;
+                get_num(*state, "untilNextEvent", &p.u0);
+                if (const Value* jobs = state->get("jobs")) {
+                    if (!jobs->is_array()) return c.fail(13, hm.id + ": state.jobs must be an array");
+                    uint32_t seq = 0;
+                    for (auto& jb : jobs->arr) {
+                        std::string name;
+                        if (!jb.is_object() || !get_str(jb, "name", &name)) return c.fail(13, hm.id + ": state.jobs entries need `name`");
+                        double t0 = 0.0, t1 = 0.0;
+                        // Option<f64>: null / absent = None (not the "null = infinity" reading of get_num)
+                        const Value* vs = jb.get("start");
+                        const Value* ve = jb.get("stop");
+                        const bool hs = vs && vs->kind != Value::Null && get_num(jb, "start", &t0);
+                        const bool he = ve && ve->kind != Value::Null && get_num(jb, "stop", &t1);
+                        if (hs && he) {  // completed: only the best one matters (release_minimum / _maximum :216-250,
+                                         // strict compare, first in insertion order)
+                            const double dur = t1 - t0;
+                            const bool mx = (md.flags & MF_METRIC_MAX) != 0;
+                            if (!p.has_best ? (mx ? dur > -std::numeric_limits<double>::infinity() : dur < std::numeric_limits<double>::infinity())
+                                            : (mx ? dur > p.best_dur : dur < p.best_dur)) {
+                                p.has_best = true;
+                                p.best_name = name;
+                                p.best_dur = dur;
+                                p.best_seq = seq;
+                            }
+                        } else {  // incomplete: a table entry (name, seq << 2 | has_stop << 1 | has_start, the time present)
+                            p.preload.push_back(name);
+                            p.preload1.push_back((seq << 2) | (he ? 2u : 0u) | (hs ? 1u : 0u));
+                            p.preload_d.push_back(hs ? t0 : he ? t1 : 0.0);
+                        }
+                        seq++;
+                    }
+                    p.words0[2] = seq;
+                    if (p.preload.size() > p.ring_cap) p.ring_cap = clamp_u32(p.preload.size(), 65535);
+                }
+            }
         } else if (t == "Batcher") {  // batcher.rs:22-33
             md.type = MT_BATCHER;
             if (!need_ports(true, true) || !port(pin, "job", &hm.ports_in) || !port(pout, "job", &hm.ports_out))
@@ -720,9 +791,22 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
         if (md.type == MT_STORAGE) {
             if (!pm[i].preload.empty()) hn.w_init[md.wrow] = hn.content_code(pm[i].preload[0], &overflow);
         } else if (!pm[i].preload.empty()) {  // `state.queue` / `state.jobs` injected on input (tests/web.rs:30-46)
-            for (size_t k = 0; k < pm[i].preload.size(); k++)
+            for (size_t k = 0; k < pm[i].preload.size(); k++) {
                 hn.ring_preload.push_back(RingPreload{md.ring_w0 + (uint32_t)k, hn.content_code(pm[i].preload[k], &overflow)});
-            hn.w_init[md.wrow] = (uint32_t)pm[i].preload.size();  // head 0, len n
+                if (k < pm[i].preload1.size()) hn.ring_preload.push_back(RingPreload{md.ring_w1 + (uint32_t)k, pm[i].preload1[k]});
+                if (k < pm[i].preload_d.size()) {  // an f64 slot travels as two words (RING_PRELOAD_F64)
+                    uint64_t bits;
+                    std::memcpy(&bits, &pm[i].preload_d[k], 8);
+                    hn.ring_preload.push_back(RingPreload{RING_PRELOAD_F64 | (md.ring_d + (uint32_t)k), (uint32_t)bits});
+                    hn.ring_preload.push_back(RingPreload{RING_PRELOAD_F64 | RING_PRELOAD_HI | (md.ring_d + (uint32_t)k), (uint32_t)(bits >> 32)});
+                }
+            }
+            hn.w_init[md.wrow] = (uint32_t)pm[i].preload.size();  // head 0, len n / table entries
+        }
+        if (md.type == MT_STOPWATCH && pm[i].has_best) {
+            hn.w_init[md.wrow + 1] = hn.content_code(pm[i].best_name, &overflow);
+            hn.w_init[md.wrow + 3] = pm[i].best_seq;
+            hn.d_init[md.drow] = pm[i].best_dur;
         }
         if (net.models[i].dist_kind == DK_EXP) net.uses_exp = 1;
         if (net.models[i].dist_kind == DK_NORMAL || net.models[i].dist_kind == DK_GAMMA ||

@@ -27,9 +27,11 @@ struct HostConnector {
     std::string id, source_id, target_id, source_port, target_port;
 };
 struct RingPreload {
-    uint32_t slot;   // absolute slot in ring_w
+    uint32_t slot;   // absolute slot in ring_w; with RING_PRELOAD_F64: slot in ring_d, one 32-bit half of the f64
     uint32_t value;
 };
+#define RING_PRELOAD_F64 0x80000000u
+#define RING_PRELOAD_HI 0x40000000u
 
 struct HostNet {
     SimbNetDesc desc;

@@ -101,6 +101,15 @@ def load_library() -> C.CDLL:
     L.simb_usize_sqrt.restype = C.c_uint64
     L.simb_usize_sqrt.argtypes = [C.c_uint64]
     L.simb_post_json.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(SimbConfig), C.POINTER(C.c_void_p)]
+    L.simb_post_yaml.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(SimbConfig), C.POINTER(C.c_void_p)]
+    L.simb_put_yaml.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+    L.simb_get_json.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_char_p)]
+    L.simb_get_yaml.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_char_p)]
+    L.simb_yaml_to_json.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.simb_json_to_yaml.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.simb_state_size.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.simb_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.simb_put_state.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     for name in ("simb_put_json",):
         getattr(L, name).argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
     for name in ("simb_reset", "simb_reset_messages", "simb_reset_global_time", "simb_destroy", "simb_step",
@@ -191,7 +200,7 @@ class Simulation:
                   rng_kind: int = RNG_PHILOX, replication_offset: int = 0, device: int = 0, steps_per_launch: int = 0,
                   queue_capacity: int = 0, max_pending: int = 0, instrument: bool = False, trace_replications: int = 0,
                   trace_capacity: int = 0, stat_model_id: Optional[str] = None, batch_warmup: int = 0,
-                  batch_size: int = 0, series_capacity: int = 0) -> "Simulation":
+                  batch_size: int = 0, series_capacity: int = 0, _yaml: bool = False) -> "Simulation":
         """``WebSimulation::post_json`` (web.rs:23-31) form of ``post``."""
         L = load_library()
         cfg = SimbConfig()
@@ -212,7 +221,8 @@ class Simulation:
         cfg.batch_size = batch_size
         cfg.series_capacity = series_capacity
         h = C.c_void_p()
-        _check(L.simb_post_json(models_json.encode(), connectors_json.encode(), C.byref(cfg), C.byref(h)))
+        post = L.simb_post_yaml if _yaml else L.simb_post_json
+        _check(post(models_json.encode(), connectors_json.encode(), C.byref(cfg), C.byref(h)))
         return cls(h, replications, models_json, connectors_json)
 
     def __del__(self):
@@ -326,6 +336,31 @@ class Simulation:
 
     def get_trace_hash(self) -> np.ndarray:
         return self._vec(load_library().simb_get_trace_hash, np.uint64)
+
+    def get_json(self, replication: int = 0) -> str:
+        """``WebSimulation::get_json`` (web.rs:43-45) of one replication: models with their live ``state``,
+        connectors, messages, services."""
+        out = C.c_char_p()
+        _check(load_library().simb_get_json(self._h, replication, C.byref(out)))
+        return out.value.decode()
+
+    def get_yaml(self, replication: int = 0) -> str:
+        out = C.c_char_p()
+        _check(load_library().simb_get_yaml(self._h, replication, C.byref(out)))
+        return out.value.decode()
+
+    def get_state(self) -> np.ndarray:
+        """Checkpoint of the whole batch (simb_get_state): an opaque byte blob."""
+        n = C.c_uint64()
+        _check(load_library().simb_state_size(self._h, C.byref(n)))
+        buf = np.zeros(n.value, np.uint8)
+        _check(load_library().simb_get_state(self._h, buf.ctypes.data, n.value, None))
+        return buf
+
+    def put_state(self, blob: np.ndarray):
+        """Resume from a checkpoint taken on a handle posted with the same network and configuration."""
+        b = np.ascontiguousarray(blob, dtype=np.uint8)
+        _check(load_library().simb_put_state(self._h, b.ctypes.data, b.size))
 
     def get_counters(self) -> dict:
         c = _Counters()
@@ -490,14 +525,28 @@ class WebSimulation:
         return self._text(load_library().simb_step_n_json, C.c_uint64(n), self.replication)
 
 
-    # ---- YAML forms (web.rs:49-70, 93-95, 115-117, 143-146, 167-169, 190-192, 213-215).  YAML is a host-side
-    # notation only: documents are converted to / from the JSON wire form of the C ABI with PyYAML.
+    def get_json(self) -> str:
+        """``get_json`` (web.rs:43-45): the whole Simulation of the observed replication, pretty-printed."""
+        return self._text(load_library().simb_get_json, self.replication)
+
+    def get_yaml(self) -> str:
+        """``get_yaml`` (web.rs:69-71)."""
+        return self._text(load_library().simb_get_yaml, self.replication)
+
+    # ---- YAML forms (web.rs:49-70, 93-95, 115-117, 143-146, 167-169, 190-192, 213-215): the library's own YAML
+    # reader / writer (csrc/yaml.hpp) behind simb_post_yaml / simb_put_yaml / simb_get_yaml and the two converters.
     @classmethod
-    def post_yaml(cls, models: str, connectors: str, replications: int = 1, **kw) -> "WebSimulation":
-        return cls.post_json(_yaml_to_json(models), _yaml_to_json(connectors), replications, **kw)
+    def post_yaml(cls, models: str, connectors: str, replications: int = 1, *, replication: int = 0,
+                  trace_capacity: int = 1 << 16, **kw) -> "WebSimulation":
+        """``post_yaml`` (web.rs:56-64) through simb_post_yaml."""
+        kw.setdefault("trace_replications", replication + 1)
+        sim = Simulation.post_json(models, connectors, replications, instrument=True, trace_capacity=trace_capacity,
+                                   _yaml=True, **kw)
+        return cls(sim, replication)
 
     def put_yaml(self, models: str, connectors: str):
-        self.put_json(_yaml_to_json(models), _yaml_to_json(connectors))
+        """``put_yaml`` (web.rs:66-67)."""
+        _check(load_library().simb_put_yaml(self.simulation._h, models.encode(), connectors.encode()))
 
     def get_messages_yaml(self) -> str:
         return _json_to_yaml(self.get_messages_json())
@@ -518,14 +567,22 @@ class WebSimulation:
         return _json_to_yaml(self.step_n_json(n))
 
 
+def _convert(fn, text: str) -> str:
+    need = C.c_uint64()
+    _check(fn(text.encode(), None, 0, C.byref(need)))
+    buf = C.create_string_buffer(need.value)
+    _check(fn(text.encode(), buf, need.value, None))
+    return buf.value.decode()
+
+
 def _yaml_to_json(text: str) -> str:
-    import yaml
-    return json.dumps(yaml.safe_load(text))
+    """YAML text -> compact JSON text (simb_yaml_to_json)."""
+    return _convert(load_library().simb_yaml_to_json, text)
 
 
 def _json_to_yaml(text: str) -> str:
-    import yaml
-    return yaml.safe_dump(json.loads(text), sort_keys=False)
+    """JSON text -> YAML text in serde_yaml 0.8 layout (simb_json_to_yaml)."""
+    return _convert(load_library().simb_json_to_yaml, text)
 
 
 def format_f64(value: float) -> str:

@@ -145,7 +145,12 @@ void* hs_new(const char* models, const char* connectors, uint64_t n, uint64_t re
             h->w[(size_t)net.wrow_hash * n + r] = (uint32_t)TRACE_HASH_INIT;
             h->w[(size_t)(net.wrow_hash + 1) * n + r] = (uint32_t)(TRACE_HASH_INIT >> 32);
         }
-        for (auto& pl : h->hn.ring_preload) h->ring_w[(size_t)pl.slot * n + r] = pl.value;
+        for (auto& pl : h->hn.ring_preload) {
+            if (pl.slot & RING_PRELOAD_F64)
+                reinterpret_cast<uint32_t*>(h->ring_d.data())[2 * ((size_t)(pl.slot & 0x3FFFFFFFu) * n + r) + ((pl.slot >> 30) & 1u)] = pl.value;
+            else
+                h->ring_w[(size_t)pl.slot * n + r] = pl.value;
+        }
     }
     SimbDevState& st = h->st;
     std::memset(&st, 0, sizeof st);

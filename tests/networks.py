@@ -289,6 +289,52 @@ def state_injection(store_records=False):
     return models, connectors
 
 
+def state_injection_tables(store_records=False):
+    """`state` blocks of the three table-keeping models (parallel_gateway.rs:47-53, stochastic_gate.rs:50-73,
+    stopwatch.rs:66-93): a join that starts with one collection half built and one complete, a stochastic gate
+    that starts with decided jobs queued, a stopwatch that starts with a completed job, one started only, one
+    stopped only and one with neither side, and is asked for its metric at once."""
+    def with_state(body, state):
+        body.state = state
+        return body
+    inf = float("inf")
+    models = [
+        Model.new("generator", Generator.new(Exp(1.0), None, "job", store_records, None)),
+        Model.new("split", ParallelGateway.new(["in"], ["a", "b"], store_records)),
+        Model.new("proc-a", Processor.new(Exp(2.0), None, "job", "done", store_records, None)),
+        Model.new("sgate-b", with_state(StochasticGate.new(BooleanRandomVariable.Bernoulli(1.0), "job", "job", store_records, None),
+                                        {"untilNextEvent": 0.0, "records": [],
+                                         "jobs": [{"content": "pre 1", "pass": True}, {"content": "pre 2", "pass": False},
+                                                  {"content": "job 900", "pass": True}]})),
+        Model.new("join", with_state(ParallelGateway.new(["a", "b"], ["out"], store_records),
+                                     {"untilNextEvent": 0.0, "records": [],
+                                      "collections": {"job 900": 1, "whole 1": 2, "pre 1": 1}})),
+        Model.new("watch", with_state(Stopwatch.new("start", "stop", "metric", "job", Metric.Minimum, store_records),
+                                      {"phase": "JobFetch", "untilNextEvent": 0.0, "records": [],
+                                       "jobs": [{"name": "old 1", "start": 0.25, "stop": 2.0},
+                                                {"name": "old 2", "start": 1.0, "stop": 1.5},
+                                                {"name": "old 3", "start": 3.0, "stop": 3.5},
+                                                {"name": "job 1", "start": 0.125, "stop": None},
+                                                {"name": "job 2", "start": None, "stop": 0.5},
+                                                {"name": "job 3", "start": None, "stop": None}]})),
+        Model.new("watch-max", with_state(Stopwatch.new("start", "stop", "metric", "job", Metric.Maximum, store_records),
+                                          {"phase": "Passive", "records": [],
+                                           "jobs": [{"name": "old 1", "start": 0.0, "stop": 1.0},
+                                                    {"name": "old 2", "start": 0.5, "stop": 1.5}]})),
+        _storage("sink", store_records), _storage("best", store_records),
+    ]
+    C = Connector.new
+    connectors = [
+        C("c1", "generator", "split", "job", "in"), C("c2", "split", "proc-a", "a", "job"),
+        C("c3", "split", "sgate-b", "b", "job"), C("c4", "proc-a", "join", "done", "a"),
+        C("c5", "sgate-b", "join", "job", "b"), C("c6", "join", "sink", "out", "store"),
+        C("c7", "generator", "watch", "job", "start"), C("c8", "proc-a", "watch", "done", "stop"),
+        C("c9", "watch", "best", "job", "store"), C("c10", "generator", "watch-max", "job", "start"),
+        C("c11", "join", "watch-max", "out", "stop"), C("c12", "sink", "watch-max", "stored", "metric"),
+    ]
+    return models, connectors
+
+
 # ---- BASELINE.json configurations (shapes fixed in SURVEY.md 8(d)) -----------------------------------
 def tandem():
     """config 3: generator Exp(1.0) -> load balancer (3 paths) -> 3x stage-1 processor Exp(0.4) cap 8 ->
@@ -419,6 +465,7 @@ ALL = {
     "gate_blocking": gate_blocking, "load_balancer": load_balancer, "parallel_gateway": parallel_gateway,
     "stochastic_gate": stochastic_gate, "batcher": batcher, "stopwatch": stopwatch,
     "processor_from_queue": processor_from_queue, "processor_network": processor_network,
-    "generator_passive": generator_passive, "more_variables": more_variables, "beta_variables": beta_variables, "state_injection": state_injection, "tandem": tandem, "gateway_network": gateway_network,
+    "generator_passive": generator_passive, "more_variables": more_variables, "beta_variables": beta_variables, "state_injection": state_injection,
+    "state_injection_tables": state_injection_tables, "tandem": tandem, "gateway_network": gateway_network,
     "large_mixed": large_mixed,
 }

@@ -129,7 +129,26 @@ class OracleSimulation:
         else:
             raise TypeError(type(i))
         st = getattr(i, "state", None)
-        if st is not None and not isinstance(i, M.Processor):
+        if st is not None and isinstance(i, (M.ParallelGateway, M.StochasticGate, M.Stopwatch)):
+            until = st.get("untilNextEvent", float("inf"))
+            until = float("inf") if until is None else float(until)
+            if isinstance(i, M.ParallelGateway):  # parallel_gateway.rs:47-53
+                col = st.get("collections", {})
+                cnt = (C.c_uint64 * max(1, len(col)))(*col.values())
+                e = L.orc_preload_parallel_gateway(h, b, d(until), _b("\n".join(col.keys())), cnt)
+            elif isinstance(i, M.StochasticGate):  # stochastic_gate.rs:50-64
+                jobs = st.get("jobs", [])
+                flags = (C.c_uint8 * max(1, len(jobs)))(*[1 if j["pass"] else 0 for j in jobs])
+                e = L.orc_preload_stochastic_gate(h, b, d(until), _b("\n".join(j["content"] for j in jobs)), flags)
+            else:  # stopwatch.rs:66-93
+                jobs = st.get("jobs", [])
+                nan = float("nan")
+                a = (C.c_double * max(1, len(jobs)))(*[nan if j.get("start") is None else j["start"] for j in jobs])
+                z = (C.c_double * max(1, len(jobs)))(*[nan if j.get("stop") is None else j["stop"] for j in jobs])
+                e = L.orc_preload_stopwatch(h, b, 1 if st.get("phase") == "JobFetch" else 0, d(until),
+                                            _b("\n".join(j["name"] for j in jobs)), a, z)
+            assert e == 0, e
+        elif st is not None and not isinstance(i, M.Processor):
             phases = {M.Gate: ["Open", "Closed", "Pass"], M.Batcher: ["Passive", "Batching", "Release"],
                       M.ExclusiveGateway: ["Passive", "Pass"], M.LoadBalancer: ["Passive", "LoadBalancing"]}[type(i)]
             until = st.get("untilNextEvent", float("inf"))

@@ -1,7 +1,9 @@
 #!/usr/bin/env python3
 """Summarise ncu captures into profiles/ncu_summary.json (read by bench.py for roofline.traffic / .ncu).
 
-usage: ncu_summary.py tag=path.ncu-rep [tag=path ...]      (tags used by bench.py: fused, k1)
+usage: ncu_summary.py tag=path.ncu-rep|path_raw.csv [tag=path ...]
+       (tags used by bench.py: fused, k1, k1_2p22, cfg_tandem, cfg_gateway_network, cfg_large_mixed; a .csv is the
+       `ncu -i X.ncu-rep --page raw --csv` export made on the GPU box, so that the reports need not travel)
 For each capture the LAST profiled launch of simb_step_kernel is summarised (steady state)."""
 import csv
 import json
@@ -22,12 +24,19 @@ WANT = {
     "launch__registers_per_thread": "registers_per_thread",
     "launch__grid_size": "grid",
     "lts__t_sector_hit_rate.pct": "l2_hit_pct",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio": "stall_no_instruction_per_issue",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio": "stall_long_scoreboard_per_issue",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio": "stall_wait_per_issue",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio": "stall_branch_resolving_per_issue",
     "l1tex__t_sector_hit_rate.pct": "l1_hit_pct",
 }
 
 
 def summarise(path):
-    out = subprocess.check_output(["ncu", "-i", path, "--page", "raw", "--csv"], text=True, stderr=subprocess.DEVNULL)
+    if path.endswith(".csv"):
+        out = open(path, encoding="latin-1").read()
+    else:
+        out = subprocess.check_output(["ncu", "-i", path, "--page", "raw", "--csv"], text=True, stderr=subprocess.DEVNULL)
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     data = [r for r in rows[2:] if "simb_step_kernel" in r[hdr.index("Kernel Name")]]
