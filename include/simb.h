@@ -317,6 +317,24 @@ int simb_oa_steady_state(const double* series, uint64_t n, double alpha, simb_ci
 int simb_oa_t_score(double alpha, uint64_t df, double* out);
 uint64_t simb_usize_sqrt(uint64_t n);
 
+/* ---- input_modeling (sim/src/input_modeling) ------------------------------------------------------
+ * simb_sample_random_variable <- {Continuous, Boolean, Discrete, Index}::random_variate (random_variable.rs:65-131) on
+ *     the device: `count` variates per replication of ONE random variable, given in the reference's JSON form
+ *     (e.g. {"exp":{"lambda":0.5}}, {"bernoulli":{"p":0.3}}, {"poisson":{"lambda":7.0}}, {"geometric":{"p":0.2}},
+ *     {"uniform":{"min":7,"max":11}}, {"weightedIndex":{"weights":[1,2,3,4]}}) with family = "continuous" | "boolean" |
+ *     "discrete" | "index", drawn from the per-replication Philox streams the engine uses (key = global replication
+ *     index, seed; draws numbered from 0).  out[i * replications + r]: continuous -> out_f64, all others -> out_u64
+ *     (booleans 0 / 1); draws_consumed[r] (may be NULL) = u64 draws replication r used.  Parameter errors are
+ *     reported as the reference raises them, at draw time (BetaError ... WeightedError, Panic for Uniform low >= high).
+ * simb_thinning_evaluate      <- Thinning::evaluate (thinning.rs:27-34): the normalised polynomial thinning function,
+ *     coefficients from the highest order down (utils/mod.rs:34-41).  (The reference's Generator stores a Thinning and
+ *     never evaluates it, generator.rs:98-146; posted models may carry the field, the engine ignores it the same way.)
+ */
+int simb_sample_random_variable(const char* family, const char* variable_json, uint64_t replications, uint64_t count,
+                                uint64_t seed, uint64_t replication_offset, int device, double* out_f64,
+                                uint64_t* out_u64, uint32_t* draws_consumed);
+int simb_thinning_evaluate(const double* coefficients, uint64_t n, double point, double* out);
+
 /* ---- introspection -----------------------------------------------------------------------------*/
 int simb_describe(simb_sim* sim, char* out, uint64_t capacity); /* JSON: layout rows, rings, K, TPB ... */
 int simb_model_count(simb_sim* sim, uint64_t* models, uint64_t* connectors);

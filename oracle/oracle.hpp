@@ -116,6 +116,15 @@ struct Index {  // Index::Uniform{min,max} | Index::WeightedIndex{weights}
     int random_variate(Rng& rng, uint64_t* out) const;  // random_variable.rs:122-130
 };
 
+struct Discrete {  // Discrete::Geometric{p} | Poisson{lambda} | Uniform{min,max}  (random_variable.rs:36-50)
+    int kind = 0;  // 0 Geometric, 1 Poisson, 2 Uniform
+    double p = 0.5;  // Geometric p / Poisson lambda
+    uint64_t min = 0, max = 1;
+    int random_variate(Rng& rng, uint64_t* out) const;  // random_variable.rs:108-115
+};
+// Thinning::evaluate (input_modeling/thinning.rs:27-34) = utils::evaluate_polynomial (utils/mod.rs:34-69)
+int thinning_evaluate(const double* coefficients, size_t n, double point, double* out);
+
 // low-level pieces exposed for tests
 double standard_f64(Rng& rng);
 double open01_f64(Rng& rng);

@@ -397,6 +397,24 @@ int orc_sample_bernoulli(double p, int rng_kind, uint64_t seed, uint64_t rep, ui
     if (consumed) *consumed = r->draws;
     return 0;
 }
+int orc_sample_discrete(int kind, double p, uint64_t mn, uint64_t mx, int rng_kind, uint64_t seed, uint64_t rep,
+                        uint64_t* out, uint64_t n, uint64_t* consumed) {
+    auto r = mk_rng(rng_kind, seed, rep);
+    Discrete d;
+    d.kind = kind;
+    d.p = p;
+    d.min = mn;
+    d.max = mx;
+    for (uint64_t i = 0; i < n; i++) {
+        int e = d.random_variate(*r, &out[i]);
+        if (e) return e;
+    }
+    if (consumed) *consumed = r->draws;
+    return 0;
+}
+int orc_thinning_evaluate(const double* coefficients, uint64_t n, double point, double* out) {
+    return thinning_evaluate(coefficients, (size_t)n, point, out);
+}
 int orc_sample_index(int weighted, uint64_t mn, uint64_t mx, const uint64_t* w, int nw, int rng_kind, uint64_t seed,
                      uint64_t rep, uint64_t* out, uint64_t n, uint64_t* consumed) {
     auto r = mk_rng(rng_kind, seed, rep);

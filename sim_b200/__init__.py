@@ -6,13 +6,13 @@ Host-side mirror of the reference's Rust API for the accelerated path
 (include/simb.h).  There is no CPU fallback: without the CUDA library the engine raises.
 """
 from .coupling import Connector, Message  # noqa: F401
-from .input_modeling import (BooleanRandomVariable, ContinuousRandomVariable,  # noqa: F401
-                             IndexRandomVariable)
+from .input_modeling import (BooleanRandomVariable, ContinuousRandomVariable, DiscreteRandomVariable,  # noqa: F401
+                             IndexRandomVariable, Thinning)
 from .models import (Batcher, ExclusiveGateway, Gate, Generator, LoadBalancer, Metric, Model,  # noqa: F401
                      ParallelGateway, Passive, Processor, StochasticGate, Stopwatch, Storage)
 
 __all__ = [
-    "Connector", "Message", "BooleanRandomVariable", "ContinuousRandomVariable", "IndexRandomVariable",
+    "Connector", "Message", "BooleanRandomVariable", "ContinuousRandomVariable", "DiscreteRandomVariable", "IndexRandomVariable", "Thinning",
     "Batcher", "ExclusiveGateway", "Gate", "Generator", "LoadBalancer", "Metric", "Model", "ParallelGateway",
     "Passive", "Processor", "StochasticGate", "Stopwatch", "Storage",
 ]

@@ -1502,6 +1502,73 @@ int simb_put_state(simb_sim* s, const void* data, uint64_t bytes) {
     return 0;
 }
 
+// ---- input_modeling on the device (random_variable.rs:65-131, thinning.rs:27-34) ----------------------------------
+int simb_sample_random_variable(const char* family, const char* variable_json, uint64_t replications, uint64_t count,
+                                uint64_t seed, uint64_t replication_offset, int device, double* out_f64, uint64_t* out_u64,
+                                uint32_t* draws_consumed) {
+    if (!family || !variable_json) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    int fam;
+    const std::string f = family;
+    if (f == "continuous") fam = FAM_CONTINUOUS;
+    else if (f == "boolean") fam = FAM_BOOLEAN;
+    else if (f == "discrete") fam = FAM_DISCRETE;
+    else if (f == "index") fam = FAM_INDEX;
+    else return fail(SIMB_ERR_INVALID_ARGUMENT, "family must be continuous, boolean, discrete or index");
+    if (replications == 0) return fail(SIMB_ERR_INVALID_ARGUMENT, "replications must be > 0");
+    if (fam == FAM_CONTINUOUS ? !out_f64 : !out_u64)
+        return fail(SIMB_ERR_INVALID_ARGUMENT, "continuous variates go to out_f64, all others to out_u64");
+    SimbNetDesc net;
+    std::string err;
+    int e = lower_random_variable(fam, variable_json, &net, &err);
+    if (e) return fail(e, err);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(SIMB_ERR_CUDA, "no CUDA device available; libsimb200 has no CPU fallback");
+    CUDA_TRY(cudaSetDevice(device));
+    SimbDevState st;
+    std::memset(&st, 0, sizeof st);
+    st.n = st.stride = replications;
+    st.rep_offset = replication_offset;
+    st.seed = seed;
+    const size_t total = (size_t)(replications * count);
+    double* d_d = nullptr;
+    unsigned long long* d_u = nullptr;
+    uint32_t* d_draws = nullptr;
+    int32_t* d_status = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_d);
+        cudaFree(d_u);
+        cudaFree(d_draws);
+        cudaFree(d_status);
+    };
+    cudaError_t ce = cudaSuccess;
+    if (fam == FAM_CONTINUOUS) ce = cudaMalloc((void**)&d_d, std::max<size_t>(1, total) * 8);
+    else ce = cudaMalloc((void**)&d_u, std::max<size_t>(1, total) * 8);
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&d_draws, replications * 4);
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&d_status, 4);
+    if (ce == cudaSuccess) ce = cudaMemset(d_status, 0, 4);
+    if (ce == cudaSuccess) ce = (cudaError_t)engine_launch_sample(net, st, (uint32_t)fam, count, d_d, d_u, d_draws, d_status, nullptr);
+    if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
+    int32_t status = 0;
+    if (ce == cudaSuccess) ce = cudaMemcpy(&status, d_status, 4, cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess && total)
+        ce = fam == FAM_CONTINUOUS ? cudaMemcpy(out_f64, d_d, total * 8, cudaMemcpyDeviceToHost)
+                                   : cudaMemcpy(out_u64, d_u, total * 8, cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess && draws_consumed) ce = cudaMemcpy(draws_consumed, d_draws, replications * 4, cudaMemcpyDeviceToHost);
+    cleanup();
+    if (ce != cudaSuccess) return fail(SIMB_ERR_CUDA, std::string("simb_sample_random_variable: ") + cudaGetErrorString(ce));
+    if (status) return fail(status, std::string("random variable parameters: ") + status_name(status));  // raised at draw time
+    return 0;
+}
+int simb_thinning_evaluate(const double* coefficients, uint64_t n, double point, double* out) {
+    if (!out || (n && !coefficients)) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    // Thinning::evaluate -> utils::evaluate_polynomial (utils/mod.rs:34-69): coefficients from the highest order down
+    double acc = 0.0;
+    for (uint64_t i = 0; i < n; i++) acc = acc * point + coefficients[i];
+    *out = acc;
+    return 0;
+}
+
 // ---- statistics ---------------------------------------------------------------------------------------
 int simb_get_wait_stats(simb_sim* s, double* sum, uint32_t* count, uint64_t capacity) {
     if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");

@@ -518,6 +518,91 @@ struct Engine {
                 return RARE ? sample_continuous_rare(ln, dist_kind, pd) : 0.0;
         }
     }
+    // ---- Discrete::random_variate (random_variable.rs:108-115); rand_distr 0.4 Geometric / Poisson ------------------
+    static SIMB_HD double powi_f64(double a, int b) {  // compiler-rt __powidf2 (f64::powi)
+        const bool recip = b < 0;
+        double r = 1.0;
+        for (;;) {
+            if (b & 1) r *= a;
+            b /= 2;
+            if (b == 0) break;
+            a *= a;
+        }
+        return recip ? 1.0 / r : r;
+    }
+    static SIMB_HD double log_gamma(double x) {  // rand_distr 0.4 utils::log_gamma (6-term Lanczos)
+        const double co[6] = {76.18009172947146, -86.50532032941677, 24.01409824083091,
+                              -1.231739572450155, 0.1208650973866179e-2, -0.5395239384953e-5};
+        const double tmp = x + 5.5;
+        const double lg = (x + 0.5) * log(tmp) - tmp;
+        double a = 1.000000000190015, denom = x;
+        for (int i = 0; i < 6; i++) {
+            denom = denom + 1.0;
+            a = a + (co[i] / denom);
+        }
+        return lg + log(2.5066282746310005 * a / x);
+    }
+    template <class P>
+    SIMB_HD uint64_t sample_discrete_kind(Lane& ln, uint32_t dist_kind, const P& pd) {
+        if (pd.dist_err()) {
+            if (!ln.err) ln.err = pd.dist_err();
+            return 0;
+        }
+        if (dist_kind == DK_GEOMETRIC) {
+            const double p = pd.p0(), pi = pd.p1();
+            if (p >= 2.0 / 3.0) {  // the trivial algorithm
+                uint64_t failures = 0;
+                for (;;) {
+                    const double u = standard_f64(ln);
+                    if (u <= p || ln.err) break;
+                    failures++;
+                }
+                return failures;
+            }
+            if (p == 0.0) return 0xFFFFFFFFFFFFFFFFull;
+            const uint64_t k = pd.q0();
+            uint64_t d = 0;  // D ~ Geo(pi) = Geo(p) / 2^k
+            while (standard_f64(ln) < pi && !ln.err) d++;
+            uint64_t m;  // M ~ Geo(p) % 2^k by rejection
+            for (;;) {
+                m = next_u64(ln) & ((1ull << k) - 1ull);
+                const double p_reject = m <= 0x7FFFFFFFull ? powi_f64(1.0 - p, (int)m) : pow(1.0 - p, (double)m);
+                const double u = standard_f64(ln);
+                if (u < p_reject || ln.err) break;
+            }
+            return (d << k) + m;
+        }
+        if (dist_kind == DK_POISSON) {  // Poisson<f64>::sample, then `as u64`
+            const double lambda = pd.p0();
+            double result;
+            if (lambda < 12.0) {  // Knuth
+                const double exp_lambda = pd.p1();
+                double prod = 1.0;
+                result = 0.0;
+                while (prod > exp_lambda && !ln.err) {
+                    prod = prod * standard_f64(ln);
+                    result = result + 1.0;
+                }
+                result = result - 1.0;
+            } else {  // rejection from a Cauchy envelope (Numerical Recipes)
+                const double log_lambda = pd.p2(), sqrt_2lambda = bits_f64(pd.q0()), magic_val = bits_f64(pd.q1());
+                for (;;) {
+                    double comp_dev;
+                    for (;;) {
+                        comp_dev = tan(3.14159265358979323846 * standard_f64(ln));
+                        result = sqrt_2lambda * comp_dev + lambda;
+                        if (result >= 0.0 || ln.err) break;
+                    }
+                    result = floor(result);
+                    const double check = 0.9 * (1.0 + comp_dev * comp_dev) *
+                                         exp(result * log_lambda - log_gamma(1.0 + result) - magic_val);
+                    if (standard_f64(ln) <= check || ln.err) break;
+                }
+            }
+            return result >= 18446744073709551615.0 ? 0xFFFFFFFFFFFFFFFFull : result > 0.0 ? (uint64_t)result : 0ull;
+        }
+        return sample_uniform_int(ln, pd.q0(), pd.q1(), pd.q2());  // DK_UNIFORM_INT
+    }
     // rand 0.8 UniformInt<u64>::sample: widening multiply + zone rejection
     SIMB_HD uint64_t sample_uniform_int(Lane& ln, uint64_t low, uint64_t range, uint64_t zone) {
         for (;;) {

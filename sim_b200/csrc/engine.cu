@@ -260,6 +260,40 @@ simb_steady_state_kernel(const __grid_constant__ SimbNetDesc net, const __grid_c
     }
     out[r] = o;
 }
+// input_modeling on the device: every thread (= replication) draws `count` variates of ONE random variable
+// (net.models[0], lowered by lower_random_variable) from its own Philox stream -- the streams the engine itself uses:
+// key = (global replication index, seed), draws numbered from 0.  out[i * n + r]; draws[r] = u64s consumed.
+// The samplers are the Engine's own (core.cuh), so a variate here is bit-identical to the one a model would draw.
+__global__ void __launch_bounds__(128)
+simb_sample_kernel(const __grid_constant__ SimbNetDesc net, const __grid_constant__ SimbDevState st, uint32_t family,
+                   uint64_t count, double* __restrict__ out_d, unsigned long long* __restrict__ out_u,
+                   uint32_t* __restrict__ draws, int32_t* __restrict__ status) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= st.n) return;
+    Tables tab;
+    tab.exp_x = ZIG_EXP_X;  // (read from global memory here: this is not the hot path)
+    tab.exp_f = ZIG_EXP_F;
+    tab.norm_x = ZIG_NORM_X;
+    tab.norm_f = ZIG_NORM_F;
+    tab.mt = nullptr;
+    tab.vt = nullptr;
+    tab.rng_cache = nullptr;
+    tab.rng_slots = 0;
+    Engine<0, 0, true, false> eng(net, st, tab);
+    Lane ln;
+    memset(&ln, 0, sizeof ln);
+    ln.rep = (uint32_t)r;
+    const SimbModelDesc& md = net.models[0];
+    const DescP pd{md};
+    for (uint64_t i = 0; i < count && !ln.err; i++) {
+        if (family == FAM_CONTINUOUS) out_d[i * st.n + r] = eng.sample_continuous_kind(ln, md.dist_kind, pd);
+        else if (family == FAM_BOOLEAN) out_u[i * st.n + r] = eng.sample_bernoulli_p(ln, md.flags, pd) ? 1ull : 0ull;
+        else if (family == FAM_DISCRETE) out_u[i * st.n + r] = eng.sample_discrete_kind(ln, md.dist_kind, pd);
+        else out_u[i * st.n + r] = eng.sample_index_p(ln, md.flags, md.n_w, md.wtab, pd);
+    }
+    if (draws) draws[r] = ln.draw_idx;
+    if (ln.err) atomicCAS(status, 0, (int32_t)ln.err);
+}
 // exact u64 sums of the steps / events rows
 __global__ void __launch_bounds__(RED_THREADS)
 simb_count_kernel(const __grid_constant__ SimbNetDesc net, const __grid_constant__ SimbDevState st,
@@ -490,6 +524,11 @@ int engine_launch_steady_state(const SimbNetDesc& net, const SimbDevState& st, c
         ts.t_hi[i] = t_hi[i];
     }
     simb_steady_state_kernel<<<blocks_for(st.n, 128), 128, 0, stream>>>(net, st, ts, out);
+    return (int)cudaGetLastError();
+}
+int engine_launch_sample(const SimbNetDesc& net, const SimbDevState& st, uint32_t family, uint64_t count, double* out_d,
+                         unsigned long long* out_u, uint32_t* draws, int32_t* status, cudaStream_t stream) {
+    simb_sample_kernel<<<blocks_for(st.n, 128), 128, 0, stream>>>(net, st, family, count, out_d, out_u, draws, status);
     return (int)cudaGetLastError();
 }
 uint32_t engine_reduce_blocks(uint64_t n) { return blocks_for(n, RED_THREADS * RED_ITEMS); }

@@ -55,6 +55,11 @@ int engine_launch_reduce(const SimbNetDesc& net, const SimbDevState& st, int whi
 int engine_launch_steady_state(const SimbNetDesc& net, const SimbDevState& st, const double* t_lo, const double* t_hi,
                                SimbSteadyState* out, cudaStream_t stream);
 
+// `count` variates per replication of the random variable lowered into net.models[0] (lower_random_variable), from the
+// per-replication Philox streams (st.n, st.rep_offset, st.seed); out[i * st.n + r]
+int engine_launch_sample(const SimbNetDesc& net, const SimbDevState& st, uint32_t family, uint64_t count, double* out_d,
+                         unsigned long long* out_u, uint32_t* draws, int32_t* status, cudaStream_t stream);
+
 uint32_t engine_reduce_blocks(uint64_t n);
 
 }  // namespace simb

@@ -322,6 +322,74 @@ int lower_index(Ctx& c, const Value* v, SimbModelDesc* md, SimbNetDesc* net, uin
     return c.fail(13, "unknown variant `" + kind + "`");
 }
 
+// Discrete (random_variable.rs:36-50)
+int lower_discrete(Ctx& c, const Value* v, SimbModelDesc* md) {
+    if (!v || !v->is_object() || v->obj.size() != 1) return c.fail(13, "expected a one-variant discrete random variable");
+    const std::string& kind = v->obj[0].first;
+    const Value& p = v->obj[0].second;
+    md->dist_err = 0;
+    if (kind == "geometric") {  // rand_distr 0.4 Geometric::new
+        double pr;
+        if (!get_num(p, "p", &pr)) return c.fail(13, "geometric: missing field `p`");
+        md->dist_kind = DK_GEOMETRIC;
+        if (!std::isfinite(pr) || pr < 0.0 || pr > 1.0) {
+            md->dist_err = 21;
+            return 0;
+        }
+        md->p0 = pr;
+        md->p1 = pr;
+        md->q0 = 0;
+        if (!(pr == 0.0 || pr >= 2.0 / 3.0)) {  // smallest k with pi = (1-p)^(2^k) <= 1/2
+            uint64_t k = 1;
+            double pi = (1.0 - pr) * (1.0 - pr);
+            while (pi > 0.5) {
+                k++;
+                pi = pi * pi;
+            }
+            md->p1 = pi;
+            md->q0 = k;
+        }
+        return 0;
+    }
+    if (kind == "poisson") {  // rand_distr 0.4 Poisson::new
+        double lambda;
+        if (!get_num(p, "lambda", &lambda)) return c.fail(13, "poisson: missing field `lambda`");
+        md->dist_kind = DK_POISSON;
+        if (!(lambda > 0.0)) {
+            md->dist_err = 22;
+            return 0;
+        }
+        md->p0 = lambda;
+        md->p1 = std::exp(-lambda);
+        md->p2 = std::log(lambda);
+        const double sq = std::sqrt(2.0 * lambda);
+        // utils::log_gamma(1 + lambda), 6-term Lanczos
+        const double x = 1.0 + lambda, tmp = x + 5.5;
+        static const double co[6] = {76.18009172947146, -86.50532032941677, 24.01409824083091,
+                                     -1.231739572450155, 0.1208650973866179e-2, -0.5395239384953e-5};
+        double a = 1.000000000190015, denom = x;
+        for (double cf : co) {
+            denom = denom + 1.0;
+            a = a + (cf / denom);
+        }
+        const double lg = (x + 0.5) * std::log(tmp) - tmp + std::log(2.5066282746310005 * a / x);
+        const double magic = lambda * md->p2 - lg;
+        std::memcpy(&md->q0, &sq, 8);
+        std::memcpy(&md->q1, &magic, 8);
+        return 0;
+    }
+    if (kind == "uniform") {
+        const Value* mn = p.get("min");
+        const Value* mx = p.get("max");
+        if (!mn || !mx || !mn->is_uint || !mx->is_uint) return c.fail(13, "discrete uniform: min/max must be unsigned integers");
+        md->dist_kind = DK_UNIFORM_INT;
+        if (!(mn->u < mx->u)) md->dist_err = 34;  // Uniform::new asserts low < high
+        else uniform_int_params(mn->u, mx->u, md);
+        return 0;
+    }
+    return c.fail(13, "unknown variant `" + kind + "`");
+}
+
 struct PendingModel {
     // lowering scratch per model
     uint32_t n_words = 0, n_dwords = 0;
@@ -343,6 +411,37 @@ struct PendingModel {
 uint32_t clamp_u32(uint64_t v, uint32_t hi) { return v > hi ? hi : (uint32_t)v; }
 
 }  // namespace
+
+// one random variable of the given family (0 Continuous, 1 Boolean, 2 Discrete, 3 Index) into models[0] (+ wcum)
+int lower_random_variable(int family, const char* variable_json, SimbNetDesc* net, std::string* err) {
+    Ctx c{err};
+    if (!variable_json || !net) return c.fail(36, "null argument");
+    Value v;
+    json::Parser p(variable_json);
+    if (!p.parse(v)) return c.fail(13, "random variable: " + p.err);
+    std::memset(net, 0, sizeof *net);
+    SimbModelDesc* md = &net->models[0];
+    md->dist_kind = DK_NONE;
+    uint32_t n_wcum = 0;
+    switch (family) {
+        case FAM_CONTINUOUS: return lower_continuous(c, &v, md);
+        case FAM_DISCRETE: return lower_discrete(c, &v, md);
+        case FAM_INDEX: return lower_index(c, &v, md, net, &n_wcum);
+        case FAM_BOOLEAN: {  // Boolean::Bernoulli (random_variable.rs:30-34); rand 0.8 Bernoulli::new
+            const Value* b = v.get("bernoulli");
+            double pr;
+            if (!b || !get_num(*b, "p", &pr)) return c.fail(13, "expected {\"bernoulli\": {\"p\": ..}}");
+            if (!(pr >= 0.0 && pr < 1.0)) {
+                if (pr == 1.0) md->flags |= MF_BERNOULLI_ALWAYS;
+                else md->dist_err = 20;
+            } else {
+                md->q0 = (uint64_t)(pr * (2.0 * (double)(1ull << 63)));
+            }
+            return 0;
+        }
+    }
+    return c.fail(36, "unknown random variable family");
+}
 
 int lower_network(const char* models_json, const char* connectors_json, const LowerOptions& opt, HostNet* out,
                   std::string* err) {
@@ -661,8 +760,52 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
     if (hn.connectors.size() > 0xFFFE) return c.fail(32, "too many connectors");
     net.n_connectors = (uint32_t)hn.connectors.size();
 
+    // ---- bursts: the largest number of jobs a model can send on one port / receive in ONE step ---------
+    // Most models send one job per firing; a Gate or an ExclusiveGateway sends everything that arrived in the step, a
+    // Batcher a whole batch.  Propagated along the connectors to a fixed point (cycles: clamped), these bounds size the
+    // transient queues and the mailbox, so that e.g. Batcher(20) -> Gate -> Storage runs as it does in the reference
+    // (whose Vecs are unbounded) instead of overflowing a 16-slot ring.
+    const uint32_t BURST_MAX = 4096;
+    std::vector<uint32_t> burst_out(hn.models.size(), 1u), burst_in(hn.models.size(), 0u);
+    for (size_t pass = 0; pass < hn.models.size() + 2; pass++) {
+        bool changed = false;
+        for (size_t i = 0; i < hn.models.size(); i++) {
+            uint64_t in = 0;
+            for (auto& hc : hn.connectors)
+                if (hc.target_id == hn.models[i].id) {
+                    const int sm = hn.find_model(hc.source_id);
+                    if (sm >= 0) in += burst_out[sm];
+                }
+            const uint32_t bi = clamp_u32(in, BURST_MAX);
+            uint32_t bo = 1;
+            const uint8_t ty = net.models[i].type;
+            if (ty == MT_GATE || ty == MT_EXCLUSIVE_GATEWAY) bo = bi ? bi : 1;
+            else if (ty == MT_BATCHER) bo = clamp_u32(net.models[i].cap, BURST_MAX);
+            if (bi != burst_in[i] || bo != burst_out[i]) changed = true;
+            burst_in[i] = bi;
+            burst_out[i] = bo;
+        }
+        if (!changed) break;
+    }
+    if (!opt.queue_capacity) {  // an explicit simb_config.queue_capacity is taken as given
+        for (size_t i = 0; i < hn.models.size(); i++) {
+            uint32_t want = 0;
+            switch (net.models[i].type) {
+                case MT_GATE:
+                case MT_EXCLUSIVE_GATEWAY: want = burst_in[i]; break;                         // emptied in the step they fill
+                case MT_LOAD_BALANCER:
+                case MT_STOCHASTIC_GATE: want = 2u * burst_in[i]; break;                      // one job leaves per step
+                case MT_BATCHER: want = clamp_u32((uint64_t)net.models[i].cap + burst_in[i] + 8ull, 65535); break;
+                default: break;
+            }
+            if (want > 65535u) want = 65535u;
+            if (want > pm[i].ring_cap) pm[i].ring_cap = want;
+        }
+    }
+
     // ---- routes: (model, out-port) -> connectors in connector order (mod.rs:155-182) -------------
-    uint32_t n_routes = 0, n_outports = 0, pending_bound = 0;
+    uint32_t n_routes = 0, n_outports = 0;
+    uint64_t pending_bound = 0;
     for (size_t i = 0; i < hn.models.size(); i++) {
         SimbModelDesc& md = net.models[i];
         md.out_base = (uint16_t)n_outports;
@@ -685,25 +828,19 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
             }
         }
         net.route_begin[n_outports] = (uint16_t)n_routes;
-        // mailbox bound: messages one firing of this model can emit
+        // mailbox bound: messages one firing of this model can emit = jobs per firing x connectors per port
         uint32_t fan_max = 0;
         for (size_t k = 0; k < hn.models[i].ports_out.size(); k++) {
             uint32_t f = net.route_begin[md.out_base + k + 1] - net.route_begin[md.out_base + k];
             if (f > fan_max) fan_max = f;
         }
-        uint32_t inbound = 0;
-        for (auto& hc : hn.connectors)
-            if (hc.target_id == hn.models[i].id) inbound++;
-        switch (md.type) {
-            case MT_PARALLEL_GATEWAY: pending_bound += fan_total; break;
-            case MT_GATE:
-            case MT_EXCLUSIVE_GATEWAY: pending_bound += fan_max * (inbound ? inbound : 1); break;
-            case MT_BATCHER: pending_bound += fan_max * (md.cap > 64 ? 64 : md.cap); break;
-            default: pending_bound += fan_max; break;
-        }
+        if (md.type == MT_PARALLEL_GATEWAY) pending_bound += fan_total;  // one job on every port
+        else pending_bound += (uint64_t)fan_max * burst_out[i];
     }
     net.n_routes = n_routes;
-    uint32_t mp = opt.max_pending ? opt.max_pending : (pending_bound ? pending_bound : 1);
+    // (the mailbox fill and the sequence number are 8-bit fields: 255 messages in flight per replication at most;
+    // a replication that needs more reports SIMB_ERR_CAPACITY)
+    uint32_t mp = opt.max_pending ? opt.max_pending : (pending_bound ? clamp_u32(pending_bound, 255) : 1);
     if (mp > 255) mp = 255;
     net.max_pending = mp;
 

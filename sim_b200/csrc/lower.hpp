@@ -57,6 +57,10 @@ struct HostNet {
 int lower_network(const char* models_json, const char* connectors_json, const LowerOptions& opt, HostNet* out,
                   std::string* err);
 
+// one random variable (JSON form of Continuous / Boolean / Discrete / Index, random_variable.rs:17-63) lowered into
+// net->models[0] (+ net->wcum); family = SimbFamily
+int lower_random_variable(int family, const char* variable_json, SimbNetDesc* net, std::string* err);
+
 const char* action_name(int action);
 const char* status_name(int status);
 

@@ -37,8 +37,15 @@ enum SimbDistKind : uint8_t {
     DK_LOGNORMAL = 5,  // p0 = mu, p1 = sigma
     DK_WEIBULL = 6,    // p0 = scale, p1 = 1/shape (rand_distr's roles, i.e. the reference's swapped ones)
     DK_BETA = 7,       // p0 = a, p1 = b as rand_distr's Beta keeps them; q0 bit 0: algorithm BC, bit 1: switched_params
+    // the Discrete variables (random_variable.rs:36-50): no built-in model draws them; simb_sample_random_variable does
+    DK_GEOMETRIC = 16,    // p0 = p, p1 = pi = (1-p)^(2^k), q0 = k
+    DK_POISSON = 17,      // p0 = lambda, p1 = exp(-lambda), p2 = ln lambda, q0 = bits of sqrt(2 lambda), q1 = bits of the
+                          // "magic value" lambda ln lambda - log_gamma(1 + lambda)
+    DK_UNIFORM_INT = 18,  // q0 = low, q1 = range, q2 = zone (as Index::Uniform)
     DK_NONE = 255
 };
+// random-variable families of simb_sample_random_variable (the four enums of random_variable.rs:17-63)
+enum SimbFamily : uint32_t { FAM_CONTINUOUS = 0, FAM_BOOLEAN = 1, FAM_DISCRETE = 2, FAM_INDEX = 3 };
 
 // ModelDesc.flags
 #define MF_STORE_RECORDS 1u

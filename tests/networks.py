@@ -289,6 +289,31 @@ def state_injection(store_records=False):
     return models, connectors
 
 
+def batch_bursts(store_records=False):
+    """Bursts larger than the default 16-slot transient queues (the reference's Vecs are unbounded): a Batcher of 20
+    feeds a Gate and, through an ExclusiveGateway, a LoadBalancer; each must take a whole batch in one step."""
+    models = [
+        Model.new("generator", Generator.new(Exp(4.0), None, "job", store_records, None)),
+        Model.new("batcher", Batcher.new("job", "job", 50.0, 20, store_records)),
+        Model.new("gate", Gate.new("job", "activation", "deactivation", "job", store_records)),
+        Model.new("exclusive", ExclusiveGateway.new(["in"], ["a", "b"], IndexRandomVariable.WeightedIndex([3, 1]),
+                                                    store_records, None)),
+        Model.new("balancer", LoadBalancer.new("job", ["p", "q"], store_records)),
+        Model.new("sgate", StochasticGate.new(BooleanRandomVariable.Bernoulli(0.5), "job", "job", store_records, None)),
+        _storage("storage-gate", store_records), _storage("storage-p", store_records), _storage("storage-q", store_records),
+        _storage("storage-s", store_records),
+    ]
+    C = Connector.new
+    connectors = [
+        C("c1", "generator", "batcher", "job", "job"), C("c2", "batcher", "gate", "job", "job"),
+        C("c3", "batcher", "exclusive", "job", "in"), C("c4", "gate", "storage-gate", "job", "store"),
+        C("c5", "exclusive", "balancer", "a", "job"), C("c6", "exclusive", "sgate", "b", "job"),
+        C("c7", "balancer", "storage-p", "p", "store"), C("c8", "balancer", "storage-q", "q", "store"),
+        C("c9", "sgate", "storage-s", "job", "store"),
+    ]
+    return models, connectors
+
+
 def state_injection_tables(store_records=False):
     """`state` blocks of the three table-keeping models (parallel_gateway.rs:47-53, stochastic_gate.rs:50-73,
     stopwatch.rs:66-93): a join that starts with one collection half built and one complete, a stochastic gate
@@ -466,6 +491,6 @@ ALL = {
     "stochastic_gate": stochastic_gate, "batcher": batcher, "stopwatch": stopwatch,
     "processor_from_queue": processor_from_queue, "processor_network": processor_network,
     "generator_passive": generator_passive, "more_variables": more_variables, "beta_variables": beta_variables, "state_injection": state_injection,
-    "state_injection_tables": state_injection_tables, "tandem": tandem, "gateway_network": gateway_network,
+    "state_injection_tables": state_injection_tables, "batch_bursts": batch_bursts, "tandem": tandem, "gateway_network": gateway_network,
     "large_mixed": large_mixed,
 }

@@ -376,3 +376,19 @@ def zig_table(which):
     out = np.zeros(257, np.float64)
     lib().orc_zig_table(which, out.ctypes.data_as(C.POINTER(C.c_double)))
     return out
+
+
+def sample_discrete(kind, n, p=0.0, mn=0, mx=1, rng_kind=0, seed=42, rep=0):
+    """kind: 0 Geometric(p), 1 Poisson(lambda = p), 2 Uniform[mn, mx)"""
+    out = np.zeros(n, np.uint64)
+    used = C.c_uint64()
+    e = lib().orc_sample_discrete(kind, C.c_double(p), C.c_uint64(mn), C.c_uint64(mx), rng_kind, C.c_uint64(seed),
+                                  C.c_uint64(rep), out.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_uint64(n), C.byref(used))
+    return e, out, used.value
+
+
+def thinning_evaluate(coefficients, point):
+    a = (C.c_double * max(1, len(coefficients)))(*coefficients)
+    out = C.c_double()
+    lib().orc_thinning_evaluate(a, C.c_uint64(len(coefficients)), C.c_double(point), C.byref(out))
+    return out.value
