@@ -484,46 +484,187 @@ int simb_post_json(const char* models_json, const char* connectors_json, const s
     return 0;
 }
 
+// Pending messages across Simulation::put (mod.rs:82-85 keeps `messages`; they are strings, matched against the NEW
+// models' ids and ports when delivered, mod.rs:204-216).  The device keeps (content code, route word) pairs resolved
+// against the OLD network, so a put that changes ids, ports, connectors or generator prefixes re-resolves them by
+// name: content codes through the interned names, targets through (target id, target port); a message whose target
+// no longer exists stays in the mailbox and is never delivered, like the reference's.
+namespace {
+struct CarriedMail {
+    std::vector<uint32_t> npend;                  // per replication
+    std::vector<std::vector<uint32_t>> content;   // [slot][replication]
+    std::vector<std::vector<uint32_t>> route;
+    uint32_t max_np = 0;
+};
+int read_mail(simb_sim* s, CarriedMail* cm) {
+    const SimbNetDesc& net = s->hn.desc;
+    const uint64_t n = s->st.n, S = s->st.stride;
+    std::vector<uint32_t> ctl(n);
+    CUDA_TRY(cudaMemcpy(ctl.data(), s->st.w + (uint64_t)net.wrow_ctl * S, n * 4, cudaMemcpyDeviceToHost));
+    cm->npend.resize(n);
+    for (uint64_t r = 0; r < n; r++) {
+        cm->npend[r] = CTL_NPEND(ctl[r]);
+        cm->max_np = std::max(cm->max_np, cm->npend[r]);
+    }
+    cm->content.assign(cm->max_np, std::vector<uint32_t>(n));
+    cm->route.assign(cm->max_np, std::vector<uint32_t>(n));
+    for (uint32_t j = 0; j < cm->max_np; j++) {
+        const uint32_t* c = j < net.pend_tile ? s->st.w + (uint64_t)(net.wrow_pend + 2u * j) * S
+                                              : s->st.mail + (uint64_t)(2u * (j - net.pend_tile)) * S;
+        CUDA_TRY(cudaMemcpy(cm->content[j].data(), c, n * 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(cm->route[j].data(), c + S, n * 4, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+// old -> new (content code, route word); the interned names of `old` must already be interned in `nw` (name_map)
+void remap_mail(const HostNet& old, const HostNet& nw, const std::vector<uint32_t>& name_map, CarriedMail* cm) {
+    // route index of the old network -> route word (without sequence number) in the new one
+    std::vector<uint32_t> route_map(SIMB_MAX_ROUTES, 0);
+    for (uint32_t r = 0; r < old.desc.n_routes; r++) {
+        const HostConnector& oc = old.connectors[old.desc.routes[r].connector];
+        const int tm = nw.find_model(oc.target_id);
+        const uint32_t port = tm < 0 ? SIMB_PORT_UNKNOWN : nw.resolve_in_port(tm, oc.target_port);
+        uint32_t nr = ROUTE_INJECTED;  // no connector of the new network carries it: it renders as an injected message
+        for (uint32_t q = 0; q < nw.desc.n_routes; q++) {
+            const HostConnector& nc = nw.connectors[nw.desc.routes[q].connector];
+            if (nc.source_id == oc.source_id && nc.source_port == oc.source_port && nc.target_id == oc.target_id &&
+                nc.target_port == oc.target_port) {
+                nr = q;
+                break;
+            }
+        }
+        route_map[r] = ROUTE_WORD(tm < 0 ? 0xFF : tm, port, nr, 0);
+    }
+    for (uint32_t j = 0; j < cm->max_np; j++)
+        for (size_t r = 0; r < cm->npend.size(); r++) {
+            if (j >= cm->npend[r]) continue;
+            uint32_t& c = cm->content[j][r];
+            if (c != SIMB_CONTENT_NONE) {
+                const uint32_t pfx = c >> 24;
+                c = ((pfx < name_map.size() ? name_map[pfx] : pfx) << 24) | (c & 0xFFFFFFu);
+            }
+            uint32_t& rw = cm->route[j][r];
+            const uint32_t seq = ROUTE_SEQ(rw);
+            if (ROUTE_R(rw) == ROUTE_INJECTED || ROUTE_R(rw) >= old.desc.n_routes) {  // inject_input: (model, port) by name
+                const uint32_t tgt = ROUTE_TGT(rw);
+                int tm = -1;
+                uint32_t port = SIMB_PORT_UNKNOWN;
+                if (tgt < old.models.size()) {
+                    tm = nw.find_model(old.models[tgt].id);
+                    const uint32_t op = ROUTE_PORT(rw);
+                    if (tm >= 0 && op < old.models[tgt].ports_in.size()) port = nw.resolve_in_port(tm, old.models[tgt].ports_in[op]);
+                }
+                rw = ROUTE_WORD(tm < 0 ? 0xFF : tm, port, ROUTE_INJECTED, seq);
+            } else {
+                rw = route_map[ROUTE_R(rw)] | (seq << 24);
+            }
+        }
+}
+int write_mail(simb_sim* s, const CarriedMail& cm) {
+    const SimbNetDesc& net = s->hn.desc;
+    const uint64_t n = s->st.n, S = s->st.stride;
+    std::vector<uint32_t> ctl(n);
+    CUDA_TRY(cudaMemcpy(ctl.data(), s->st.w + (uint64_t)net.wrow_ctl * S, n * 4, cudaMemcpyDeviceToHost));
+    for (uint64_t r = 0; r < n; r++) {
+        uint32_t np = cm.npend[r], err = CTL_ERR(ctl[r]);
+        if (np > net.max_pending) {  // the new network's mailbox is smaller than what is in flight
+            np = net.max_pending;
+            if (!err) err = SIMB_ERR_CAPACITY;
+        }
+        ctl[r] = CTL_MAKE(err, CTL_EPOCH(ctl[r]), np, CTL_ABSENT(ctl[r]));
+    }
+    CUDA_TRY(cudaMemcpy(s->st.w + (uint64_t)net.wrow_ctl * S, ctl.data(), n * 4, cudaMemcpyHostToDevice));
+    for (uint32_t j = 0; j < cm.max_np && j < net.max_pending; j++) {
+        uint32_t* c = j < net.pend_tile ? s->st.w + (uint64_t)(net.wrow_pend + 2u * j) * S
+                                        : s->st.mail + (uint64_t)(2u * (j - net.pend_tile)) * S;
+        CUDA_TRY(cudaMemcpy(c, cm.content[j].data(), n * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(c + S, cm.route[j].data(), n * 4, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+}  // namespace
+
 int simb_put_json(simb_sim* s, const char* models_json, const char* connectors_json) {
     if (!s) return fail(SIMB_ERR_INVALID_ARGUMENT, "null handle");
     // Simulation::put (mod.rs:82-85): new models (fresh state) and connectors; the clock, the
     // pending messages and the RNG position are kept.
     HostNet hn;
     std::string err;
-    int e = lower_network(models_json, connectors_json, s->opt, &hn, &err);
-    if (e) return fail(e, err);
+    std::vector<uint32_t> name_map;
+    bool same_layout = false, same_meaning = false;
+    CarriedMail cm;
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    LowerOptions opt = s->opt;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        err.clear();
+        int e = lower_network(models_json, connectors_json, opt, &hn, &err);
+        if (e) return fail(e, err);
+        // content names interned so far (generator prefixes, preloaded jobs, injected contents) keep meaning something:
+        // intern them into the new table; name_map[i] = new id of old name i
+        name_map.assign(s->hn.names.size(), 0);
+        bool overflow = false, same_names = true;
+        for (size_t i = 0; i < s->hn.names.size(); i++) {
+            name_map[i] = hn.intern(s->hn.names[i], &overflow);
+            if (name_map[i] != i) same_names = false;
+        }
+        if (overflow) return fail(SIMB_ERR_CAPACITY, "content intern table overflow (more than 255 distinct names)");
+        const SimbNetDesc& o = s->hn.desc;
+        const SimbNetDesc& nw = hn.desc;
+        same_layout = o.n_models == nw.n_models && o.n_connectors == nw.n_connectors &&  // counter arrays
+                      o.n_drows == nw.n_drows && o.n_wrows == nw.n_wrows && o.wrow_pend == nw.wrow_pend &&
+                      o.max_pending == nw.max_pending && o.wrow_rng == nw.wrow_rng && o.drow_time == nw.drow_time &&
+                      o.wrow_ctl == nw.wrow_ctl && o.pend_tile == nw.pend_tile &&
+                      s->hn.ring_w_slots == hn.ring_w_slots && s->hn.ring_d_slots == hn.ring_d_slots &&
+                      s->hn.ring_preload.size() == hn.ring_preload.size();
+        // do the (content, route) words in the mailboxes mean the same thing in the new network?
+        same_meaning = same_layout && same_names && o.n_routes == nw.n_routes && s->hn.connectors.size() == hn.connectors.size();
+        for (size_t i = 0; same_meaning && i < hn.models.size(); i++)
+            same_meaning = s->hn.models[i].id == hn.models[i].id && s->hn.models[i].ports_in == hn.models[i].ports_in;
+        for (size_t i = 0; same_meaning && i < hn.connectors.size(); i++) {
+            const HostConnector &a = s->hn.connectors[i], &b = hn.connectors[i];
+            same_meaning = a.source_id == b.source_id && a.source_port == b.source_port && a.target_id == b.target_id &&
+                           a.target_port == b.target_port;
+        }
+        for (uint32_t r = 0; same_meaning && r < nw.n_routes; r++)
+            same_meaning = o.routes[r].tgt_model == nw.routes[r].tgt_model && o.routes[r].tgt_port == nw.routes[r].tgt_port &&
+                           o.routes[r].connector == nw.routes[r].connector;
+        if (same_meaning || attempt == 1) break;
+        // carry the pending messages over by name; the new mailbox must hold what is in flight (the reference's Vec
+        // has no bound): lower once more with that as the explicit bound if the derived one is smaller
+        if ((e = read_mail(s, &cm))) return e;
+        if (cm.max_np <= hn.desc.max_pending) break;
+        opt.max_pending = cm.max_np;
+    }
+    if (!same_meaning && cm.max_np) remap_mail(s->hn, hn, name_map, &cm);
+    const SimbNetDesc& o = s->hn.desc;
+    const SimbNetDesc& nw = hn.desc;
+    int e = 0;
     {
         json::Parser pm(models_json), pc(connectors_json);
         pm.parse(s->models_doc);
         pc.parse(s->connectors_doc);
     }
-    const SimbNetDesc& o = s->hn.desc;
-    const SimbNetDesc& nw = hn.desc;
-    const bool same_layout = o.n_models == nw.n_models && o.n_connectors == nw.n_connectors &&  // counter arrays
-                             o.n_drows == nw.n_drows && o.n_wrows == nw.n_wrows && o.wrow_pend == nw.wrow_pend &&
-                             o.max_pending == nw.max_pending && o.wrow_rng == nw.wrow_rng &&
-                             s->hn.ring_w_slots == hn.ring_w_slots && s->hn.ring_d_slots == hn.ring_d_slots &&
-                             s->hn.ring_preload.size() == hn.ring_preload.size();
-    CUDA_TRY(cudaSetDevice(s->cfg.device));
     if (!same_layout) {
-        // different shape: keep clock / RNG position only if the rows line up; otherwise start fresh
-        std::vector<double> time(s->st.n);
-        std::vector<uint32_t> rng(s->st.n * (s->rng_kind == 1 ? 4 : 1));
-        CUDA_TRY(cudaMemcpy(time.data(), s->st.d + (uint64_t)o.drow_time * s->st.stride, s->st.n * 8, cudaMemcpyDeviceToHost));
+        // different state layout: the clock and the RNG position move to their new rows (device-to-device)
         const uint32_t rr = s->rng_kind == 1 ? 4 : 1;
-        for (uint32_t k = 0; k < rr; k++)
-            CUDA_TRY(cudaMemcpy(rng.data() + (size_t)k * s->st.n, s->st.w + (uint64_t)(o.wrow_rng + k) * s->st.stride, s->st.n * 4,
-                                cudaMemcpyDeviceToHost));
+        double* t_time = nullptr;
+        uint32_t* t_rng = nullptr;
+        CUDA_TRY(cudaMalloc((void**)&t_time, s->st.stride * 8));
+        CUDA_TRY(cudaMalloc((void**)&t_rng, (size_t)rr * s->st.stride * 4));
+        CUDA_TRY(cudaMemcpy(t_time, s->st.d + (uint64_t)o.drow_time * s->st.stride, s->st.stride * 8, cudaMemcpyDeviceToDevice));
+        CUDA_TRY(cudaMemcpy(t_rng, s->st.w + (uint64_t)o.wrow_rng * s->st.stride, (size_t)rr * s->st.stride * 4, cudaMemcpyDeviceToDevice));
         free_device(s);
         s->hn = hn;
         e = build_device(s, 0, nullptr);
+        if (!e) {
+            const SimbNetDesc& n2 = s->hn.desc;
+            cudaMemcpy(s->st.d + (uint64_t)n2.drow_time * s->st.stride, t_time, s->st.stride * 8, cudaMemcpyDeviceToDevice);
+            cudaMemcpy(s->st.w + (uint64_t)n2.wrow_rng * s->st.stride, t_rng, (size_t)rr * s->st.stride * 4, cudaMemcpyDeviceToDevice);
+        }
+        cudaFree(t_time);
+        cudaFree(t_rng);
         if (e) return e;
-        const SimbNetDesc& n2 = s->hn.desc;
-        CUDA_TRY(cudaMemcpy(s->st.d + (uint64_t)n2.drow_time * s->st.stride, time.data(), s->st.n * 8, cudaMemcpyHostToDevice));
-        for (uint32_t k = 0; k < rr; k++)
-            CUDA_TRY(cudaMemcpy(s->st.w + (uint64_t)(n2.wrow_rng + k) * s->st.stride, rng.data() + (size_t)k * s->st.n, s->st.n * 4,
-                                cudaMemcpyHostToDevice));
-        return 0;
+        return cm.max_np ? write_mail(s, cm) : 0;
     }
     s->hn = hn;
     if ((e = upload_tables(s))) return e;
@@ -546,6 +687,7 @@ int simb_put_json(simb_sim* s, const char* models_json, const char* connectors_j
         CUDA_TRY(cudaMemsetAsync(s->st.conn_count, 0, (size_t)(nw.n_connectors ? nw.n_connectors : 1) * sizeof(unsigned long long), s->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (!same_meaning && cm.max_np) return write_mail(s, cm);
     return 0;
 }
 

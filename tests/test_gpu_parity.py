@@ -10,7 +10,9 @@ import pytest
 
 import networks
 import oracle_api
-from sim_b200 import Message
+from sim_b200 import ContinuousRandomVariable, Message
+
+Exp = ContinuousRandomVariable.Exp
 
 pytestmark = pytest.mark.gpu
 
@@ -637,3 +639,70 @@ def test_streaming_passes_at_full_width(k):
     assert np.array_equal(fused.get_draws(), sim.get_draws())
     for m in models:
         assert np.array_equal(fused.get_until_next_event(m.id), sim.get_until_next_event(m.id), equal_nan=True)
+
+
+# ---- Simulation::put with messages in flight (mod.rs:82-85: `messages` survive, matched by id / port strings) --------
+def _put_case(new_models, new_conns, steps=60, seed=17):
+    """Post M/M/1, inject two messages, put the new network, step; the oracle posts the new network directly and gets
+    the same two messages injected (put keeps them as strings)."""
+    from sim_b200 import Simulation
+    models, conns = networks.mm1()
+    sim = Simulation.post(models, conns, replications=64, seed=seed, instrument=True, trace_replications=2, trace_capacity=4096)
+    sim.inject_input(Message("manual", "manual", "processor-01", "job", 0.0, "x 1"))
+    sim.inject_input(Message("manual", "manual", "storage-01", "store", 0.0, "y 2"))
+    sim.put(new_models, new_conns)
+    pend = [(m.target_id, m.target_port, m.content) for m in sim.get_messages(1)]
+    err = None
+    try:
+        sim.step_n(steps)
+    except Exception as e:  # noqa: BLE001 - the status is compared below
+        err = e.status
+    ref = []
+    for r in range(2):
+        o = oracle_api.OracleSimulation(new_models, new_conns)
+        o.set_rng_philox(seed, r)
+        o.trace_enable(False)
+        o.trace_intern("x 1")   # content codes are handed out in the order the strings are first seen: the engine saw
+        o.trace_intern("y 2")   # them at inject_input
+        o.inject_input("processor-01", "job", "x 1")
+        o.inject_input("storage-01", "store", "y 2")
+        e, _ = o.step_n(steps, collect=False)
+        ref.append((e, o.trace_hash(), o.counters()["steps"], o.get_global_time()))
+    return sim, pend, err, ref
+
+
+def test_put_keeps_pending_messages_when_models_are_reordered():
+    models, conns = networks.mm1()
+    sim, pend, err, ref = _put_case([models[2], models[0], models[1]], conns)
+    assert pend == [("processor-01", "job", "x 1"), ("storage-01", "store", "y 2")] and err is None
+    h, st, t = sim.get_trace_hash(), sim.get_steps(), sim.get_global_time()
+    for r in range(2):
+        assert ref[r][0] == 0 and h[r] == ref[r][1] and st[r] == ref[r][2] and _close(t[r], ref[r][3])
+
+
+def test_put_re_resolves_ports_and_layout_changes():
+    from sim_b200 import Generator, Model, Processor, Storage
+    # (a) the processor's input port is renamed: the pending "job" message now names a port it does not have
+    models = [Model.new("generator-01", Generator.new(Exp(0.5), None, "job", False, None)),
+              Model.new("processor-01", Processor.new(Exp(0.333333), 14, "task", "processed", False, None)),
+              Model.new("storage-01", Storage.new("store", "read", "stored", False))]
+    conns = [networks.Connector.new("connector-01", "generator-01", "processor-01", "job", "task"),
+             networks.Connector.new("connector-02", "processor-01", "storage-01", "processed", "store")]
+    sim, pend, err, ref = _put_case(models, conns)
+    assert ref[0][0] == 7 and err == 7          # InvalidMessage, as the reference's processor raises (processor.rs:225)
+    # (b) a model is added in front (different state layout): the messages follow their targets
+    base, bconns = networks.mm1()
+    models = [Model.new("storage-00", Storage.new("store", "read", "stored", False))] + list(base)
+    sim, pend, err, ref = _put_case(models, bconns)
+    assert pend == [("processor-01", "job", "x 1"), ("storage-01", "store", "y 2")] and err is None
+    h, st = sim.get_trace_hash(), sim.get_steps()
+    for r in range(2):
+        assert ref[r][0] == 0 and h[r] == ref[r][1] and st[r] == ref[r][2]
+    # (c) the target of a pending message is gone: it is never delivered, and the step still is a zero-time one
+    models = [base[0], base[1]]
+    conns = [bconns[0]]
+    sim, pend, err, ref = _put_case(models, conns)
+    assert err is None and ref[0][0] == 0
+    h, st, t = sim.get_trace_hash(), sim.get_steps(), sim.get_global_time()
+    for r in range(2):
+        assert h[r] == ref[r][1] and st[r] == ref[r][2] and _close(t[r], ref[r][3])
