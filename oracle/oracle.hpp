@@ -68,16 +68,17 @@ struct Pcg64Mcg : Rng {
     uint64_t next_u64() override;
 };
 
-// Philox4x32-10 counter stream, one per replication: key = (replication, seed), counter = block.
+// Philox4x32-10 counter stream, one per replication: key = the 64-bit seed, counter = (block, replication).
 // u64 number i is words (2*(i&1), 2*(i&1)+1) of block i>>1.  This is the batched engine's own
 // per-replication source (north_star); the oracle restates it so both sides can run identical
 // replications.
 struct Philox : Rng {
     uint32_t key0, key1;
+    uint64_t rep = 0;
     uint64_t index = 0;
     Philox(uint64_t seed, uint64_t replication);
     uint64_t next_u64() override;
-    static void block(uint32_t key0, uint32_t key1, uint64_t ctr, uint32_t out[4]);
+    static void block(uint32_t key0, uint32_t key1, uint64_t ctr, uint64_t replication, uint32_t out[4]);
     static void block_raw(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 };
 

@@ -60,6 +60,7 @@ struct simb_sim {
     int rng_kind = 0;
     uint64_t passes = 0;        // passes issued (parity = sweep direction)
     bool l2_keep = true;        // SIMB_NO_L2_KEEP = A/B switch
+    int sm_count = 148;         // cudaDevAttrMultiProcessorCount of the handle's device
     bool sweep_reverse = true;  // alternate the sweep direction of consecutive passes (SIMB_NO_REVERSE = A/B switch)
     std::string json;  // result of the last *_json call (handle-owned, see simb.h)
     json::Value models_doc, connectors_doc;  // the documents of the last post / put (simb_get_json re-emits them)
@@ -243,7 +244,8 @@ int first_error(simb_sim* s, uint64_t failed_hint) {
 // small batches (fewer than two full waves of CTAs per grid) are not split
 int grids_per_pass(const simb_sim* s) {
     const uint32_t tiles = (uint32_t)(s->st.stride / s->dims.tile);
-    return tiles >= 2u * 592u * (uint32_t)s->n_lanes ? s->n_lanes : 1;
+    // a grid of fewer than two waves (4 resident CTAs per SM) is not worth splitting
+    return tiles >= 2u * 4u * (uint32_t)s->sm_count * (uint32_t)s->n_lanes ? s->n_lanes : 1;
 }
 // One pass over the batch: the step kernel on every tile, issued as s->n_lanes concurrent grids.  The side
 // streams must have been forked from s->stream (pass_fork) and are joined back by pass_join.
@@ -473,6 +475,10 @@ int simb_post_json(const char* models_json, const char* connectors_json, const s
         if (!ok) return bail(fail(SIMB_ERR_CUDA, "side stream creation failed"));
     }
     ensure_pool(config->device);
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, config->device) == cudaSuccess && sms > 0) s->sm_count = sms;
+    }
     e = build_device(s, 0, nullptr);
     if (e) return bail(e);
     {
@@ -1739,7 +1745,9 @@ int simb_get_batch_means(simb_sim* s, double* mean, double* variance, uint32_t* 
         const double m = b ? sm[r] / (double)b : std::nan("");
         if (batches) batches[r] = b;
         if (mean) mean[r] = m;
-        if (variance) variance[r] = b ? sq[r] / (double)b - m * m : std::nan("");  // population variance, one pass
+        // population variance in one pass over the running sums; cancellation on nearly equal batch means must not
+        // produce a (slightly) negative value, whose square root would poison the interval
+        if (variance) variance[r] = b ? std::max(0.0, sq[r] / (double)b - m * m) : std::nan("");
     }
     return 0;
 }

@@ -141,9 +141,12 @@ struct Lane {
 };
 
 // ---- Philox4x32-10 (Salmon et al. SC'11); one block = two u64 draws -------------------------------
-SIMB_HD void philox_block(uint32_t key0, uint32_t key1, uint32_t ctr_lo, uint64_t* a, uint64_t* b) {
+// key = the 64-bit seed; counter = (block index, 0, global replication index low, high): every (seed, replication)
+// pair has its own stream, with no aliasing between seeds and replication indices.
+SIMB_HD void philox_block(uint32_t key0, uint32_t key1, uint32_t ctr_lo, uint32_t rep_lo, uint32_t rep_hi, uint64_t* a,
+                          uint64_t* b) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-    uint32_t c0 = ctr_lo, c1 = 0u, c2 = 0u, c3 = 0u, k0 = key0, k1 = key1;
+    uint32_t c0 = ctr_lo, c1 = 0u, c2 = rep_lo, c3 = rep_hi, k0 = key0, k1 = key1;
 #pragma unroll
     for (int r = 0; r < 10; r++) {
         uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
@@ -164,12 +167,13 @@ struct U64Pair {
 // out-of-line copy for the rarely taken refill inside next_u64 (arguments and result by value, so the
 // caller's Lane stays in registers)
 #ifdef __CUDACC__
-static __device__ __host__ __noinline__ U64Pair philox_pair_cold(uint32_t key0, uint32_t key1, uint32_t ctr_lo) {
+static __device__ __host__ __noinline__ U64Pair philox_pair_cold(uint32_t key0, uint32_t key1, uint32_t ctr_lo,
+                                                                 uint32_t rep_lo, uint32_t rep_hi) {
 #else
-static inline U64Pair philox_pair_cold(uint32_t key0, uint32_t key1, uint32_t ctr_lo) {
+static inline U64Pair philox_pair_cold(uint32_t key0, uint32_t key1, uint32_t ctr_lo, uint32_t rep_lo, uint32_t rep_hi) {
 #endif
     U64Pair r;
-    philox_block(key0, key1, ctr_lo, &r.a, &r.b);
+    philox_block(key0, key1, ctr_lo, rep_lo, rep_hi, &r.a, &r.b);
     return r;
 }
 
@@ -236,9 +240,12 @@ struct Engine {
     SIMB_HD Engine(const SimbNetDesc& structure, const SimbNetDesc& values, const SimbDevState& s, const Tables& t)
         : net(structure), par(values), st(s), tab(t) {}
 
-    // Philox key of this replication: (global replication index, seed) -- derived on demand, not kept in registers
-    SIMB_HD uint32_t key0(const Lane& ln) const { return (uint32_t)(st.rep_offset + ln.rep); }
-    SIMB_HD uint32_t key1(const Lane& ln) const { return (uint32_t)st.seed + (uint32_t)((st.rep_offset + ln.rep) >> 32); }
+    // Philox key = the seed (warp-uniform), counter words 2 / 3 = the global replication index -- derived on demand,
+    // not kept in registers
+    SIMB_HD uint32_t key0(const Lane&) const { return (uint32_t)st.seed; }
+    SIMB_HD uint32_t key1(const Lane&) const { return (uint32_t)(st.seed >> 32); }
+    SIMB_HD uint32_t rep_lo(const Lane& ln) const { return (uint32_t)(st.rep_offset + ln.rep); }
+    SIMB_HD uint32_t rep_hi(const Lane& ln) const { return (uint32_t)((st.rep_offset + ln.rep) >> 32); }
     // Philox prefetch.  Draw number i is word pair (i & 1) of block i >> 1, so a cache of upcoming draws is a pure
     // prefetch of the stream: nothing of it is persisted, a launch starts with an empty cache.
     //  * generic interpreter: three draws in registers; a lane whose cache is down to one draw refills at the
@@ -272,12 +279,12 @@ struct Engine {
     SIMB_HD void philox_refill(Lane& ln) {
         const uint32_t nxt = ln.draw_idx + ln.ccount;
         uint64_t a, b;
-        philox_block(key0(ln), key1(ln), nxt >> 1, &a, &b);
+        philox_block(key0(ln), key1(ln), nxt >> 1, rep_lo(ln), rep_hi(ln), &a, &b);
         cache_push(ln, nxt, a, b);
     }
     SIMB_HD void philox_refill_cold(Lane& ln) {
         const uint32_t nxt = ln.draw_idx + ln.ccount;
-        const U64Pair p = philox_pair_cold(key0(ln), key1(ln), nxt >> 1);
+        const U64Pair p = philox_pair_cold(key0(ln), key1(ln), nxt >> 1, rep_lo(ln), rep_hi(ln));
         cache_push(ln, nxt, p.a, p.b);
     }
     // the step's converged refill point (every lane of the warp calls it; `live` lanes take part)

@@ -525,11 +525,13 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
                 cap = qc->u;
             }
             p.ring0 = true;
-            if (cap <= 4096) {
+            if (cap <= 65535) {  // honoured exactly (the ring's head / length fields are 16 bits)
                 md.cap = (uint32_t)cap;
                 p.ring_cap = cap ? (uint32_t)cap : 1;
             } else {
-                md.cap = SIMB_CAP_INF;  // never "full"; the device ring raises SIMB_ERR_CAPACITY instead
+                // larger than any device ring, usize::MAX included: the queue is never "full" (no Drop records); the
+                // ring holds simb_config.queue_capacity jobs (default 64) and raises SIMB_ERR_CAPACITY beyond that
+                md.cap = SIMB_CAP_INF;
                 p.ring_cap = qcap;
             }
             p.n_words = 1;  // head|len

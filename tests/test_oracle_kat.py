@@ -90,12 +90,15 @@ def test_philox4x32_10_random123_vectors():
 
 
 def test_philox_stream_layout():
-    # u64 number i of replication r = words (2*(i&1), 2*(i&1)+1) of block i>>1 under key (r, seed)
-    s = O.philox_fill(42, 7, 6)
-    for i in range(6):
-        o = O.philox_block([i >> 1, 0, 0, 0], [7, 42])
-        w = o[0] | (o[1] << 32) if i % 2 == 0 else o[2] | (o[3] << 32)
-        assert int(s[i]) == w
+    # u64 number i of replication r = words (2*(i&1), 2*(i&1)+1) of the block with counter (i>>1, 0, r_lo, r_hi) under
+    # the key (seed_lo, seed_hi): the whole 64-bit seed and the whole 64-bit replication index enter, nothing aliases
+    for seed, rep in ((42, 7), ((5 << 32) | 42, (3 << 32) | 7)):
+        s = O.philox_fill(seed, rep, 6)
+        for i in range(6):
+            o = O.philox_block([i >> 1, 0, rep & 0xffffffff, rep >> 32], [seed & 0xffffffff, seed >> 32])
+            w = o[0] | (o[1] << 32) if i % 2 == 0 else o[2] | (o[3] << 32)
+            assert int(s[i]) == w
+    assert not np.array_equal(O.philox_fill(42, 1 << 32, 4), O.philox_fill(43, 0, 4))
 
 
 def test_ziggurat_tables_match_generated_include_and_upstream_literals():
