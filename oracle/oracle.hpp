@@ -194,6 +194,10 @@ struct Services {
     Tracer* tracer = nullptr;
     int cur_model = -1;
     uint32_t cur_step = 0;
+    // event counters of the running Simulation: a Coupled model counts the events_ext / events_int calls it makes on
+    // its components instead of its own (one event = one transition of an ATOMIC model)
+    uint64_t* n_ext = nullptr;
+    uint64_t* n_int = nullptr;
 };
 
 // ---- DevsModel + Reportable (sim/src/models/model_trait.rs:37-59) ------------------------------
@@ -215,6 +219,24 @@ struct Model {  // sim/src/models/model.rs:13-26
     std::string id;
     std::unique_ptr<ModelBase> inner;
 };
+// Coupled (sim/src/models/coupled.rs): couplings as plain string tuples
+struct ExternalInputCoupling {
+    std::string target_id, source_port, target_port;
+};
+struct ExternalOutputCoupling {
+    std::string source_id, source_port, target_port;
+};
+struct InternalCoupling {
+    std::string source_id, target_id, source_port, target_port;
+};
+std::unique_ptr<ModelBase> make_coupled(const std::vector<std::string>& ports_in, const std::vector<std::string>& ports_out,
+                                        std::vector<Model> components, const std::vector<ExternalInputCoupling>& eic,
+                                        const std::vector<ExternalOutputCoupling>& eoc,
+                                        const std::vector<InternalCoupling>& ic);
+bool is_coupled(const ModelBase* m);
+// trace indices: atomic models are numbered in document order with the components of a Coupled model in its place
+// (the order a flattened network would list them); returns the next free index
+int assign_trace_indices(std::vector<Model>& models, int first);
 
 struct Simulation {  // sim/src/simulator/mod.rs:39-304
     std::vector<Model> models;
@@ -225,6 +247,7 @@ struct Simulation {  // sim/src/simulator/mod.rs:39-304
     Tracer tracer;
     // counters (test instrumentation): one "event" = one events_ext or events_int call
     uint64_t n_steps = 0, n_ext = 0, n_int = 0;
+    std::vector<int> top_trace_index;  // trace index of each top-level model (-1: a Coupled model)
     std::vector<uint64_t> connector_messages;  // per-connector routed message count
 
     Simulation();

@@ -11,12 +11,23 @@
 using namespace orc;
 
 namespace {
+struct CoupledDraft {  // a Coupled model under construction (orc_begin_coupled .. orc_end_coupled)
+    std::string id;
+    std::vector<std::string> ports_in, ports_out;
+    std::vector<Model> components;
+    std::vector<ExternalInputCoupling> eic;
+    std::vector<ExternalOutputCoupling> eoc;
+    std::vector<InternalCoupling> ic;
+};
 struct Handle {
     Simulation sim;
     std::vector<Model> staged_models;
     std::vector<Connector> staged_connectors;
     std::vector<Message> returned;
+    std::vector<CoupledDraft> building;  // innermost last; models are added to its components
 };
+// where orc_add_* / orc_preload_* currently act: the components of the innermost Coupled draft, else the top level
+std::vector<Model>& target(Handle* h) { return h->building.empty() ? h->staged_models : h->building.back().components; }
 std::vector<std::string> split_nl(const char* s) {
     std::vector<std::string> out;
     if (!s || !*s) return out;
@@ -50,7 +61,7 @@ void stage(Handle* h, const char* id, std::unique_ptr<ModelBase> m) {
     Model mod;
     mod.id = id;
     mod.inner = std::move(m);
-    h->staged_models.push_back(std::move(mod));
+    target(h).push_back(std::move(mod));
 }
 std::vector<Model> clone_models(const std::vector<Model>& src) {
     std::vector<Model> out;
@@ -149,34 +160,70 @@ int orc_add_connector(void* h, const char* id, const char* src, const char* tgt,
 }
 int orc_preload_processor(void* hv, const char* id, int active, double until, const char* queue_nl) {
     Handle* h = (Handle*)hv;
-    for (auto& m : h->staged_models)
+    for (auto& m : target(h))
         if (m.id == id) return preload_processor(m.inner.get(), active, until, split_nl(queue_nl));
     return ModelNotFound;
 }
 int orc_preload_state(void* hv, const char* id, int phase, double until, const char* jobs_nl) {
     Handle* h = (Handle*)hv;
-    for (auto& m : h->staged_models)
+    for (auto& m : target(h))
         if (m.id == id) return preload_state(m.inner.get(), phase, until, split_nl(jobs_nl));
     return ModelNotFound;
 }
 int orc_preload_parallel_gateway(void* hv, const char* id, double until, const char* names_nl, const uint64_t* counts) {
     Handle* h = (Handle*)hv;
-    for (auto& m : h->staged_models)
+    for (auto& m : target(h))
         if (m.id == id) return preload_parallel_gateway(m.inner.get(), until, split_nl(names_nl), counts);
     return ModelNotFound;
 }
 int orc_preload_stochastic_gate(void* hv, const char* id, double until, const char* contents_nl, const uint8_t* pass) {
     Handle* h = (Handle*)hv;
-    for (auto& m : h->staged_models)
+    for (auto& m : target(h))
         if (m.id == id) return preload_stochastic_gate(m.inner.get(), until, split_nl(contents_nl), pass);
     return ModelNotFound;
 }
 int orc_preload_stopwatch(void* hv, const char* id, int job_fetch, double until, const char* names_nl, const double* start,
                           const double* stop) {
     Handle* h = (Handle*)hv;
-    for (auto& m : h->staged_models)
+    for (auto& m : target(h))
         if (m.id == id) return preload_stopwatch(m.inner.get(), job_fetch, until, split_nl(names_nl), start, stop);
     return ModelNotFound;
+}
+// Coupled::new (coupled.rs:87-106): the models added between begin and end become its components
+int orc_begin_coupled(void* hv, const char* id, const char* ports_in_nl, const char* ports_out_nl) {
+    Handle* h = (Handle*)hv;
+    CoupledDraft d;
+    d.id = id;
+    d.ports_in = split_nl(ports_in_nl);
+    d.ports_out = split_nl(ports_out_nl);
+    h->building.push_back(std::move(d));
+    return 0;
+}
+int orc_coupled_eic(void* hv, const char* target_id, const char* source_port, const char* target_port) {
+    Handle* h = (Handle*)hv;
+    if (h->building.empty()) return InvalidModelConfiguration;
+    h->building.back().eic.push_back(ExternalInputCoupling{target_id, source_port, target_port});
+    return 0;
+}
+int orc_coupled_eoc(void* hv, const char* source_id, const char* source_port, const char* target_port) {
+    Handle* h = (Handle*)hv;
+    if (h->building.empty()) return InvalidModelConfiguration;
+    h->building.back().eoc.push_back(ExternalOutputCoupling{source_id, source_port, target_port});
+    return 0;
+}
+int orc_coupled_ic(void* hv, const char* source_id, const char* target_id, const char* source_port, const char* target_port) {
+    Handle* h = (Handle*)hv;
+    if (h->building.empty()) return InvalidModelConfiguration;
+    h->building.back().ic.push_back(InternalCoupling{source_id, target_id, source_port, target_port});
+    return 0;
+}
+int orc_end_coupled(void* hv) {
+    Handle* h = (Handle*)hv;
+    if (h->building.empty()) return InvalidModelConfiguration;
+    CoupledDraft d = std::move(h->building.back());
+    h->building.pop_back();
+    stage(h, d.id.c_str(), make_coupled(d.ports_in, d.ports_out, std::move(d.components), d.eic, d.eoc, d.ic));
+    return 0;
 }
 // Simulation::put with fresh clones of the staged models (the reference's replication idiom:
 // reset() + put(models.to_vec(), ..), sim/tests/simulations.rs:162-170)

@@ -8,12 +8,13 @@ Host-side mirror of the reference's Rust API for the accelerated path
 from .coupling import Connector, Message  # noqa: F401
 from .input_modeling import (BooleanRandomVariable, ContinuousRandomVariable, DiscreteRandomVariable,  # noqa: F401
                              IndexRandomVariable, Thinning)
-from .models import (Batcher, ExclusiveGateway, Gate, Generator, LoadBalancer, Metric, Model,  # noqa: F401
-                     ParallelGateway, Passive, Processor, StochasticGate, Stopwatch, Storage)
+from .models import (Batcher, Coupled, ExclusiveGateway, ExternalInputCoupling, ExternalOutputCoupling, Gate,  # noqa: F401
+                     Generator, InternalCoupling, LoadBalancer, Metric, Model, ParallelGateway, Passive, Processor,
+                     StochasticGate, Stopwatch, Storage)
 
 __all__ = [
     "Connector", "Message", "BooleanRandomVariable", "ContinuousRandomVariable", "DiscreteRandomVariable", "IndexRandomVariable", "Thinning",
-    "Batcher", "ExclusiveGateway", "Gate", "Generator", "LoadBalancer", "Metric", "Model", "ParallelGateway",
+    "Batcher", "Coupled", "ExternalInputCoupling", "ExternalOutputCoupling", "InternalCoupling", "ExclusiveGateway", "Gate", "Generator", "LoadBalancer", "Metric", "Model", "ParallelGateway",
     "Passive", "Processor", "StochasticGate", "Stopwatch", "Storage",
 ]
 

@@ -258,6 +258,67 @@ class Passive(_ModelBody):
 
 
 @dataclass
+class ExternalInputCoupling:
+    """coupled.rs:40-47"""
+    target_id: str
+    source_port: str
+    target_port: str
+
+    def to_dict(self):
+        return {"targetID": self.target_id, "sourcePort": self.source_port, "targetPort": self.target_port}
+
+
+@dataclass
+class ExternalOutputCoupling:
+    """coupled.rs:49-56"""
+    source_id: str
+    source_port: str
+    target_port: str
+
+    def to_dict(self):
+        return {"sourceID": self.source_id, "sourcePort": self.source_port, "targetPort": self.target_port}
+
+
+@dataclass
+class InternalCoupling:
+    """coupled.rs:58-67"""
+    source_id: str
+    target_id: str
+    source_port: str
+    target_port: str
+
+    def to_dict(self):
+        return {"sourceID": self.source_id, "targetID": self.target_id, "sourcePort": self.source_port,
+                "targetPort": self.target_port}
+
+
+@dataclass
+class Coupled(_ModelBody):
+    """coupled.rs:14-25; ``Coupled::new(ports_in, ports_out, components, external_input_couplings,
+    external_output_couplings, internal_couplings)`` (:87-106).  Messages between components travel over the internal
+    couplings and are delivered when the coupled model next fires (parked messages, :186-255)."""
+    ports_in: List[str]
+    ports_out: List[str]
+    components: List["Model"]
+    external_input_couplings: List[ExternalInputCoupling]
+    external_output_couplings: List[ExternalOutputCoupling]
+    internal_couplings: List[InternalCoupling]
+    type_name = "Coupled"
+
+    @classmethod
+    def new(cls, ports_in, ports_out, components, external_input_couplings, external_output_couplings, internal_couplings):
+        return cls(list(ports_in), list(ports_out), list(components), list(external_input_couplings),
+                   list(external_output_couplings), list(internal_couplings))
+
+    def fields(self):
+        return {"portsIn": {"flowPaths": list(self.ports_in)}, "portsOut": {"flowPaths": list(self.ports_out)},
+                "components": [c.to_dict() for c in self.components],
+                "externalInputCouplings": [c.to_dict() for c in self.external_input_couplings],
+                "externalOutputCouplings": [c.to_dict() for c in self.external_output_couplings],
+                "internalCouplings": [c.to_dict() for c in self.internal_couplings]}
+
+
+@dataclass
 class Model:
     """``Model`` (sim/src/models/model.rs:13-26): an id plus a boxed model."""
     id: str

@@ -1,9 +1,9 @@
 """Test networks.  The first group restates the networks of the reference's own tests
 (sim/tests/simulations.rs, sim/tests/web.rs, sim/tests/custom.rs; cited per function); the second
 group are the BASELINE.json configurations with the concrete shapes of SURVEY.md 8(d)."""
-from sim_b200 import (Batcher, BooleanRandomVariable, Connector, ContinuousRandomVariable, ExclusiveGateway, Gate,
-                      Generator, IndexRandomVariable, LoadBalancer, Metric, Model, ParallelGateway, Passive, Processor,
-                      StochasticGate, Stopwatch, Storage)
+from sim_b200 import (Batcher, BooleanRandomVariable, Connector, ContinuousRandomVariable, Coupled, ExclusiveGateway,
+                      ExternalInputCoupling, ExternalOutputCoupling, Gate, Generator, IndexRandomVariable, InternalCoupling,
+                      LoadBalancer, Metric, Model, ParallelGateway, Passive, Processor, StochasticGate, Stopwatch, Storage)
 
 Exp = ContinuousRandomVariable.Exp
 
@@ -484,6 +484,67 @@ def large_mixed():
     assert len(models) <= 32, len(models)
     return models, connectors
 
+
+# ---- Coupled models (sim/src/models/coupled.rs, sim/tests/coupled.rs) --------------------------------------
+def coupled_atomic(lam_gen=0.007, lam_proc=0.011):
+    """coupled.rs:15-59: the atomic form of closure_under_coupling"""
+    models = [Model.new("generator-01", Generator.new(Exp(lam_gen), None, "job", False, None)),
+              Model.new("processor-01", Processor.new(Exp(lam_proc), 14, "job", "processed", False, None)),
+              _storage("storage-01")]
+    connectors = [Connector.new("connector-01", "generator-01", "processor-01", "job", "job"),
+                  Connector.new("connector-02", "processor-01", "storage-01", "processed", "store")]
+    return models, connectors
+
+
+def coupled_closure(lam_gen=0.007, lam_proc=0.011, store_records=False):
+    """coupled.rs:60-142: generator and processor inside one Coupled model; the generator's jobs leave on `start`
+    and reach the processor over an internal coupling, the processed jobs leave on `stop`."""
+    comp = [Model.new("generator-01", Generator.new(Exp(lam_gen), None, "job", store_records, None)),
+            Model.new("processor-01", Processor.new(Exp(lam_proc), 14, "job", "processed", store_records, None))]
+    models = [
+        Model.new("coupled-01", Coupled.new([], ["start", "stop"], comp, [],
+                                            [ExternalOutputCoupling("generator-01", "job", "start"),
+                                             ExternalOutputCoupling("processor-01", "processed", "stop")],
+                                            [InternalCoupling("generator-01", "processor-01", "job", "job")])),
+        _storage("storage-02", store_records),
+    ]
+    connectors = [Connector.new("connector-01", "coupled-01", "storage-02", "start", "store"),
+                  Connector.new("connector-02", "coupled-01", "storage-02", "stop", "store")]
+    return models, connectors
+
+
+def coupled_pipeline(store_records=False):
+    """A Coupled model with external INPUT couplings (one in-port fanned out to two components), a zero-time
+    component (load balancer) whose internal message is parked until the next firing, and a second Coupled model
+    downstream: generator -> [balancer -> 2 processors] -> [gate -> batcher] -> storage."""
+    stage = Coupled.new(
+        ["in"], ["out", "seen"],
+        [Model.new("balancer", LoadBalancer.new("job", ["a", "b"], store_records)),
+         Model.new("proc-a", Processor.new(Exp(1.5), 6, "job", "done", store_records, None)),
+         Model.new("proc-b", Processor.new(ContinuousRandomVariable.Uniform(0.2, 0.9), 6, "job", "done", store_records, None)),
+         Model.new("monitor", _storage("x", store_records).inner)],
+        [ExternalInputCoupling("balancer", "in", "job"), ExternalInputCoupling("monitor", "in", "store")],
+        [ExternalOutputCoupling("proc-a", "done", "out"), ExternalOutputCoupling("proc-b", "done", "out"),
+         ExternalOutputCoupling("balancer", "a", "seen")],
+        [InternalCoupling("balancer", "proc-a", "a", "job"), InternalCoupling("balancer", "proc-b", "b", "job")])
+    tail = Coupled.new(
+        ["in"], ["out"],
+        [Model.new("gate", Gate.new("job", "activation", "deactivation", "job", store_records)),
+         Model.new("batcher", Batcher.new("job", "job", 4.0, 3, store_records))],
+        [ExternalInputCoupling("gate", "in", "job")],
+        [ExternalOutputCoupling("batcher", "job", "out")],
+        [InternalCoupling("gate", "batcher", "job", "job")])
+    models = [Model.new("generator", Generator.new(Exp(1.0), None, "job", store_records, None)),
+              Model.new("stage", stage), Model.new("tail", tail), _storage("sink", store_records),
+              _storage("seen", store_records)]
+    C = Connector.new
+    connectors = [C("c1", "generator", "stage", "job", "in"), C("c2", "stage", "tail", "out", "in"),
+                  C("c3", "tail", "sink", "out", "store"), C("c4", "stage", "seen", "seen", "store")]
+    return models, connectors
+
+
+# networks with Coupled models (run by the oracle; the device runs them through the coupled lowering)
+COUPLED = {"coupled_closure": coupled_closure, "coupled_pipeline": coupled_pipeline}
 
 ALL = {
     "mm1": mm1, "generator_storage": generator_storage, "exclusive_gateway": exclusive_gateway,

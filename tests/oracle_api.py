@@ -126,6 +126,17 @@ class OracleSimulation:
                               C.c_uint64(i.max_batch_size), int(i.store_records))
         elif isinstance(i, M.Passive):
             L.orc_add_passive(h, b, _b(i.job_port))
+        elif isinstance(i, M.Coupled):
+            L.orc_begin_coupled(h, b, _b("\n".join(i.ports_in)), _b("\n".join(i.ports_out)))
+            for comp in i.components:
+                self._add(comp)
+            for c in i.external_input_couplings:
+                L.orc_coupled_eic(h, _b(c.target_id), _b(c.source_port), _b(c.target_port))
+            for c in i.external_output_couplings:
+                L.orc_coupled_eoc(h, _b(c.source_id), _b(c.source_port), _b(c.target_port))
+            for c in i.internal_couplings:
+                L.orc_coupled_ic(h, _b(c.source_id), _b(c.target_id), _b(c.source_port), _b(c.target_port))
+            assert L.orc_end_coupled(h) == 0
         else:
             raise TypeError(type(i))
         st = getattr(i, "state", None)
