@@ -212,8 +212,13 @@ enum {
     TF_RING_D,
     TF_CAP,
     TF_PREFIX,
+    TF_GROUP,      // group_base | coupled_of << 8 (Coupled models: the order events_ext runs in, the parked list)
     TF_COUNT
 };
+// flags in the top byte of a route-table word (the byte that becomes the sequence number of a mailbox slot)
+#define RTW_PARK (1u << 24)   /* internal coupling of a Coupled model: the job goes to its parked list */
+#define RTW_CONT (1u << 25)   /* second or later delivery of ONE message to a Coupled model: not traced, not counted */
+#define RTW_CPL(w) (((w) >> 26) & 3u)
 #define SIMB_TAB_ROUTE_BEGIN (TF_COUNT * SIMB_MAX_MODELS)                   /* per out-port: begin | end << 16 */
 #define SIMB_TAB_ROUTES (SIMB_TAB_ROUTE_BEGIN + SIMB_MAX_OUT_PORTS)           /* ROUTE_WORD(tgt, port, r, 0) */
 #define SIMB_TAB_CONN (SIMB_TAB_ROUTES + SIMB_MAX_ROUTES)                        /* connector index of route r */
@@ -236,6 +241,7 @@ inline void build_model_table(const SimbNetDesc& net, uint32_t* tab, uint64_t* v
         tab[TF_RING_D * SIMB_MAX_MODELS + m] = d.ring_d;
         tab[TF_CAP * SIMB_MAX_MODELS + m] = d.cap;
         tab[TF_PREFIX * SIMB_MAX_MODELS + m] = d.prefix;
+        tab[TF_GROUP * SIMB_MAX_MODELS + m] = net.n_coupled ? (net.group_base[m] | ((uint32_t)net.coupled_of[m] << 8)) : (m | (0xFFu << 8));
         const double p[3] = {d.p0, d.p1, d.p2};
         for (int k = 0; k < 3; k++) {
             uint64_t b = 0;
@@ -250,8 +256,10 @@ inline void build_model_table(const SimbNetDesc& net, uint32_t* tab, uint64_t* v
         tab[SIMB_TAB_ROUTE_BEGIN + p] = net.route_begin[p] | ((uint32_t)net.route_begin[p + 1] << 16);
     for (uint32_t r = 0; r < net.n_routes && r < SIMB_MAX_ROUTES; r++)
     {
-        tab[SIMB_TAB_ROUTES + r] = ROUTE_WORD(net.routes[r].tgt_model, net.routes[r].tgt_port, r, 0);
-        tab[SIMB_TAB_CONN + r] = net.routes[r].connector;
+        const uint32_t cf = net.routes[r].connector;
+        tab[SIMB_TAB_ROUTES + r] = ROUTE_WORD(net.routes[r].tgt_model, net.routes[r].tgt_port, r, 0) |
+                                   ((cf & RT_PARK) ? RTW_PARK : 0u) | ((cf & RT_CONT) ? RTW_CONT : 0u) | (RT_CPL(cf) << 26);
+        tab[SIMB_TAB_CONN + r] = RT_CONN(cf);
     }
 }
 

@@ -527,12 +527,12 @@ void remap_mail(const HostNet& old, const HostNet& nw, const std::vector<uint32_
     // route index of the old network -> route word (without sequence number) in the new one
     std::vector<uint32_t> route_map(SIMB_MAX_ROUTES, 0);
     for (uint32_t r = 0; r < old.desc.n_routes; r++) {
-        const HostConnector& oc = old.connectors[old.desc.routes[r].connector];
+        const HostConnector& oc = old.connectors[RT_CONN(old.desc.routes[r].connector)];
         const int tm = nw.find_model(oc.target_id);
         const uint32_t port = tm < 0 ? SIMB_PORT_UNKNOWN : nw.resolve_in_port(tm, oc.target_port);
         uint32_t nr = ROUTE_INJECTED;  // no connector of the new network carries it: it renders as an injected message
         for (uint32_t q = 0; q < nw.desc.n_routes; q++) {
-            const HostConnector& nc = nw.connectors[nw.desc.routes[q].connector];
+            const HostConnector& nc = nw.connectors[RT_CONN(nw.desc.routes[q].connector)];
             if (nc.source_id == oc.source_id && nc.source_port == oc.source_port && nc.target_id == oc.target_id &&
                 nc.target_port == oc.target_port) {
                 nr = q;
@@ -759,12 +759,27 @@ int simb_inject_input(simb_sim* s, const char* target_id, const char* target_por
                       const uint8_t* replica_mask) {
     if (!s || !target_id || !target_port || !content) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
     CUDA_TRY(cudaSetDevice(s->cfg.device));
-    const int tm = s->hn.find_model(target_id);  // unknown target: kept, never delivered (mod.rs:204-216)
     bool overflow = false;
     const uint32_t code = s->hn.content_code(content, &overflow);
     if (overflow) return fail(SIMB_ERR_CAPACITY, "content intern table overflow");
-    const uint32_t port = tm < 0 ? SIMB_PORT_UNKNOWN : s->hn.resolve_in_port(tm, target_port);
-    const uint32_t rw = ROUTE_WORD(tm < 0 ? 0xFF : tm, port, ROUTE_INJECTED, 0);  // the kernel adds the sequence number
+    // deliveries: the named model, or -- for a Coupled model -- the components its external input couplings name for
+    // that port, in coupling order (coupled.rs:102-131); an unknown target is kept and never delivered (mod.rs:204-216)
+    std::vector<uint32_t> words;
+    const int tt = s->hn.find_top(target_id);
+    if (tt >= 0 && s->hn.tops[tt].coupled >= 0) {
+        const int cpl = s->hn.tops[tt].coupled;
+        for (auto& e : s->hn.coupled[cpl].eic) {
+            if (e.source_port != target_port) continue;
+            const int comp = s->hn.find_component(cpl, e.target_id);
+            if (comp < 0) continue;
+            words.push_back(ROUTE_WORD(comp, s->hn.resolve_in_port(comp, e.target_port),
+                                       words.empty() ? ROUTE_INJECTED : ROUTE_INJECTED_CONT, 0));
+        }
+    } else if (tt >= 0) {
+        const int tm = s->hn.tops[tt].flat;
+        words.push_back(ROUTE_WORD(tm, s->hn.resolve_in_port(tm, target_port), ROUTE_INJECTED, 0));
+    }
+    if (words.empty()) words.push_back(ROUTE_WORD(0xFF, SIMB_PORT_UNKNOWN, ROUTE_INJECTED, 0));
     uint8_t* d_mask = nullptr;
     if (replica_mask) {
         CUDA_TRY(cudaMalloc((void**)&d_mask, s->st.n));
@@ -775,7 +790,9 @@ int simb_inject_input(simb_sim* s, const char* target_id, const char* target_por
         }
     }
     cudaMemsetAsync(s->d_overflow, 0, sizeof(unsigned long long), s->stream);
-    int e = engine_launch_inject(s->hn.desc, s->st, code, rw, d_mask, s->d_overflow, s->stream);
+    int e = 0;
+    for (uint32_t rw : words)  // (the kernel adds the sequence number)
+        if (!e) e = engine_launch_inject(s->hn.desc, s->st, code, rw, d_mask, s->d_overflow, s->stream);
     unsigned long long ov = 0;
     cudaMemcpyAsync(&ov, s->d_overflow, sizeof ov, cudaMemcpyDeviceToHost, s->stream);
     cudaError_t ce = cudaStreamSynchronize(s->stream);
@@ -851,19 +868,44 @@ int simb_get_messages(simb_sim* s, uint64_t rep, simb_message* out, uint64_t cap
                      [](const std::pair<uint32_t, uint32_t>& a, const std::pair<uint32_t, uint32_t>& b) {
                          return ROUTE_SEQ(a.second) < ROUTE_SEQ(b.second);
                      });
-    for (uint32_t j = 0; j < np && j < capacity && out; j++) {
+    if (net.n_coupled) {  // one Message to a Coupled model sits in the mailbox once per component it reaches: show it once
+        std::vector<std::pair<uint32_t, uint32_t>> shown;
+        for (auto& mw : mail) {
+            const uint32_t r = ROUTE_R(mw.second);
+            if (r == ROUTE_INJECTED_CONT) continue;
+            if (r != ROUTE_INJECTED && r < net.n_routes && (net.routes[r].connector & RT_CONT)) continue;
+            shown.push_back(mw);
+        }
+        mail.swap(shown);
+        *count = mail.size();
+    }
+    const uint32_t np_shown = (uint32_t)mail.size();
+    for (uint32_t j = 0; j < np_shown && j < capacity && out; j++) {
         const uint32_t content = mail[j].first, rw = mail[j].second;
         simb_message& m = out[j];
         std::memset(&m, 0, sizeof m);
-        const uint32_t conn = ROUTE_R(rw) == ROUTE_INJECTED ? 0xFFFFu : net.routes[ROUTE_R(rw)].connector;
+        const uint32_t conn = ROUTE_R(rw) == ROUTE_INJECTED ? 0xFFFFu : RT_CONN(net.routes[ROUTE_R(rw)].connector);
         if (conn == 0xFFFF) {  // injected: Message::new("manual","manual",..) in the reference's tests
             put_str(m.source_id, sizeof m.source_id, "manual");
             put_str(m.source_port, sizeof m.source_port, "manual");
             const uint32_t tm = ROUTE_TGT(rw);
             if (tm < net.n_models) {
-                put_str(m.target_id, sizeof m.target_id, s->hn.models[tm].id);
+                const HostModel& hm = s->hn.models[tm];
                 const uint32_t p = ROUTE_PORT(rw);
-                if (p < s->hn.models[tm].ports_in.size()) put_str(m.target_port, sizeof m.target_port, s->hn.models[tm].ports_in[p]);
+                const std::string pname = p < hm.ports_in.size() ? hm.ports_in[p] : std::string();
+                if (hm.coupled >= 0) {  // injected into a Coupled model: shown under the model's id and the port whose
+                                        // external input coupling led here
+                    const HostCoupled& hc = s->hn.coupled[hm.coupled];
+                    put_str(m.target_id, sizeof m.target_id, hc.id);
+                    for (auto& ec : hc.eic)
+                        if (ec.target_id == hm.id && ec.target_port == pname) {
+                            put_str(m.target_port, sizeof m.target_port, ec.source_port);
+                            break;
+                        }
+                } else {
+                    put_str(m.target_id, sizeof m.target_id, hm.id);
+                    put_str(m.target_port, sizeof m.target_port, pname);
+                }
             }
         } else if (conn < s->hn.connectors.size()) {
             const HostConnector& c = s->hn.connectors[conn];
@@ -879,9 +921,22 @@ int simb_get_messages(simb_sim* s, uint64_t rep, simb_message* out, uint64_t cap
 }
 int simb_get_status(simb_sim* s, const char* model_id, uint64_t rep, char* out, uint64_t capacity) {
     if (!s || !model_id || !out) return fail(SIMB_ERR_INVALID_ARGUMENT, "null argument");
+    if (rep >= s->st.n) return fail(SIMB_ERR_INVALID_ARGUMENT, "replication index out of range");
+    {
+        const int tt = s->hn.find_top(model_id);
+        if (tt >= 0 && s->hn.tops[tt].coupled >= 0) {  // Coupled::status (coupled.rs:296-302; the branches are the way
+                                                       // round the reference has them)
+            CUDA_TRY(cudaSetDevice(s->cfg.device));
+            std::vector<uint32_t> wc;
+            int ec = column_w(s, rep, &wc);
+            if (ec) return ec;
+            const uint32_t parked = wc[s->hn.desc.coupled[s->hn.tops[tt].coupled].wrow];
+            put_str(out, capacity, parked == 0 ? std::string("Processing 0 messages") : std::string("Processing no messages"));
+            return 0;
+        }
+    }
     const int m = s->hn.find_model(model_id);
     if (m < 0) return fail(SIMB_ERR_MODEL_NOT_FOUND, std::string("no model `") + model_id + "`");  // mod.rs:111
-    if (rep >= s->st.n) return fail(SIMB_ERR_INVALID_ARGUMENT, "replication index out of range");
     CUDA_TRY(cudaSetDevice(s->cfg.device));
     const SimbNetDesc& net = s->hn.desc;
     const SimbModelDesc& md = net.models[m];
@@ -1421,6 +1476,9 @@ int model_state(simb_sim* s, uint64_t rep, uint32_t m, const std::vector<uint32_
 // Simulation { models, connectors, messages, services } (mod.rs:37-45) of one replication
 int simulation_doc(simb_sim* s, uint64_t rep, json::Value* doc) {
     if (rep >= s->st.n) return fail(SIMB_ERR_INVALID_ARGUMENT, "replication index out of range");
+    if (s->hn.desc.n_coupled)
+        return fail(SIMB_ERR_UNSUPPORTED_MODEL, "get_json / get_yaml of a simulation with Coupled models is not implemented "
+                                                "(use simb_get_state for checkpoints)");
     CUDA_TRY(cudaSetDevice(s->cfg.device));
     std::vector<uint32_t> w;
     std::vector<double> d;

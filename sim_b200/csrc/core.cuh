@@ -897,7 +897,7 @@ struct Engine {
                 uint32_t j = i;
                 while (j > 0u) {
                     const uint32_t prev = mail_word(ln, j - 1u, 1);
-                    if (ROUTE_TGT(prev) <= ROUTE_TGT(rw)) break;
+                    if (order_key(ROUTE_TGT(prev)) <= order_key(ROUTE_TGT(rw))) break;
                     mail_word(ln, j, 0) = mail_word(ln, j - 1u, 0);
                     mail_word(ln, j, 1) = prev;
                     j--;
@@ -1345,6 +1345,9 @@ struct Engine {
         // release in progress (events_int of a queueing model): jobs left | REL_* flags, model | absolute out-port << 8,
         // and the job content when it does not come from the model's ring
         uint32_t rel, rel_mp, rel_one;
+        // Coupled models (RARE builds): coupled models that have opened (delivered their parked messages) in this
+        // step, the one delivering now (+1), and the scan position in its parked list (component << 16 | index)
+        uint32_t copen, cdel, cpos;
     };
 #define REL_RING 0x10000u
 #define REL_PORTS 0x20000u
@@ -1355,6 +1358,26 @@ struct Engine {
         pg.nev = 0;
         pg.flush = false;
         pg.rel = pg.rel_mp = pg.rel_one = 0;
+        pg.copen = pg.cdel = pg.cpos = 0;
+    }
+    // ---- Coupled models (sim/src/models/coupled.rs; RARE builds only) ---------------------------------------------
+    // order key of a mailbox slot: events_ext runs over the TOP-LEVEL models in order, so the components of a Coupled
+    // model share their model's place and keep emission order among themselves
+    SIMB_HD uint32_t order_key(uint32_t tgt) const {
+        if (!RARE || STATIC || net.n_coupled == 0u) return tgt;
+        return tgt < SIMB_MAX_MODELS ? (TF(TF_GROUP, tgt) & 0xFFu) : tgt;
+    }
+    // internal coupling: the job waits in the coupled model's parked list (coupled.rs:238-247)
+    SIMB_HD void park(Lane& ln, uint32_t cpl, uint32_t tgt_port, uint32_t content) {
+        const SimbCoupledDesc& cd = net.coupled[cpl];
+        const uint32_t cnt = ln.W(cd.wrow);
+        if (cnt >= cd.ring_cap) {
+            if (!ln.err) ln.err = 32;  // SIMB_ERR_CAPACITY: the reference's Vec is unbounded
+            return;
+        }
+        RW(ln, cd.ring_w0 + cnt) = content;
+        RW(ln, cd.ring_w1 + cnt) = tgt_port;
+        ln.W(cd.wrow) = cnt + 1u;
     }
     // until_next_event[m] := 0 / +INF / p0 / "a fresh variate" (deferred, see flush_draws), keeping the
     // active and imminent masks exact.  false: a distribution parameter error froze the replication.
@@ -1556,16 +1579,22 @@ struct Engine {
     SIMB_HD void emit2(Lane& ln, uint32_t out_port_abs, uint32_t content) {
         const uint32_t be = tab.mt[SIMB_TAB_ROUTE_BEGIN + out_port_abs];
         for (uint32_t r = be & 0xFFFFu; r < (be >> 16); r++) {
+            const uint32_t tw = tab.mt[SIMB_TAB_ROUTES + r];
+            if (RARE && (tw & RTW_PARK)) {  // (before the mailbox bound: a parked job is not a message)
+                park(ln, RTW_CPL(tw), tw & 0xFFFFu, content);
+                continue;
+            }
             if (ln.npend >= net.max_pending) {
                 if (!ln.err) ln.err = 32;  // SIMB_ERR_CAPACITY: mailbox overflow
                 return;
             }
-            const uint32_t rw = tab.mt[SIMB_TAB_ROUTES + r] | (ln.npend << 24);
+            const uint32_t rw = (tw & 0x00FFFFFFu) | (ln.npend << 24);
             // keep the mailbox sorted by target model (stable): the order events_ext runs in (mod.rs:203-221)
             uint32_t j = ln.npend;
+            const uint32_t key = order_key(ROUTE_TGT(rw));
             while (j > 0u) {
                 const uint32_t prev = mail_word(ln, j - 1u, 1);
-                if (ROUTE_TGT(prev) <= ROUTE_TGT(rw)) break;
+                if (order_key(ROUTE_TGT(prev)) <= key) break;
                 mail_word(ln, j, 0) = mail_word(ln, j - 1u, 0);
                 mail_word(ln, j, 1) = prev;
                 j--;
@@ -1573,7 +1602,7 @@ struct Engine {
             mail_word(ln, j, 0) = content;
             mail_word(ln, j, 1) = rw;
             ln.npend++;
-            if (INSTR) {
+            if (INSTR && !(RARE && (tw & RTW_CONT))) {  // one Message of the reference = one trace entry
                 const uint32_t conn = SIMB_LDG(st.tab + SIMB_TAB_CONN + r);
                 ln.hash = (ln.hash ^ TRACE_MESSAGE_WORD(conn, content)) * TRACE_HASH_PRIME;
 #if SIMB_ON_DEVICE
@@ -1758,6 +1787,7 @@ struct Engine {
             pg.nev = 0;
             pg.ei = 0;
             pg.np = ln.npend;
+            pg.copen = 0;
         }
         // ---- one external event: model order, then message order (:202-223) ----
         if (act && pg.stage == 1u && pg.ei < pg.np && !ln.err) {
@@ -1823,8 +1853,61 @@ struct Engine {
                 pg.zmk = ln.zm;
             }
         }
+        // ---- a Coupled model whose turn has come (coupled.rs:186-255): before any of its components fires, its
+        // parked messages are delivered -- component order, then parked order --, the draws they owe are paid, and
+        // the components that are imminent NOW are the ones that fire ----
+        if (RARE && net.n_coupled != 0u && act && !ln.err && pg.rel == 0u && !pg.flush) {
+            if (pg.stage == 2u && pg.zmk) {
+                const uint32_t cpl = TF(TF_GROUP, (uint32_t)lowest_bit(pg.zmk)) >> 8;
+                if (cpl < SIMB_MAX_COUPLED && !(pg.copen & (1u << cpl))) {
+                    pg.copen |= 1u << cpl;
+                    pg.cdel = cpl + 1u;
+                    pg.cpos = (uint32_t)net.coupled[cpl].first << 16;
+                    pg.stage = 3u;
+                }
+            }
+            if (pg.stage == 3u) {
+                const SimbCoupledDesc& cd = net.coupled[pg.cdel - 1u];
+                const uint32_t cnt = ln.W(cd.wrow);
+                uint32_t comp = pg.cpos >> 16, idx = pg.cpos & 0xFFFFu;
+                bool found = false;
+                while (comp < (uint32_t)cd.first + cd.count) {  // next parked message of component `comp`
+                    for (; idx < cnt; idx++)
+                        if ((RW(ln, cd.ring_w1 + idx) & 0xFFu) == comp) {
+                            found = true;
+                            break;
+                        }
+                    if (found) break;
+                    comp++;
+                    idx = 0;
+                }
+                if (found) {
+                    const uint32_t tp = RW(ln, cd.ring_w1 + idx);
+                    if (ext2<INSTR>(ln, comp, (tp >> 8) & 0xFFu, RW(ln, cd.ring_w0 + idx))) {
+                        pg.nev++;
+                        idx++;
+                    } else {
+                        pg.flush = true;  // the component draws inline: pay the earlier draws, then deliver again
+                    }
+                    pg.cpos = (comp << 16) | idx;
+                } else {  // all delivered: the list is emptied (:227); pay what the deliveries owe before looking at
+                          // the components' until_next_event (:231-233)
+                    ln.W(cd.wrow) = 0u;
+                    pg.stage = 4u;
+                    pg.flush = (ln.dm_int | ln.dm_ext) != 0u;
+                }
+            } else if (pg.stage == 4u) {
+                const SimbCoupledDesc& cd = net.coupled[pg.cdel - 1u];
+                const uint32_t mask = (cd.count >= 32u ? 0xFFFFFFFFu : ((1u << cd.count) - 1u)) << cd.first;
+                pg.zmk = (pg.zmk & ~mask) | (ln.zm & mask);
+                pg.cdel = 0;
+                pg.stage = 2u;
+            }
+        }
         // ---- one internal event, in model order (:237-268) ----
-        if (act && pg.stage == 2u && pg.zmk && pg.rel == 0u && !ln.err) {
+        if (act && pg.stage == 2u && pg.zmk && pg.rel == 0u && !ln.err &&
+            !(RARE && net.n_coupled != 0u && (TF(TF_GROUP, (uint32_t)lowest_bit(pg.zmk)) >> 8) < SIMB_MAX_COUPLED &&
+              !(pg.copen & (1u << (TF(TF_GROUP, (uint32_t)lowest_bit(pg.zmk)) >> 8))))) {
             const uint32_t m = (uint32_t)lowest_bit(pg.zmk);
             if (int2<INSTR>(ln, pg, m)) {
                 pg.zmk &= pg.zmk - 1u;
@@ -1836,9 +1919,10 @@ struct Engine {
         // ---- one outgoing job of that event ----
         if (act && pg.rel != 0u && !ln.err) release_one<INSTR>(ln, pg);
         // ---- step end ----
-        if (act && pg.stage == 2u && ((pg.zmk == 0u && pg.rel == 0u) || ln.err)) {
+        if (act && ((pg.stage == 2u && pg.zmk == 0u && pg.rel == 0u) || (pg.stage >= 2u && ln.err))) {
             pg.stage = 0u;
             pg.rel = 0;
+            pg.cdel = 0;
             ln.events += pg.nev;
             if (!ln.err) ln.steps++;
             return true;

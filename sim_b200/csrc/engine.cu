@@ -410,8 +410,9 @@ const char* engine_shape_name(int shape) { return (shape >= 0 && shape < SIMB_N_
 
 int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool instrument, EngineDims* dims) {
     dims->shape = engine_match_shape(net, rng_kind, instrument);
-    dims->rare = uses_rare_variables(net);
-    dims->basic = only_basic_models(net);
+    // (Coupled models need the full interpreter: the lean builds compile their parked-message logic out)
+    dims->rare = uses_rare_variables(net) || net.n_coupled != 0u;
+    dims->basic = only_basic_models(net) && net.n_coupled == 0u;
     // Tile width = replications per CTA.  Pick the width that keeps the most warps resident per SM
     // (shared memory 227 KB, 64 registers per thread -> at most 32 warps, at most 32 CTAs); among equals
     // prefer the wider tile (fewer, larger bulk copies), and keep half of the SM's unified storage for L1

@@ -5,6 +5,7 @@
 // connectors are resolved ONCE into integer routes kept in connector order.
 #include "lower.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -58,7 +59,18 @@ const char* status_name(int s) {
 
 int HostNet::find_model(const std::string& id) const {
     for (size_t i = 0; i < models.size(); i++)
-        if (models[i].id == id) return (int)i;
+        if (models[i].coupled < 0 && models[i].id == id) return (int)i;
+    return -1;
+}
+int HostNet::find_top(const std::string& id) const {
+    for (size_t i = 0; i < tops.size(); i++)
+        if (tops[i].id == id) return (int)i;
+    return -1;
+}
+int HostNet::find_component(int ci, const std::string& id) const {
+    if (ci < 0 || ci >= (int)coupled.size()) return -1;
+    for (int k = coupled[ci].first; k < coupled[ci].first + coupled[ci].count; k++)
+        if (models[k].id == id) return k;
     return -1;
 }
 uint32_t HostNet::intern(const std::string& s, bool* overflow) {
@@ -455,15 +467,72 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
         if (!q.parse(jc)) return c.fail(13, "connectors: " + q.err);
     }
     if (!jm.is_array() || !jc.is_array()) return c.fail(13, "models and connectors must be JSON arrays");
-    if (jm.arr.size() > SIMB_MAX_MODELS) return c.fail(32, "more than 32 models");
     if (jm.arr.empty()) return c.fail(1, "a simulation needs at least one model");
 
     HostNet& hn = *out;
     hn = HostNet();
     SimbNetDesc& net = hn.desc;
     std::memset(&net, 0, sizeof net);
-    net.n_models = (uint32_t)jm.arr.size();
-    std::vector<PendingModel> pm(jm.arr.size());
+    // ---- pass 0: flatten -- the components of a Coupled model (coupled.rs:14-25) take its place in the model list ----
+    struct FlatSrc {
+        const Value* j;
+        int top, coupled;
+    };
+    std::vector<FlatSrc> flat;
+    for (size_t i = 0; i < jm.arr.size(); i++) {
+        const Value& j = jm.arr[i];
+        if (!j.is_object()) return c.fail(13, "model entries must be objects");
+        HostTop top;
+        std::string type;
+        if (!get_str(j, "id", &top.id)) return c.fail(13, "model: missing field `id`");
+        if (!get_str(j, "type", &type)) return c.fail(13, "model " + top.id + ": missing field `type`");
+        if (type != "Coupled") {
+            top.flat = (int)flat.size();
+            flat.push_back(FlatSrc{&j, (int)i, -1});
+            hn.tops.push_back(top);
+            continue;
+        }
+        if (hn.coupled.size() >= SIMB_MAX_COUPLED) return c.fail(32, "more than 4 Coupled models");
+        HostCoupled hc;
+        hc.id = top.id;
+        const Value* pin = j.get("portsIn");
+        const Value* pout = j.get("portsOut");
+        const Value* comps = j.get("components");
+        if (!pin || !pout || !get_str_list(*pin, "flowPaths", &hc.ports_in) || !get_str_list(*pout, "flowPaths", &hc.ports_out))
+            return c.fail(13, hc.id + ": portsIn.flowPaths / portsOut.flowPaths missing");
+        if (!comps || !comps->is_array()) return c.fail(13, hc.id + ": missing field `components`");
+        hc.first = (int)flat.size();
+        for (auto& cj : comps->arr) {
+            std::string ct;
+            if (!cj.is_object() || !get_str(cj, "type", &ct)) return c.fail(13, hc.id + ": component entries must be model objects");
+            if (ct == "Coupled")
+                return c.fail(33, hc.id + ": a Coupled model inside a Coupled model cannot run on the device (one level of coupling is lowered)");
+            flat.push_back(FlatSrc{&cj, (int)i, (int)hn.coupled.size()});
+        }
+        hc.count = (int)flat.size() - hc.first;
+        auto couplings = [&](const char* key, bool has_source, bool has_target, std::vector<HostCoupled::Coupling>* dst) -> bool {
+            const Value* a = j.get(key);
+            if (!a || !a->is_array()) return false;
+            for (auto& e : a->arr) {
+                HostCoupled::Coupling cp;
+                if (!e.is_object() || !get_str(e, "sourcePort", &cp.source_port) || !get_str(e, "targetPort", &cp.target_port)) return false;
+                if (has_source && !get_str(e, "sourceID", &cp.source_id)) return false;
+                if (has_target && !get_str(e, "targetID", &cp.target_id)) return false;
+                dst->push_back(cp);
+            }
+            return true;
+        };
+        if (!couplings("externalInputCouplings", false, true, &hc.eic) || !couplings("externalOutputCouplings", true, false, &hc.eoc) ||
+            !couplings("internalCouplings", true, true, &hc.ic))
+            return c.fail(13, hc.id + ": externalInputCouplings / externalOutputCouplings / internalCouplings missing or malformed");
+        top.coupled = (int)hn.coupled.size();
+        hn.coupled.push_back(hc);
+        hn.tops.push_back(top);
+    }
+    if (flat.size() > SIMB_MAX_MODELS) return c.fail(32, "more than 32 models");
+    if (flat.empty()) return c.fail(1, "a simulation needs at least one atomic model");
+    net.n_models = (uint32_t)flat.size();
+    std::vector<PendingModel> pm(flat.size());
     uint32_t n_wcum = 0;
     const uint32_t qcap = opt.queue_capacity ? clamp_u32(opt.queue_capacity, 65535) : 64;
     // transient queues (LoadBalancer, Gate, gateways: they drain within a step or two) default to 16
@@ -472,10 +541,12 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
     bool overflow = false;
 
     // ---- pass 1: models -------------------------------------------------------------------------
-    for (size_t i = 0; i < jm.arr.size(); i++) {
-        const Value& j = jm.arr[i];
+    for (size_t i = 0; i < flat.size(); i++) {
+        const Value& j = *flat[i].j;
         if (!j.is_object()) return c.fail(13, "model entries must be objects");
         HostModel hm;
+        hm.top = flat[i].top;
+        hm.coupled = flat[i].coupled;
         if (!get_str(j, "id", &hm.id)) return c.fail(13, "model: missing field `id`");
         if (!get_str(j, "type", &hm.type)) return c.fail(13, "model " + hm.id + ": missing field `type`");
         if (const Value* sr = j.get("storeRecords")) hm.store_records = sr->kind == Value::Bool && sr->b;
@@ -739,16 +810,26 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
             md.type = MT_PASSIVE;
             if (pin && pin->is_object()) port(pin, "job", &hm.ports_in);
         } else {
-            return c.fail(33, "model type `" + t + "` cannot run on the device (custom and Coupled models are out of scope)");
+            return c.fail(33, "model type `" + t + "` cannot run on the device (custom models are out of scope)");
         }
         md.n_in = (uint8_t)(hm.ports_in.size() > 254 ? 254 : hm.ports_in.size());
         md.n_out = (uint8_t)hm.ports_out.size();
         if (hm.ports_out.size() > 64) return c.fail(32, hm.id + ": too many output ports");
         hn.models.push_back(hm);
     }
-    for (size_t i = 0; i < hn.models.size(); i++)
-        for (size_t k = i + 1; k < hn.models.size(); k++)
-            if (hn.models[i].id == hn.models[k].id) return c.fail(1, "duplicate model id `" + hn.models[i].id + "`");
+    for (size_t i = 0; i < hn.tops.size(); i++)
+        for (size_t k = i + 1; k < hn.tops.size(); k++)
+            if (hn.tops[i].id == hn.tops[k].id) return c.fail(1, "duplicate model id `" + hn.tops[i].id + "`");
+    for (auto& hc : hn.coupled)
+        for (int i = hc.first; i < hc.first + hc.count; i++)
+            for (int k = i + 1; k < hc.first + hc.count; k++)
+                if (hn.models[i].id == hn.models[k].id) return c.fail(1, hc.id + ": duplicate component id `" + hn.models[i].id + "`");
+    net.n_coupled = (uint32_t)hn.coupled.size();
+    for (size_t i = 0; i < hn.models.size(); i++) {
+        const int cp = hn.models[i].coupled;
+        net.coupled_of[i] = cp < 0 ? 0xFF : (uint8_t)cp;
+        net.group_base[i] = cp < 0 ? (uint8_t)i : (uint8_t)hn.coupled[cp].first;
+    }
 
     // ---- connectors (coupling.rs:7-17) ----------------------------------------------------------
     for (auto& j : jc.arr) {
@@ -762,20 +843,97 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
     if (hn.connectors.size() > 0xFFFE) return c.fail(32, "too many connectors");
     net.n_connectors = (uint32_t)hn.connectors.size();
 
+    // ---- routes: (model, out-port) -> deliveries, in the reference's order (mod.rs:155-182, coupled.rs:133-164) -------
+    uint32_t n_routes = 0, n_outports = 0;
+    bool bad_eic = false;
+    auto push_route = [&](int tgt, uint32_t port, uint32_t conn) -> bool {
+        if (n_routes >= SIMB_MAX_ROUTES) return false;
+        SimbRoute r;
+        r.tgt_model = tgt < 0 ? 0xFF : (uint8_t)tgt;  // unknown target: never delivered, but it still makes the next
+                                                      // step a zero-time one
+        r.tgt_port = tgt < 0 ? SIMB_PORT_UNKNOWN : (uint8_t)port;
+        r.connector = (uint16_t)conn;
+        net.routes[n_routes++] = r;
+        return true;
+    };
+    // the deliveries of one message over top-level connector ci: one model, or -- for a Coupled target -- every
+    // component its external input couplings name for that port, in coupling order (coupled.rs:102-131, 166-184)
+    auto send_over = [&](size_t ci) -> bool {
+        const HostConnector& hc = hn.connectors[ci];
+        const int tt = hn.find_top(hc.target_id);
+        if (tt >= 0 && hn.tops[tt].coupled >= 0) {
+            const int cpl = hn.tops[tt].coupled;
+            uint32_t k = 0;
+            for (auto& e : hn.coupled[cpl].eic) {
+                if (e.source_port != hc.target_port) continue;
+                const int comp = hn.find_component(cpl, e.target_id);
+                if (comp < 0) {
+                    bad_eic = true;  // the reference unwraps a None here (coupled.rs:173-176)
+                    return false;
+                }
+                if (!push_route(comp, hn.resolve_in_port(comp, e.target_port), (uint32_t)ci | (k ? RT_CONT : 0u))) return false;
+                k++;
+            }
+            if (k == 0) return push_route(-1, 0, (uint32_t)ci);  // no coupling takes that port: the message evaporates
+            return true;
+        }
+        const int tm = tt >= 0 ? hn.tops[tt].flat : -1;
+        return push_route(tm, tm < 0 ? 0u : hn.resolve_in_port(tm, hc.target_port), (uint32_t)ci);
+    };
+    for (size_t i = 0; i < hn.models.size(); i++) {
+        SimbModelDesc& md = net.models[i];
+        md.out_base = (uint16_t)n_outports;
+        for (size_t k = 0; k < hn.models[i].ports_out.size(); k++) {
+            if (n_outports >= SIMB_MAX_OUT_PORTS) return c.fail(32, "too many output ports in the network");
+            net.route_begin[n_outports++] = (uint16_t)n_routes;
+            const std::string& pname = hn.models[i].ports_out[k];
+            bool ok = true;
+            if (hn.models[i].coupled < 0) {
+                for (size_t ci = 0; ci < hn.connectors.size() && ok; ci++)
+                    if (hn.connectors[ci].source_id == hn.models[i].id && hn.connectors[ci].source_port == pname) ok = send_over(ci);
+            } else {
+                const int cpl = hn.models[i].coupled;
+                const HostCoupled& C = hn.coupled[cpl];
+                for (auto& ic : C.ic) {  // internal couplings: parked until the coupled model next fires (:238-247)
+                    if (!ok || ic.source_id != hn.models[i].id || ic.source_port != pname) continue;
+                    const int comp = hn.find_component(cpl, ic.target_id);
+                    if (comp < 0) return c.fail(1, C.id + ": internal coupling names the unknown component `" + ic.target_id + "`");
+                    ok = push_route(comp, hn.resolve_in_port(comp, ic.target_port), RT_PARK | ((uint32_t)cpl << 12));
+                }
+                for (auto& eo : C.eoc) {  // external output couplings, then the connectors of the coupled model (:248-252)
+                    if (eo.source_id != hn.models[i].id || eo.source_port != pname) continue;
+                    for (size_t ci = 0; ci < hn.connectors.size() && ok; ci++)
+                        if (hn.connectors[ci].source_id == C.id && hn.connectors[ci].source_port == eo.target_port) ok = send_over(ci);
+                }
+            }
+            if (bad_eic) return c.fail(1, "an external input coupling names a component its Coupled model does not have");
+            if (!ok) return c.fail(32, "too many routes");
+        }
+        net.route_begin[n_outports] = (uint16_t)n_routes;
+    }
+    net.n_routes = n_routes;
+
     // ---- bursts: the largest number of jobs a model can send on one port / receive in ONE step ---------
     // Most models send one job per firing; a Gate or an ExclusiveGateway sends everything that arrived in the step, a
-    // Batcher a whole batch.  Propagated along the connectors to a fixed point (cycles: clamped), these bounds size the
+    // Batcher a whole batch.  Propagated along the routes to a fixed point (cycles: clamped), these bounds size the
     // transient queues and the mailbox, so that e.g. Batcher(20) -> Gate -> Storage runs as it does in the reference
     // (whose Vecs are unbounded) instead of overflowing a 16-slot ring.
     const uint32_t BURST_MAX = 4096;
     std::vector<uint32_t> burst_out(hn.models.size(), 1u), burst_in(hn.models.size(), 0u);
+    auto route_source = [&](uint32_t r) -> int {
+        for (size_t i = 0; i < hn.models.size(); i++) {
+            const SimbModelDesc& md = net.models[i];
+            if (r >= net.route_begin[md.out_base] && r < net.route_begin[md.out_base + md.n_out]) return (int)i;
+        }
+        return -1;
+    };
     for (size_t pass = 0; pass < hn.models.size() + 2; pass++) {
         bool changed = false;
         for (size_t i = 0; i < hn.models.size(); i++) {
             uint64_t in = 0;
-            for (auto& hc : hn.connectors)
-                if (hc.target_id == hn.models[i].id) {
-                    const int sm = hn.find_model(hc.source_id);
+            for (uint32_t r = 0; r < n_routes; r++)
+                if (net.routes[r].tgt_model == i) {
+                    const int sm = route_source(r);
                     if (sm >= 0) in += burst_out[sm];
                 }
             const uint32_t bi = clamp_u32(in, BURST_MAX);
@@ -804,42 +962,27 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
             if (want > pm[i].ring_cap) pm[i].ring_cap = want;
         }
     }
-
-    // ---- routes: (model, out-port) -> connectors in connector order (mod.rs:155-182) -------------
-    uint32_t n_routes = 0, n_outports = 0;
+    // mailbox bound: messages one firing of a model can emit = jobs per firing x deliveries per port (a
+    // ParallelGateway sends one job on every port); parked messages of a Coupled model: the same sum over its
+    // internal couplings
     uint64_t pending_bound = 0;
+    std::vector<uint64_t> park_bound(hn.coupled.size(), 0);
     for (size_t i = 0; i < hn.models.size(); i++) {
-        SimbModelDesc& md = net.models[i];
-        md.out_base = (uint16_t)n_outports;
-        uint32_t fan_total = 0;
-        for (size_t k = 0; k < hn.models[i].ports_out.size(); k++) {
-            if (n_outports >= SIMB_MAX_OUT_PORTS) return c.fail(32, "too many output ports in the network");
-            net.route_begin[n_outports++] = (uint16_t)n_routes;
-            for (size_t ci = 0; ci < hn.connectors.size(); ci++) {
-                const HostConnector& hc = hn.connectors[ci];
-                if (hc.source_id != hn.models[i].id || hc.source_port != hn.models[i].ports_out[k]) continue;
-                if (n_routes >= SIMB_MAX_ROUTES) return c.fail(32, "too many routes");
-                int tm = hn.find_model(hc.target_id);
-                SimbRoute r;
-                r.tgt_model = tm < 0 ? 0xFF : (uint8_t)tm;  // unknown target: never delivered, but it
-                                                            // still makes the next step zero-time
-                r.tgt_port = tm < 0 ? SIMB_PORT_UNKNOWN : (uint8_t)hn.resolve_in_port(tm, hc.target_port);
-                r.connector = (uint16_t)ci;
-                net.routes[n_routes++] = r;
-                fan_total++;
-            }
+        const SimbModelDesc& md = net.models[i];
+        uint64_t send_max = 0, send_total = 0, park_max = 0, park_total = 0;
+        for (uint32_t k = 0; k < md.n_out; k++) {
+            uint64_t sends = 0, parks = 0;
+            for (uint32_t r = net.route_begin[md.out_base + k]; r < net.route_begin[md.out_base + k + 1]; r++)
+                (net.routes[r].connector & RT_PARK) ? parks++ : sends++;
+            send_max = std::max(send_max, sends);
+            park_max = std::max(park_max, parks);
+            send_total += sends;
+            park_total += parks;
         }
-        net.route_begin[n_outports] = (uint16_t)n_routes;
-        // mailbox bound: messages one firing of this model can emit = jobs per firing x connectors per port
-        uint32_t fan_max = 0;
-        for (size_t k = 0; k < hn.models[i].ports_out.size(); k++) {
-            uint32_t f = net.route_begin[md.out_base + k + 1] - net.route_begin[md.out_base + k];
-            if (f > fan_max) fan_max = f;
-        }
-        if (md.type == MT_PARALLEL_GATEWAY) pending_bound += fan_total;  // one job on every port
-        else pending_bound += (uint64_t)fan_max * burst_out[i];
+        const bool pg = md.type == MT_PARALLEL_GATEWAY;
+        pending_bound += pg ? send_total : send_max * burst_out[i];
+        if (hn.models[i].coupled >= 0) park_bound[hn.models[i].coupled] += pg ? park_total : park_max * burst_out[i];
     }
-    net.n_routes = n_routes;
     // (the mailbox fill and the sequence number are 8-bit fields: 255 messages in flight per replication at most;
     // a replication that needs more reports SIMB_ERR_CAPACITY)
     uint32_t mp = opt.max_pending ? opt.max_pending : (pending_bound ? clamp_u32(pending_bound, 255) : 1);
@@ -890,6 +1033,7 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
             dr += (uint16_t)pm[i].n_dwords;
         }
     }
+    for (size_t k = 0; k < hn.coupled.size(); k++) net.coupled[k].wrow = wr++;  // parked-message count
     net.wrow_pend = wr;
     net.pend_tile = (uint16_t)(net.max_pending < SIMB_MAIL_TILE_SLOTS ? net.max_pending : SIMB_MAIL_TILE_SLOTS);
     wr += (uint16_t)(2 * net.pend_tile);
@@ -913,6 +1057,17 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
             md.ring_d = rd;
             rd += md.ring_cap;
         }
+    }
+    for (size_t k = 0; k < hn.coupled.size(); k++) {  // parked messages: (content, target component | port << 8)
+        SimbCoupledDesc& cd = net.coupled[k];
+        cd.first = (uint8_t)hn.coupled[k].first;
+        cd.count = (uint8_t)hn.coupled[k].count;
+        // what one firing parks stays until the next firing, which first delivers it: twice the per-firing bound
+        cd.ring_cap = opt.queue_capacity ? tcap : clamp_u32(std::max<uint64_t>(16, 2 * park_bound[k]), 65535);
+        cd.ring_w0 = rw;
+        rw += cd.ring_cap;
+        cd.ring_w1 = rw;
+        rw += cd.ring_cap;
     }
     hn.ring_w_slots = rw;
     hn.ring_d_slots = rd;

@@ -22,6 +22,24 @@ struct HostModel {
     std::string id, type;
     std::vector<std::string> ports_in, ports_out;
     bool store_records = false;
+    int top = -1;      // index of the top-level entry (HostNet::tops) it is or belongs to
+    int coupled = -1;  // index into HostNet::coupled when it is a component of a Coupled model
+};
+// a Coupled model of the posted document (sim/src/models/coupled.rs:14-67)
+struct HostCoupled {
+    std::string id;
+    std::vector<std::string> ports_in, ports_out;
+    int first = 0, count = 0;  // its components in HostNet::models
+    struct Coupling {
+        std::string source_id, target_id, source_port, target_port;
+    };
+    std::vector<Coupling> eic, eoc, ic;  // external input (target_id, source_port, target_port), external output
+                                         // (source_id, source_port, target_port), internal
+};
+struct HostTop {  // one entry of the posted model list
+    std::string id;
+    int flat = -1;     // its model when atomic
+    int coupled = -1;  // its HostCoupled otherwise
 };
 struct HostConnector {
     std::string id, source_id, target_id, source_port, target_port;
@@ -35,7 +53,9 @@ struct RingPreload {
 
 struct HostNet {
     SimbNetDesc desc;
-    std::vector<HostModel> models;
+    std::vector<HostModel> models;  // the atomic models, flattened (components in place of their Coupled model)
+    std::vector<HostTop> tops;
+    std::vector<HostCoupled> coupled;
     std::vector<HostConnector> connectors;
     std::vector<std::string> names;       // content intern table (prefixes and literals)
     std::vector<double> d_init;           // initial value of every f64 row
@@ -44,7 +64,9 @@ struct HostNet {
     uint32_t ring_w_slots = 0, ring_d_slots = 0;
     int stat_model = -1;
 
-    int find_model(const std::string& id) const;
+    int find_model(const std::string& id) const;  // a TOP-LEVEL atomic model (what Simulation::get_status etc. can name)
+    int find_top(const std::string& id) const;
+    int find_component(int coupled_index, const std::string& id) const;  // flat index, or -1
     uint32_t intern(const std::string& s, bool* overflow);
     // canonical content code of an arbitrary string (DESIGN.md "content codes")
     uint32_t content_code(const std::string& content, bool* overflow);

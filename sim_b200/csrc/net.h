@@ -83,7 +83,24 @@ struct SimbModelDesc {
 struct SimbRoute {
     uint8_t tgt_model;
     uint8_t tgt_port;     // index among the target's input ports, SIMB_PORT_UNKNOWN if absent
-    uint16_t connector;   // connector index (0xFFFF for injected messages)
+    uint16_t connector;   // connector index (RT_CONN) and, for networks with Coupled models, the RT_* flags
+};
+// Coupled models (sim/src/models/coupled.rs) are lowered into the flat model list: components sit where the coupled
+// model stood, and its couplings become routes.  A component's out-port route is either a top-level message (over an
+// external output coupling and a connector; a Coupled TARGET is expanded over its external input couplings, the
+// second and later copies flagged RT_CONT: one Message of the reference, several deliveries) or RT_PARK: an internal
+// coupling, kept in the coupled model's parked list until that model next fires (coupled.rs:186-255).
+#define RT_CONN(c) ((c) & 0x0FFFu)
+#define RT_CPL(c) (((c) >> 12) & 3u)
+#define RT_CONT 0x4000u
+#define RT_PARK 0x8000u
+#define SIMB_MAX_COUPLED 4
+struct SimbCoupledDesc {
+    uint8_t first, count;  // its components: flat models [first, first + count)
+    uint16_t wrow;         // u32 state row: number of parked messages
+    uint32_t ring_cap;     // parked-message slots
+    uint32_t ring_w0;      // ring_w slots: content
+    uint32_t ring_w1;      // ring_w slots: target component | input port << 8
 };
 
 struct SimbNetDesc {
@@ -112,6 +129,12 @@ struct SimbNetDesc {
     uint16_t route_begin[SIMB_MAX_OUT_PORTS + 1];
     SimbRoute routes[SIMB_MAX_ROUTES];
     uint64_t wcum[SIMB_MAX_WEIGHTS];
+    // Coupled models (appended: the baked shapes' aggregate initialisers leave these zero)
+    uint32_t n_coupled;
+    SimbCoupledDesc coupled[SIMB_MAX_COUPLED];
+    uint8_t group_base[SIMB_MAX_MODELS];  // flat index of the first model of the top-level entry a model belongs to
+                                          // (itself for an atomic top-level model): the order events_ext runs in
+    uint8_t coupled_of[SIMB_MAX_MODELS];  // coupled model a component belongs to, 0xFF for a top-level atomic model
 };
 
 // ctl word fields
@@ -128,6 +151,7 @@ struct SimbNetDesc {
 // the order events_ext is called in (mod.rs:203-221); the sequence number restores the reference's message
 // order for get_messages.
 #define ROUTE_INJECTED 0xFFu
+#define ROUTE_INJECTED_CONT 0xFEu /* further deliveries of one injected message to a Coupled model (not shown) */
 #define ROUTE_WORD(tgt, port, r, seq) \
     (((uint32_t)(tgt) & 0xFFu) | (((uint32_t)(port) & 0xFFu) << 8) | (((uint32_t)(r) & 0xFFu) << 16) | (((uint32_t)(seq) & 0xFFu) << 24))
 #define ROUTE_TGT(w) ((w) & 0xFFu)

@@ -63,6 +63,14 @@ int main(int argc, char** argv) {
     for (int i = 0; i < SIMB_MAX_ROUTES; i++) std::printf("{%u,%u,%u},", n.routes[i].tgt_model, n.routes[i].tgt_port, n.routes[i].connector);
     std::printf("},\n {");
     for (int i = 0; i < SIMB_MAX_WEIGHTS; i++) std::printf("%lluull,", (unsigned long long)n.wcum[i]);
+    std::printf("},\n %uu, {", n.n_coupled);
+    for (int i = 0; i < SIMB_MAX_COUPLED; i++)
+        std::printf("{%u,%u,%u,%uu,%uu,%uu},", n.coupled[i].first, n.coupled[i].count, n.coupled[i].wrow, n.coupled[i].ring_cap,
+                    n.coupled[i].ring_w0, n.coupled[i].ring_w1);
+    std::printf("},\n {");
+    for (int i = 0; i < SIMB_MAX_MODELS; i++) std::printf("%u,", n.group_base[i]);
+    std::printf("},\n {");
+    for (int i = 0; i < SIMB_MAX_MODELS; i++) std::printf("%u,", n.coupled_of[i]);
     std::printf("}}\n");
     return 0;
 }

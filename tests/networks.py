@@ -543,7 +543,6 @@ def coupled_pipeline(store_records=False):
     return models, connectors
 
 
-# networks with Coupled models (run by the oracle; the device runs them through the coupled lowering)
 COUPLED = {"coupled_closure": coupled_closure, "coupled_pipeline": coupled_pipeline}
 
 ALL = {
@@ -553,5 +552,5 @@ ALL = {
     "processor_from_queue": processor_from_queue, "processor_network": processor_network,
     "generator_passive": generator_passive, "more_variables": more_variables, "beta_variables": beta_variables, "state_injection": state_injection,
     "state_injection_tables": state_injection_tables, "batch_bursts": batch_bursts, "tandem": tandem, "gateway_network": gateway_network,
-    "large_mixed": large_mixed,
+    "large_mixed": large_mixed, "coupled_closure": coupled_closure, "coupled_pipeline": coupled_pipeline,
 }

@@ -81,8 +81,15 @@ def test_no_cpu_fallback():
 def test_lowering_errors_come_before_the_device_check():
     from sim_b200 import Simulation, SimulationError
     with pytest.raises(SimulationError) as ei:
-        Simulation.post_json("[{\"id\": \"c\", \"type\": \"Coupled\"}]", "[]", 1)
-    assert ei.value.name == "UnsupportedModel"
+        Simulation.post_json("[{\"id\": \"c\", \"type\": \"MyCustomModel\"}]", "[]", 1)
+    assert ei.value.name == "UnsupportedModel"   # custom (sim_derive) models cannot run on the device
+    nested = {"id": "outer", "type": "Coupled", "portsIn": {"flowPaths": []}, "portsOut": {"flowPaths": []},
+              "components": [{"id": "inner", "type": "Coupled"}], "externalInputCouplings": [],
+              "externalOutputCouplings": [], "internalCouplings": []}
+    import json
+    with pytest.raises(SimulationError) as ei:
+        Simulation.post_json(json.dumps([nested]), "[]", 1)
+    assert ei.value.name == "UnsupportedModel"   # one level of coupling is lowered; nesting is refused explicitly
 
 
 def test_product_does_not_reference_the_oracle():

@@ -32,8 +32,8 @@ def test_field_order_is_irrelevant_and_unknown_fields_are_ignored():
 
 
 @pytest.mark.parametrize("doc,status", [
-    ("[{\"id\": \"x\", \"type\": \"Coupled\"}]", 33),           # out of scope: SIMB_ERR_UNSUPPORTED_MODEL
-    ("[{\"id\": \"x\", \"type\": \"MyCustomModel\"}]", 33),
+    ("[{\"id\": \"x\", \"type\": \"MyCustomModel\"}]", 33),     # custom models: SIMB_ERR_UNSUPPORTED_MODEL
+    ("[{\"id\": \"x\", \"type\": \"Coupled\"}]", 13),           # a Coupled model needs its ports, components and couplings
     ("[{\"id\": \"x\"}]", 13),                                   # missing field `type`
     ("[{\"id\": \"g\", \"type\": \"Generator\", \"portsIn\": {}, \"portsOut\": {\"job\": \"job\"}}]", 13),
     ("[{\"id\": \"g\", \"type\": \"Generator\", \"portsIn\": {}, \"portsOut\": {\"job\": \"job\"}, "
@@ -68,7 +68,9 @@ def test_every_network_fits_the_descriptor():
     for name, f in networks.ALL.items():
         models, conns = f()
         lay = H.HostSim(models, conns, n=1).layout()
-        assert lay["n_models"] == len(models) and lay["n_connectors"] == len(conns), name
+        # (the components of a Coupled model take its place in the device's model list)
+        atomic = sum(len(m.inner.components) if m.inner.type_name == "Coupled" else 1 for m in models)
+        assert lay["n_models"] == atomic and lay["n_connectors"] == len(conns), name
 
 
 def test_yaml_documents_of_the_reference_lower_like_their_json_form():
