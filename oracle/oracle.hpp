@@ -204,6 +204,13 @@ struct Services {
 struct ModelBase {
     bool store_records = false;
     std::vector<ModelRecord> recs;
+    // `rng: Option<DynRng>` of Generator / Processor / ExclusiveGateway / StochasticGate (e.g. generator.rs:39,
+    // 102-109): a model constructed with its own generator draws from it instead of Services::global_rng.  Here the
+    // override is a seed: the model's stream is the Philox stream (own_seed, replication), created at put().
+    bool has_own_rng = false;
+    uint64_t own_seed = 0;
+    std::shared_ptr<Rng> own_rng;
+    Rng& rng_of(Services& s) { return own_rng ? *own_rng : *s.global_rng; }
     virtual ~ModelBase() {}
     virtual int events_ext(const ModelMessage& m, Services& s) = 0;
     virtual int events_int(Services& s, std::vector<ModelMessage>& out) = 0;
@@ -248,6 +255,7 @@ struct Simulation {  // sim/src/simulator/mod.rs:39-304
     // counters (test instrumentation): one "event" = one events_ext or events_int call
     uint64_t n_steps = 0, n_ext = 0, n_int = 0;
     std::vector<int> top_trace_index;  // trace index of each top-level model (-1: a Coupled model)
+    void bind_model_rngs();            // (re)create the streams of models that carry their own generator
     std::vector<uint64_t> connector_messages;  // per-connector routed message count
 
     Simulation();

@@ -158,6 +158,17 @@ int orc_add_connector(void* h, const char* id, const char* src, const char* tgt,
     ((Handle*)h)->staged_connectors.push_back(Connector{id, src, tgt, sport, tport});
     return 0;
 }
+// Generator::new(.., rng: Some(..)) etc.: the last model added draws from its own stream
+int orc_set_model_rng(void* hv, const char* id, uint64_t seed) {
+    Handle* h = (Handle*)hv;
+    for (auto& m : target(h))
+        if (m.id == id) {
+            m.inner->has_own_rng = true;
+            m.inner->own_seed = seed;
+            return 0;
+        }
+    return ModelNotFound;
+}
 int orc_preload_processor(void* hv, const char* id, int active, double until, const char* queue_nl) {
     Handle* h = (Handle*)hv;
     for (auto& m : target(h))
@@ -246,6 +257,7 @@ int orc_set_rng_philox(void* hv, uint64_t seed, uint64_t rep) {
     Handle* h = (Handle*)hv;
     h->sim.rng_owner = std::make_unique<Philox>(seed, rep);
     h->sim.services.global_rng = h->sim.rng_owner.get();
+    h->sim.bind_model_rngs();
     return 0;
 }
 int orc_set_rng_external(void* hv, const uint64_t* v, size_t n) {

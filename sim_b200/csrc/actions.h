@@ -213,6 +213,7 @@ enum {
     TF_CAP,
     TF_PREFIX,
     TF_GROUP,      // group_base | coupled_of << 8 (Coupled models: the order events_ext runs in, the parked list)
+    TF_RNG,        // rng_row: the model draws from its own stream (0 = the simulation's)
     TF_COUNT
 };
 // flags in the top byte of a route-table word (the byte that becomes the sequence number of a mailbox slot)
@@ -223,8 +224,8 @@ enum {
 #define SIMB_TAB_ROUTES (SIMB_TAB_ROUTE_BEGIN + SIMB_MAX_OUT_PORTS)           /* ROUTE_WORD(tgt, port, r, 0) */
 #define SIMB_TAB_CONN (SIMB_TAB_ROUTES + SIMB_MAX_ROUTES)                        /* connector index of route r */
 #define SIMB_TAB_WORDS (SIMB_TAB_CONN + SIMB_MAX_ROUTES)
-// value table: [6][SIMB_MAX_MODELS] 64-bit words: p0, p1, p2 (f64 bits), q0, q1, q2
-#define SIMB_VTAB_WORDS (6 * SIMB_MAX_MODELS)
+// value table: [7][SIMB_MAX_MODELS] 64-bit words: p0, p1, p2 (f64 bits), q0, q1, q2, rng_seed
+#define SIMB_VTAB_WORDS (7 * SIMB_MAX_MODELS)
 
 inline void build_model_table(const SimbNetDesc& net, uint32_t* tab, uint64_t* vtab) {
     for (uint32_t i = 0; i < SIMB_TAB_WORDS; i++) tab[i] = 0;
@@ -241,6 +242,7 @@ inline void build_model_table(const SimbNetDesc& net, uint32_t* tab, uint64_t* v
         tab[TF_RING_D * SIMB_MAX_MODELS + m] = d.ring_d;
         tab[TF_CAP * SIMB_MAX_MODELS + m] = d.cap;
         tab[TF_PREFIX * SIMB_MAX_MODELS + m] = d.prefix;
+        tab[TF_RNG * SIMB_MAX_MODELS + m] = d.rng_row;
         tab[TF_GROUP * SIMB_MAX_MODELS + m] = net.n_coupled ? (net.group_base[m] | ((uint32_t)net.coupled_of[m] << 8)) : (m | (0xFFu << 8));
         const double p[3] = {d.p0, d.p1, d.p2};
         for (int k = 0; k < 3; k++) {
@@ -251,6 +253,7 @@ inline void build_model_table(const SimbNetDesc& net, uint32_t* tab, uint64_t* v
         vtab[3 * SIMB_MAX_MODELS + m] = d.q0;
         vtab[4 * SIMB_MAX_MODELS + m] = d.q1;
         vtab[5 * SIMB_MAX_MODELS + m] = d.q2;
+        vtab[6 * SIMB_MAX_MODELS + m] = d.rng_seed;
     }
     for (uint32_t p = 0; p < SIMB_MAX_OUT_PORTS; p++)
         tab[SIMB_TAB_ROUTE_BEGIN + p] = net.route_begin[p] | ((uint32_t)net.route_begin[p + 1] << 16);

@@ -118,6 +118,8 @@ struct Lane {
     uint32_t dm_int, dm_ext;  // deferred continuous draws: "until_next_event[m] = sample(dist[m])" still
                               // owed from the previous internal phase / this external phase
     uint32_t traced;
+    uint64_t kseed;  // RARE builds: Philox key while a model draws from its OWN stream (`own`), see own_begin
+    bool own;
     uint32_t rb;  // bytes of queue / table slots (and mailbox overflow) this lane touched in global memory in this
                   // launch: the counted part of the launch's algorithmic bytes (simb_counters.ring_bytes)
     // generic interpreter: models whose until_next_event is not +INF / is exactly 0.0 (kept in step with every
@@ -242,8 +244,32 @@ struct Engine {
 
     // Philox key = the seed (warp-uniform), counter words 2 / 3 = the global replication index -- derived on demand,
     // not kept in registers
-    SIMB_HD uint32_t key0(const Lane&) const { return (uint32_t)st.seed; }
-    SIMB_HD uint32_t key1(const Lane&) const { return (uint32_t)(st.seed >> 32); }
+    SIMB_HD uint32_t key0(const Lane& ln) const { return (uint32_t)((RARE && !STATIC && ln.own) ? ln.kseed : st.seed); }
+    SIMB_HD uint32_t key1(const Lane& ln) const { return (uint32_t)(((RARE && !STATIC && ln.own) ? ln.kseed : st.seed) >> 32); }
+    // ---- a model with its own generator (`rng: Some(..)`, generator.rs:39,102-109; processor.rs, exclusive_gateway.rs,
+    // stochastic_gate.rs alike): its draws come from the Philox stream (its seed, replication) whose position is one
+    // word of the model's state.  own_begin / own_end bracket such a draw: the simulation's stream is set aside.
+    struct SavedRng {
+        uint32_t draw_idx, ccount;
+        uint64_t c0, c1, c2;
+    };
+    SIMB_HD SavedRng own_begin(Lane& ln, uint32_t m, uint32_t rng_row) {
+        SavedRng sv{ln.draw_idx, ln.ccount, ln.c0, ln.c1, ln.c2};
+        ln.draw_idx = ln.W(rng_row);
+        ln.ccount = 0;
+        ln.kseed = tab.vt[6 * SIMB_MAX_MODELS + m];
+        ln.own = true;
+        return sv;
+    }
+    SIMB_HD void own_end(Lane& ln, uint32_t rng_row, const SavedRng& sv) {
+        ln.W(rng_row) = ln.draw_idx;
+        ln.draw_idx = sv.draw_idx;
+        ln.ccount = sv.ccount;
+        ln.c0 = sv.c0;
+        ln.c1 = sv.c1;
+        ln.c2 = sv.c2;
+        ln.own = false;
+    }
     SIMB_HD uint32_t rep_lo(const Lane& ln) const { return (uint32_t)(st.rep_offset + ln.rep); }
     SIMB_HD uint32_t rep_hi(const Lane& ln) const { return (uint32_t)((st.rep_offset + ln.rep) >> 32); }
     // Philox prefetch.  Draw number i is word pair (i & 1) of block i >> 1, so a cache of upcoming draws is a pure
@@ -721,7 +747,11 @@ struct Engine {
                 ln.dm_ext &= ln.dm_ext - 1u;
             }
             // parameter errors were raised when the debt was noted (apply_u), so dist_err is 0 here
+            const uint32_t rr = RARE ? TF(TF_RNG, m) : 0u;
+            SavedRng sv{};
+            if (RARE && rr) sv = own_begin(ln, m, rr);
             const double dv = sample_continuous_kind(ln, (TF(TF_WTAB, m) >> 16) & 0xFFu, TabP{tab.vt, m, 0u});
+            if (RARE && rr) own_end(ln, rr, sv);
             ln.D(net.drow_until + m) = dv;
             if (dv == 0.0) ln.zm |= 1u << m;  // a variate of exactly zero makes the model imminent at once
             else ln.nmin = fmin(ln.nmin, dv);
@@ -872,6 +902,8 @@ struct Engine {
         ln.ccount = 0;
         ln.traced = instr && ln.rep < st.trace_reps;
         ln.rb = 0;
+        ln.kseed = 0;
+        ln.own = false;
         ln.dm_int = ln.W(net.wrow_dmask);
         ln.dm_ext = 0;
         ln.tmask = 0;
@@ -1436,7 +1468,11 @@ struct Engine {
         const uint32_t rcap = TF(TF_RING_CAP, m), w0 = TF(TF_RING_W0, m), w1 = TF(TF_RING_W1, m);
         if (sp == XS_SGATE) {  // receive_job stochastic_gate.rs:101-122: Bernoulli draw AT ARRIVAL
             apply_u<true>(ln, m, UA_ZERO);  // (ext2 made sure that no earlier draw of the stream is still owed)
+            const uint32_t rr = RARE ? TF(TF_RNG, m) : 0u;
+            SavedRng sv{};
+            if (RARE && rr) sv = own_begin(ln, m, rr);
             const bool pass = sample_bernoulli_p(ln, flags, TabP{tab.vt, m, TF(TF_WTAB, m) >> 24});
+            if (RARE && rr) own_end(ln, rr, sv);
             if (ln.err) return;
             const uint32_t q = ln.W(wrow);
             const uint32_t head = q >> 16, len = q & 0xFFFFu;
@@ -1691,7 +1727,11 @@ struct Engine {
             aux = next + 1u;
         } else if (!BASIC && kind == KI_XGW) {  // send_jobs exclusive_gateway.rs:110-134: one draw per firing
             const uint32_t wt = TF(TF_WTAB, m);
+            const uint32_t rr = RARE ? TF(TF_RNG, m) : 0u;
+            SavedRng sv{};
+            if (RARE && rr) sv = own_begin(ln, m, rr);
             const uint32_t idx = sample_index_p(ln, flags, TF(TF_OUT, m) >> 16, wt & 0xFFFFu, TabP{tab.vt, m, wt >> 24});
+            if (RARE && rr) own_end(ln, rr, sv);
             if (ln.err) return true;
             if (idx >= n_out) {
                 ln.err = 34;  // flow_paths[idx] out of bounds panics

@@ -372,6 +372,7 @@ static bool only_basic_models(const SimbNetDesc& net) {
 }
 static bool uses_rare_variables(const SimbNetDesc& net) {
     for (uint32_t m = 0; m < net.n_models; m++) {
+        if (net.models[m].rng_row) return true;  // a model with its own generator: only the full interpreter draws from it
         const uint32_t k = net.models[m].dist_kind;
         if (k == DK_GAMMA || k == DK_LOGNORMAL || k == DK_WEIBULL || k == DK_BETA) return true;
     }
@@ -412,7 +413,7 @@ int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool inst
     dims->shape = engine_match_shape(net, rng_kind, instrument);
     // (Coupled models need the full interpreter: the lean builds compile their parked-message logic out)
     dims->rare = uses_rare_variables(net) || net.n_coupled != 0u;
-    dims->basic = only_basic_models(net) && net.n_coupled == 0u;
+    dims->basic = only_basic_models(net) && net.n_coupled == 0u && !dims->rare;
     // Tile width = replications per CTA.  Pick the width that keeps the most warps resident per SM
     // (shared memory 227 KB, 64 registers per thread -> at most 32 warps, at most 32 CTAs); among equals
     // prefer the wider tile (fewer, larger bulk copies), and keep half of the SM's unified storage for L1

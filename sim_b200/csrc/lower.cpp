@@ -410,6 +410,7 @@ struct PendingModel {
     double u0 = std::numeric_limits<double>::infinity();
     uint32_t phase0 = 0;
     std::vector<uint32_t> words0;
+    bool own_rng = false;              // `rng: {seed}`: one more private word, the draw index of the model's own stream
     std::vector<std::string> preload;  // queue contents from `state`
     std::vector<uint32_t> preload1;    // second u32 channel of those entries (collection count / pass flag / seq|flags)
     std::vector<double> preload_d;     // f64 channel of those entries (Stopwatch: the time present)
@@ -812,6 +813,21 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
         } else {
             return c.fail(33, "model type `" + t + "` cannot run on the device (custom models are out of scope)");
         }
+        if (const Value* rg = j.get("rng")) {  // the model's own generator (generator.rs:39, processor.rs, exclusive_gateway.rs,
+                                               // stochastic_gate.rs; #[serde(skip)] in the reference: an extension here)
+            if (rg->kind != Value::Null) {
+                const Value* sd = rg->get("seed");
+                if (!sd || !sd->is_uint) return c.fail(13, hm.id + ": rng must be {\"seed\": <unsigned integer>}");
+                if (md.type != MT_GENERATOR && md.type != MT_PROCESSOR && md.type != MT_EXCLUSIVE_GATEWAY && md.type != MT_STOCHASTIC_GATE)
+                    return c.fail(13, hm.id + ": this model type has no rng field");
+                if (opt.rng_kind != 0) return c.fail(36, hm.id + ": a per-model rng needs the Philox streams (rng_kind 0)");
+                md.rng_seed = sd->u;
+                p.own_rng = true;
+                p.words0.resize(p.n_words, 0u);
+                p.words0.push_back(0u);
+                p.n_words += 1;
+            }
+        }
         md.n_in = (uint8_t)(hm.ports_in.size() > 254 ? 254 : hm.ports_in.size());
         md.n_out = (uint8_t)hm.ports_out.size();
         if (hm.ports_out.size() > 64) return c.fail(32, hm.id + ": too many output ports");
@@ -1028,6 +1044,7 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
     for (size_t i = 0; i < pm.size(); i++) {
         net.models[i].wrow = wr;
         wr += (uint16_t)pm[i].n_words;
+        if (pm[i].own_rng) net.models[i].rng_row = (uint16_t)(wr - 1);
         if (pm[i].n_dwords) {
             net.models[i].drow = dr;
             dr += (uint16_t)pm[i].n_dwords;

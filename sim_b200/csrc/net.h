@@ -75,9 +75,13 @@ struct SimbModelDesc {
     uint32_t ring_d;    // slot offset of the f64 channel (arrival / start time) in ring_d
     uint32_t cap;       // Processor queue_capacity (SIMB_CAP_INF = usize::MAX), Batcher max_batch_size
     uint32_t prefix;    // Generator: (intern id of portsOut.job) << 24
+    uint16_t rng_row;   // u32 state row holding the draw index of the model's OWN Philox stream (`rng: Some(..)` of
+                        // generator.rs:39 etc.), 0 = the model draws from the simulation's stream
+    uint16_t reserved;
     double p0, p1, p2;  // Exp: p0 = 1/lambda; Normal: mean, std_dev; Triangular: min, max, mode;
                         // Uniform: low, scale (already ulp-decremented); Batcher: p0 = max_batch_time
     uint64_t q0, q1, q2;  // Bernoulli: q0 = p_int; Index: q0 = low, q1 = range, q2 = zone
+    uint64_t rng_seed;    // seed of the model's own stream (rng_row != 0): Philox key, counter = (block, replication)
 };
 
 struct SimbRoute {

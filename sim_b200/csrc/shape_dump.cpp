@@ -47,15 +47,16 @@ int main(int argc, char** argv) {
     std::printf(" {\n");
     for (int i = 0; i < SIMB_MAX_MODELS; i++) {
         const SimbModelDesc& m = n.models[i];
-        std::printf("  {%u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %uu, %uu, %uu, %uu, %uu, %uu, ", m.type, m.n_in, m.n_out, m.flags,
+        std::printf("  {%u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %uu, %uu, %uu, %uu, %uu, %uu, %u, 0, ", m.type, m.n_in, m.n_out, m.flags,
                     m.dist_kind, m.dist_err, m.wrow, m.drow, m.out_base, m.wtab, m.n_w, m.ring_cap, m.ring_w0, m.ring_w1, m.ring_d,
-                    m.cap, m.prefix);
+                    m.cap, m.prefix, m.rng_row);
         pd(m.p0);
         std::printf(", ");
         pd(m.p1);
         std::printf(", ");
         pd(m.p2);
-        std::printf(", %lluull, %lluull, %lluull},\n", (unsigned long long)m.q0, (unsigned long long)m.q1, (unsigned long long)m.q2);
+        std::printf(", %lluull, %lluull, %lluull, %lluull},\n", (unsigned long long)m.q0, (unsigned long long)m.q1,
+                    (unsigned long long)m.q2, (unsigned long long)m.rng_seed);
     }
     std::printf(" },\n {");
     for (int i = 0; i <= SIMB_MAX_OUT_PORTS; i++) std::printf("%u,", n.route_begin[i]);

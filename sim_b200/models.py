@@ -11,6 +11,18 @@ from typing import List, Optional
 from .input_modeling import _Variant
 
 
+def _own_rng(rng):
+    """``rng: Option<DynRng>`` of Generator / Processor / ExclusiveGateway / StochasticGate (e.g. generator.rs:39,
+    85-95): None, or the SEED of the model's own stream -- on the batched path a model's generator is the Philox stream
+    (seed, replication index), one per replication, written ``"rng": {"seed": S}`` in the wire form (an extension: the
+    reference's field is #[serde(skip)], only its Rust constructors can set it)."""
+    if rng is None:
+        return None
+    if isinstance(rng, bool) or not isinstance(rng, int) or rng < 0:
+        raise ValueError("a per-model rng is given as the non-negative integer seed of its Philox stream")
+    return int(rng)
+
+
 class _ModelBody:
     type_name = "?"
     # optional ``state`` block of the wire form (the reference's models carry `#[serde(default)] state`, e.g.
@@ -30,14 +42,13 @@ class Generator(_ModelBody):
     thinning: Optional[dict]
     job_port: str
     store_records: bool = False
-    rng: None = None
+    rng: Optional[int] = None
     type_name = "Generator"
 
     @classmethod
     def new(cls, message_interdeparture_time, thinning, job_port, store_records, rng=None):
-        if rng is not None:
-            raise ValueError("per-model rng overrides are not supported on the batched path")
-        return cls(message_interdeparture_time, thinning, job_port, store_records, None)
+        rng = _own_rng(rng)
+        return cls(message_interdeparture_time, thinning, job_port, store_records, rng)
 
     def fields(self):
         d = {"messageInterdepartureTime": self.message_interdeparture_time.to_dict(),
@@ -56,15 +67,14 @@ class Processor(_ModelBody):
     job_port: str
     processed_job_port: str
     store_records: bool = False
-    rng: None = None
+    rng: Optional[int] = None
     state: Optional[dict] = None
     type_name = "Processor"
 
     @classmethod
     def new(cls, service_time, queue_capacity, job_port, processed_job_port, store_records, rng=None):
-        if rng is not None:
-            raise ValueError("per-model rng overrides are not supported on the batched path")
-        return cls(service_time, queue_capacity, job_port, processed_job_port, store_records, None)
+        rng = _own_rng(rng)
+        return cls(service_time, queue_capacity, job_port, processed_job_port, store_records, rng)
 
     def fields(self):
         d = {"serviceTime": self.service_time.to_dict(), "portsIn": {"job": self.job_port},
@@ -140,14 +150,13 @@ class ExclusiveGateway(_ModelBody):
     flow_paths_out: List[str]
     port_weights: _Variant
     store_records: bool = False
-    rng: None = None
+    rng: Optional[int] = None
     type_name = "ExclusiveGateway"
 
     @classmethod
     def new(cls, flow_paths_in, flow_paths_out, port_weights, store_records, rng=None):
-        if rng is not None:
-            raise ValueError("per-model rng overrides are not supported on the batched path")
-        return cls(list(flow_paths_in), list(flow_paths_out), port_weights, store_records, None)
+        rng = _own_rng(rng)
+        return cls(list(flow_paths_in), list(flow_paths_out), port_weights, store_records, rng)
 
     def fields(self):
         return {"portsIn": {"flowPaths": list(self.flow_paths_in)},
@@ -180,14 +189,13 @@ class StochasticGate(_ModelBody):
     job_in_port: str
     job_out_port: str
     store_records: bool = False
-    rng: None = None
+    rng: Optional[int] = None
     type_name = "StochasticGate"
 
     @classmethod
     def new(cls, pass_distribution, job_in_port, job_out_port, store_records, rng=None):
-        if rng is not None:
-            raise ValueError("per-model rng overrides are not supported on the batched path")
-        return cls(pass_distribution, job_in_port, job_out_port, store_records, None)
+        rng = _own_rng(rng)
+        return cls(pass_distribution, job_in_port, job_out_port, store_records, rng)
 
     def fields(self):
         return {"passDistribution": self.pass_distribution.to_dict(), "portsIn": {"job": self.job_in_port},
@@ -331,6 +339,8 @@ class Model:
     def to_dict(self) -> dict:
         d = {"id": self.id, "type": self.inner.type_name}
         d.update(self.inner.fields())
+        if getattr(self.inner, "rng", None) is not None:
+            d["rng"] = {"seed": int(self.inner.rng)}
         if "state" not in d and getattr(self.inner, "state", None) is not None:
             d["state"] = self.inner.state
         return d

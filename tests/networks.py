@@ -485,6 +485,25 @@ def large_mixed():
     return models, connectors
 
 
+def own_rngs(store_records=False, proc_lambda=1.5):
+    """Models constructed with their own generator (`rng: Some(..)`: generator.rs:39,102-109, processor.rs,
+    exclusive_gateway.rs, stochastic_gate.rs): each draws from its own stream, the second processor from the
+    simulation's."""
+    models = [
+        Model.new("generator", Generator.new(Exp(1.0), None, "job", store_records, 11)),
+        Model.new("proc-own", Processor.new(Exp(proc_lambda), 10, "job", "done", store_records, 12)),
+        Model.new("exclusive", ExclusiveGateway.new(["in"], ["a", "b"], IndexRandomVariable.WeightedIndex([2, 1]), store_records, 13)),
+        Model.new("sgate", StochasticGate.new(BooleanRandomVariable.Bernoulli(0.6), "job", "job", store_records, 14)),
+        Model.new("proc-global", Processor.new(ContinuousRandomVariable.Normal(0.5, 0.05), 10, "job", "done", store_records, None)),
+        _storage("sink-a", store_records), _storage("sink-b", store_records),
+    ]
+    C = Connector.new
+    connectors = [C("c1", "generator", "proc-own", "job", "job"), C("c2", "proc-own", "exclusive", "done", "in"),
+                  C("c3", "exclusive", "sgate", "a", "job"), C("c4", "exclusive", "proc-global", "b", "job"),
+                  C("c5", "sgate", "sink-a", "job", "store"), C("c6", "proc-global", "sink-b", "done", "store")]
+    return models, connectors
+
+
 # ---- Coupled models (sim/src/models/coupled.rs, sim/tests/coupled.rs) --------------------------------------
 def coupled_atomic(lam_gen=0.007, lam_proc=0.011):
     """coupled.rs:15-59: the atomic form of closure_under_coupling"""
@@ -552,5 +571,5 @@ ALL = {
     "processor_from_queue": processor_from_queue, "processor_network": processor_network,
     "generator_passive": generator_passive, "more_variables": more_variables, "beta_variables": beta_variables, "state_injection": state_injection,
     "state_injection_tables": state_injection_tables, "batch_bursts": batch_bursts, "tandem": tandem, "gateway_network": gateway_network,
-    "large_mixed": large_mixed, "coupled_closure": coupled_closure, "coupled_pipeline": coupled_pipeline,
+    "large_mixed": large_mixed, "own_rngs": own_rngs, "coupled_closure": coupled_closure, "coupled_pipeline": coupled_pipeline,
 }

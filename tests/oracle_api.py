@@ -139,6 +139,8 @@ class OracleSimulation:
             assert L.orc_end_coupled(h) == 0
         else:
             raise TypeError(type(i))
+        if getattr(i, "rng", None) is not None:
+            assert L.orc_set_model_rng(h, b, C.c_uint64(int(i.rng))) == 0
         st = getattr(i, "state", None)
         if st is not None and isinstance(i, (M.ParallelGateway, M.StochasticGate, M.Stopwatch)):
             until = st.get("untilNextEvent", float("inf"))

@@ -124,3 +124,32 @@ def test_device_sampler_reference_statistics_and_errors():
         with pytest.raises(SimulationError) as ei:
             sample(fam, var, 4, 2)
         assert ei.value.name == name
+
+
+def test_a_model_with_its_own_rng_is_independent_of_the_other_draws():
+    """generator.rs:102-109 (`match &self.rng`): a Generator constructed with its own generator produces the same
+    arrival times whatever the rest of the network draws; without one its stream is shared."""
+    import networks
+
+    def generation_times(models, conns):
+        o = O.OracleSimulation(models, conns)
+        o.set_rng_philox(5, 3)
+        o.trace_enable(True)
+        e, _ = o.step_n(600, collect=False)
+        assert e == 0
+        return [ev["time"] for ev in o.trace() if ev["kind"] == 1 and ev["action"] == 1 and ev["index"] == 0]
+
+    a = generation_times(*networks.own_rngs(proc_lambda=1.5))
+    b = generation_times(*networks.own_rngs(proc_lambda=4.0))
+    n = min(len(a), len(b))
+    # (the clock is a running sum over different step sequences: equal to rounding, not to the bit)
+    assert n > 50 and np.allclose(a[:n], b[:n], rtol=1e-12, atol=0.0)
+    # the same networks with the generator on the shared stream diverge
+    def shared(lam):
+        m, c = networks.own_rngs(proc_lambda=lam)
+        m[0].inner.rng = None
+        m[1].inner.rng = None
+        return generation_times(m, c)
+    a, b = shared(1.5), shared(4.0)
+    n = min(len(a), len(b))
+    assert not np.allclose(a[:n], b[:n], rtol=1e-6, atol=0.0)
