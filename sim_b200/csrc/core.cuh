@@ -90,6 +90,18 @@ struct Tables {
     uint64_t* rng_cache;  // baked shapes: Philox draw cache, [rng_slots][lane] (shared memory on the device)
     uint32_t rng_slots;   // prefetched draws per replication there (power of two >= 2)
 };
+// Optimisations of the baked small-shape kernels (A/B switches; profiles/r02_fused_experiments.txt)
+#ifndef SIMB_OPT_NOVOTE
+#define SIMB_OPT_NOVOTE 1 /* shapes of <= 4 models: no warp votes around the per-model blocks (some lane almost always needs each) */
+#endif
+#ifndef SIMB_OPT_UREG
+#define SIMB_OPT_UREG 0   /* shapes of <= 4 models: until_next_event in registers for the whole launch (measured: -11 %,
+                             the 5-CTAs-per-SM register budget spills) */
+#endif
+#ifndef SIMB_OPT_SQUEEZE
+#define SIMB_OPT_SQUEEZE 0 /* ziggurat wedge: chord / tangent bounds before exp() (measured: -12 %, the fp64 divide and the
+                              extra table reads cost more than the exponentials they save) */
+#endif
 #ifndef SIMB_RNG_CACHE
 #define SIMB_RNG_CACHE 8u /* rng_slots of fused launches (streaming launches keep one block: 2) */
 #endif
@@ -118,6 +130,7 @@ struct Lane {
     uint32_t dm_int, dm_ext;  // deferred continuous draws: "until_next_event[m] = sample(dist[m])" still
                               // owed from the previous internal phase / this external phase
     uint32_t traced;
+    double u[4];     // baked shapes of <= 4 models: until_next_event of model m, in registers for the whole launch
     uint64_t kseed;  // RARE builds: Philox key while a model draws from its OWN stream (`own`), see own_begin
     bool own;
     uint32_t rb;  // bytes of queue / table slots (and mailbox overflow) this lane touched in global memory in this
@@ -324,6 +337,10 @@ struct Engine {
         }
     }
 
+    // until_next_event of model m.  Baked shapes of at most four models keep it in registers (every index is a literal
+    // there, so ln.u[] is scalarised); everything else reads the state tile.
+    static constexpr bool UREG = STATIC && SM <= 4 && SIMB_OPT_UREG;
+    SIMB_HD double& U(Lane& ln, uint32_t m) { return UREG ? ln.u[m & 3u] : ln.D(net.drow_until + m); }
     // queue / table storage in global memory, [slot][replication]
     SIMB_HD uint32_t& RW(Lane& ln, uint32_t slot) {
         ln.rb += 4u;
@@ -396,7 +413,22 @@ struct Engine {
             if (x < tab.exp_x[i + 1]) return x;
             if (i == 0) return 7.69711747013104972 - log(standard_f64(ln));
             double f1 = tab.exp_f[i + 1], f0 = tab.exp_f[i];
-            if (f1 + (f0 - f1) * standard_f64(ln) < exp(-x)) return x;
+            const double y = f1 + (f0 - f1) * standard_f64(ln);
+            if (SIMB_OPT_SQUEEZE) {
+                // exp(-x) on [x_{i+1}, x_i] lies above its tangent at x_i and below its chord, so most wedge points are
+                // decided without the exponential; the narrow band in between (and anything within 1e-9 of a bound, so
+                // that rounding can never flip a decision) falls through to the exact test.  Same accept / reject
+                // decisions, same draws.
+                const double xi = tab.exp_x[i], xj = tab.exp_x[i + 1];
+                const double tangent = f0 * (1.0 + (xi - x));
+                const double chord = f0 + (f1 - f0) * ((xi - x) / (xi - xj));
+                if (y < tangent * (1.0 - 1e-9)) return x;
+                if (y > chord * (1.0 + 1e-9)) {
+                    if (ln.err) return x;
+                    continue;
+                }
+            }
+            if (y < exp(-x)) return x;
             if (ln.err) return x;  // external stream ran dry: do not spin
         }
     }
@@ -716,7 +748,15 @@ struct Engine {
                         m = (uint32_t)lowest_bit(ln.dm_ext);
                         ln.dm_ext &= ln.dm_ext - 1u;
                     }
-                    ln.D(net.drow_until + m) = sample_continuous_kind(ln, kind, DescP{par.models[m]});
+                    const double dv = sample_continuous_kind(ln, kind, DescP{par.models[m]});
+                    if (UREG) {  // (m is a run-time value here: select the register)
+                        if (m == 0u) ln.u[0] = dv;
+                        else if (m == 1u) ln.u[1] = dv;
+                        else if (m == 2u) ln.u[2] = dv;
+                        else ln.u[3] = dv;
+                    } else {
+                        ln.D(net.drow_until + m) = dv;
+                    }
                 }
                 return;
             }
@@ -724,12 +764,12 @@ struct Engine {
 #define SIMB_FLUSH_INT(m)                                                                            \
     if ((m) < net.n_models && net.models[m].dist_kind != DK_NONE && (ln.dm_int & (1u << (m)))) {     \
         ln.dm_int &= ~(1u << (m));                                                                   \
-        ln.D(net.drow_until + (m)) = sample_continuous(ln, net.models[m], par.models[m]);            \
+        U(ln, (m)) = sample_continuous(ln, net.models[m], par.models[m]);                            \
     }
 #define SIMB_FLUSH_EXT(m)                                                                            \
     if ((m) < net.n_models && net.models[m].dist_kind != DK_NONE && (ln.dm_ext & (1u << (m)))) {     \
         ln.dm_ext &= ~(1u << (m));                                                                   \
-        ln.D(net.drow_until + (m)) = sample_continuous(ln, net.models[m], par.models[m]);            \
+        U(ln, (m)) = sample_continuous(ln, net.models[m], par.models[m]);                            \
     }
             if (ln.dm_int) SIMB_FOR_MODELS(SM, SIMB_FLUSH_INT);
             if (ln.dm_ext) SIMB_FOR_MODELS(SM, SIMB_FLUSH_EXT);
@@ -915,6 +955,12 @@ struct Engine {
                 const uint32_t t = ROUTE_TGT(mail_word(ln, j, 1));
                 if (t < SIMB_MAX_MODELS) ln.tmask |= 1u << t;
             }
+            if (UREG) {
+                ln.u[0] = net.n_models > 0u ? ln.D(net.drow_until + 0u) : 0.0;
+                ln.u[1] = net.n_models > 1u ? ln.D(net.drow_until + 1u) : 0.0;
+                ln.u[2] = net.n_models > 2u ? ln.D(net.drow_until + 2u) : 0.0;
+                ln.u[3] = net.n_models > 3u ? ln.D(net.drow_until + 3u) : 0.0;
+            }
         } else {
             for (uint32_t m = 0; m < net.n_models; m++) {
                 const double u = ln.D(net.drow_until + m);
@@ -944,6 +990,12 @@ struct Engine {
     }
     SIMB_HD void lane_store(Lane& ln, bool instr, uint32_t done_epoch, uint32_t absent) {
         ln.D(net.drow_time) = ln.time;
+        if (UREG) {
+            if (net.n_models > 0u) ln.D(net.drow_until + 0u) = ln.u[0];
+            if (net.n_models > 1u) ln.D(net.drow_until + 1u) = ln.u[1];
+            if (net.n_models > 2u) ln.D(net.drow_until + 2u) = ln.u[2];
+            if (net.n_models > 3u) ln.D(net.drow_until + 3u) = ln.u[3];
+        }
         ln.W(net.wrow_ctl) = CTL_MAKE(ln.err, done_epoch, ln.npend, absent);
         ln.W(net.wrow_steps) = ln.steps;
         ln.W(net.wrow_events) = ln.events;
@@ -969,7 +1021,6 @@ struct Engine {
     // ================================================================================================
     template <bool INSTR>
     SIMB_HD void events_ext(Lane& ln, uint32_t m, const SimbModelDesc& md, uint32_t port, uint32_t content) {
-        const uint32_t urow = net.drow_until + m;
         switch (md.type) {
             case MT_GENERATOR:  // generator.rs:161-167: no-op
             case MT_PASSIVE:    // tests/custom.rs:49-56
@@ -1004,7 +1055,7 @@ struct Engine {
                     record<INSTR>(ln, m, ACT_ARRIVAL, content);
                 } else if (port == 1) {  // get_job :101-104
                     ln.set_phase(m, 1);
-                    ln.D(urow) = 0.0;
+                    U(ln, m) = 0.0;
                 } else {
                     ln.err = 7;
                 }
@@ -1012,7 +1063,7 @@ struct Engine {
             }
             case MT_LOAD_BALANCER: {  // pass_job load_balancer.rs:78-87 (any port)
                 ln.set_phase(m, 1);
-                ln.D(urow) = 0.0;
+                U(ln, m) = 0.0;
                 uint32_t slot;
                 if (!ring_push(ln, md, content, &slot)) break;
                 record<INSTR>(ln, m, ACT_ARRIVAL, content);
@@ -1023,18 +1074,18 @@ struct Engine {
                 if (port == 0) {
                     if (ln.phase(m) != 1) {  // pass_job :127-137
                         ln.set_phase(m, 2);
-                        ln.D(urow) = 0.0;
+                        U(ln, m) = 0.0;
                         uint32_t slot;
                         if (!ring_push(ln, md, content, &slot)) break;
                     }
                     record<INSTR>(ln, m, ACT_ARRIVAL, content);  // also when Closed (drop_job :139-145)
                 } else if (port == 1) {  // activate :107-115
                     ln.set_phase(m, 0);
-                    ln.D(urow) = SIMB_INF;
+                    U(ln, m) = SIMB_INF;
                     record<INSTR>(ln, m, ACT_ACTIVATION, content);
                 } else if (port == 2) {  // deactivate :117-125
                     ln.set_phase(m, 1);
-                    ln.D(urow) = SIMB_INF;
+                    U(ln, m) = SIMB_INF;
                     record<INSTR>(ln, m, ACT_DEACTIVATION, content);
                 } else {
                     ln.err = 7;
@@ -1044,7 +1095,7 @@ struct Engine {
             case MT_EXCLUSIVE_GATEWAY: {  // pass_job exclusive_gateway.rs:95-108 (any port)
                 if (BASIC) break;
                 ln.set_phase(m, 1);
-                ln.D(urow) = 0.0;
+                U(ln, m) = 0.0;
                 uint32_t slot;
                 if (!ring_push(ln, md, content, &slot)) break;
                 record<INSTR>(ln, m, ACT_ARRIVAL, content, port == SIMB_PORT_UNKNOWN ? 0u : port + 1u);
@@ -1066,13 +1117,13 @@ struct Engine {
                     ln.W(md.wrow) = cnt + 1u;
                 }
                 record<INSTR>(ln, m, ACT_ARRIVAL, content, port + 1u);
-                ln.D(urow) = 0.0;
+                U(ln, m) = 0.0;
                 break;
             }
             case MT_STOCHASTIC_GATE: {  // stochastic_gate.rs:163-172, receive_job :101-122
                 if (BASIC) break;
                 if (port != 0) { ln.err = 7; break; }
-                ln.D(urow) = 0.0;
+                U(ln, m) = 0.0;
                 if (ln.dm_int | ln.dm_ext) flush_draws(ln);  // earlier draws of the stream come first
                 bool pass = sample_bernoulli(ln, md, par.models[m]);  // Bernoulli draw AT ARRIVAL
                 if (ln.err) break;
@@ -1086,7 +1137,7 @@ struct Engine {
                 if (BASIC) break;
                 if (port == 2) {  // get_job :211-214
                     ln.set_phase(m, 1);
-                    ln.D(urow) = 0.0;
+                    U(ln, m) = 0.0;
                     break;
                 }
                 if (port > 2) { ln.err = 7; break; }
@@ -1150,11 +1201,11 @@ struct Engine {
                 if (room) {
                     if (ph == 0) {  // start_batch :103-112
                         ln.set_phase(m, 1);
-                        ln.D(urow) = par.models[m].p0;
+                        U(ln, m) = par.models[m].p0;
                     }  // add_to_batch :93-101 leaves the timer alone
                 } else {  // fill_batch :114-123
                     ln.set_phase(m, 2);
-                    ln.D(urow) = 0.0;
+                    U(ln, m) = 0.0;
                 }
                 uint32_t slot;
                 if (!ring_push(ln, md, content, &slot)) break;
@@ -1187,7 +1238,6 @@ struct Engine {
 
     template <bool INSTR>
     SIMB_HD void events_int(Lane& ln, uint32_t m, const SimbModelDesc& md) {
-        const uint32_t urow = net.drow_until + m;
         switch (md.type) {
             case MT_GENERATOR: {  // generator.rs:169-177
                 if (!defer_draw(ln, m, md, false)) break;  // the draw comes first (:102-109, :129-136)
@@ -1209,7 +1259,7 @@ struct Engine {
                 uint32_t head = q >> 16, len = q & 0xFFFFu;
                 if (ln.phase(m) == 0) {
                     if (len == 0) {  // passivate :192-196
-                        ln.D(urow) = SIMB_INF;
+                        U(ln, m) = SIMB_INF;
                         break;
                     }
                     ln.set_phase(m, 1);  // process_next :160-175
@@ -1222,13 +1272,13 @@ struct Engine {
                 uint32_t slot;
                 uint32_t c = ring_pop(ln, md, &slot);  // release_job :177-190
                 ln.set_phase(m, 0);
-                ln.D(urow) = 0.0;
+                U(ln, m) = 0.0;
                 record<INSTR>(ln, m, ACT_DEPARTURE, c);
                 emit<INSTR>(ln, md, 0, c);
                 break;
             }
             case MT_STORAGE: {  // storage.rs:163-171
-                ln.D(urow) = SIMB_INF;
+                U(ln, m) = SIMB_INF;
                 if (ln.phase(m) == 1) {  // release_job :115-130
                     ln.set_phase(m, 0);
                     uint32_t c = ln.W(md.wrow);
@@ -1241,11 +1291,11 @@ struct Engine {
                 uint32_t len = ln.W(md.wrow) & 0xFFFFu;
                 if (len == 0) {  // passivate
                     ln.set_phase(m, 0);
-                    ln.D(urow) = SIMB_INF;
+                    U(ln, m) = SIMB_INF;
                     break;
                 }
                 if (md.n_out == 0) { ln.err = 34; break; }  // `% 0` panics
-                ln.D(urow) = 0.0;  // send_job :95-111 (pre-increment)
+                U(ln, m) = 0.0;  // send_job :95-111 (pre-increment)
                 uint32_t next = ln.W(md.wrow + 1) + 1u;
                 if (next >= md.n_out) next = 0;
                 ln.W(md.wrow + 1) = next;
@@ -1255,13 +1305,13 @@ struct Engine {
             case MT_GATE: {  // send_jobs gate.rs:149-165
                 if (BASIC) break;
                 ln.set_phase(m, 0);
-                ln.D(urow) = SIMB_INF;
+                U(ln, m) = SIMB_INF;
                 release_n<INSTR>(ln, m, md, ln.W(md.wrow) & 0xFFFFu, 0, 0);
                 break;
             }
             case MT_EXCLUSIVE_GATEWAY: {  // exclusive_gateway.rs:153-161
                 if (BASIC) break;
-                ln.D(urow) = SIMB_INF;
+                U(ln, m) = SIMB_INF;
                 if (ln.phase(m) == 1) {  // send_jobs :110-134: one draw per firing
                     ln.set_phase(m, 0);
                     if (ln.dm_int | ln.dm_ext) flush_draws(ln);  // earlier draws of the stream come first
@@ -1279,10 +1329,10 @@ struct Engine {
                 for (; i < cnt; i++)  // canonical choice: earliest-inserted full collection
                     if (RW(ln, md.ring_w1 + i) == md.n_in) break;
                 if (i == cnt) {  // passivate
-                    ln.D(urow) = SIMB_INF;
+                    U(ln, m) = SIMB_INF;
                     break;
                 }
-                ln.D(urow) = 0.0;  // send_job :118-143
+                U(ln, m) = 0.0;  // send_job :118-143
                 uint32_t c = RW(ln, md.ring_w0 + i);
                 for (uint32_t j = i; j + 1u < cnt; j++) {  // remove, keeping insertion order
                     RW(ln, md.ring_w0 + j) = RW(ln, md.ring_w0 + j + 1u);
@@ -1298,10 +1348,10 @@ struct Engine {
                 if (BASIC) break;
                 uint32_t len = ln.W(md.wrow) & 0xFFFFu;
                 if (len == 0) {
-                    ln.D(urow) = SIMB_INF;
+                    U(ln, m) = SIMB_INF;
                     break;
                 }
-                ln.D(urow) = 0.0;
+                U(ln, m) = 0.0;
                 uint32_t slot;
                 uint32_t c = ring_pop(ln, md, &slot);
                 if (RW(ln, md.ring_w1 + slot)) {  // pass_job :129-141
@@ -1314,7 +1364,7 @@ struct Engine {
             }
             case MT_STOPWATCH: {  // stopwatch.rs:284-293
                 if (BASIC) break;
-                ln.D(urow) = SIMB_INF;
+                U(ln, m) = SIMB_INF;
                 if (ln.phase(m) == 1) {  // release_minimum / release_maximum :216-250
                     ln.set_phase(m, 0);
                     uint32_t c = ln.W(md.wrow + 1);
@@ -1330,15 +1380,15 @@ struct Engine {
                 if (le && ge2) { ln.err = 5; break; }
                 if (le) {  // release_full_queue :125-141
                     ln.set_phase(m, 0);
-                    ln.D(urow) = SIMB_INF;
+                    U(ln, m) = SIMB_INF;
                     release_n<INSTR>(ln, m, md, len, 0, 0);
                 } else if (ge2) {  // release_multiple :161-177
                     ln.set_phase(m, 2);
-                    ln.D(urow) = 0.0;
+                    U(ln, m) = 0.0;
                     release_n<INSTR>(ln, m, md, md.cap, 0, 0);
                 } else {  // release_partial_queue :143-159
                     ln.set_phase(m, 1);
-                    ln.D(urow) = par.models[m].p0;
+                    U(ln, m) = par.models[m].p0;
                     release_n<INSTR>(ln, m, md, md.cap, 0, 0);
                 }
                 break;
@@ -2007,7 +2057,9 @@ struct Engine {
             const uint32_t tmask = had ? ln.tmask : 0u;  // a target id matching no model has no bit: dropped
             const uint32_t np = had ? ln.npend : 0u;
             if (STATIC) {
-                const uint32_t wm = warp_or(tmask);
+                // shapes of more than four models: a warp vote skips the blocks of models no lane has mail for
+                constexpr bool VOTE = !(SM <= 4 && SIMB_OPT_NOVOTE);
+                const uint32_t wm = VOTE ? warp_or(tmask) : 0xFFFFFFFFu;
 #define SIMB_EXT_ONE(m)                                                                \
     if ((m) < M && ((wm >> (m)) & 1u)) { /* warp-uniform */                            \
         if (((tmask >> (m)) & 1u) && !ln.err) ext_model<INSTR>(ln, (m), np, nev);      \
@@ -2038,17 +2090,17 @@ struct Engine {
         if (STATIC) {
             if (go && !had) {
                 dt = SIMB_INF;
-#define SIMB_MIN_ONE(m) if ((m) < M) dt = fmin(dt, ln.D(net.drow_until + (m)));
+#define SIMB_MIN_ONE(m) if ((m) < M) dt = fmin(dt, U(ln, (m)));
                 SIMB_FOR_MODELS(SM, SIMB_MIN_ONE);
 #undef SIMB_MIN_ONE
             }
             if (go) {
 #define SIMB_ADV_ONE(m)                                          \
     if ((m) < M) {                                               \
-        double u = ln.D(net.drow_until + (m));                   \
+        double u = U(ln, (m));                                   \
         if (!had && net.models[m].type != MT_PASSIVE) {          \
             u = u - dt;                                          \
-            ln.D(net.drow_until + (m)) = u;                      \
+            U(ln, (m)) = u;                                      \
         }                                                        \
         if (u == 0.0) zmask |= 1u << (m);                        \
     }
@@ -2095,7 +2147,8 @@ struct Engine {
         }
         // ---- internal events in model order (:237-268) ----
         if (STATIC) {
-            const uint32_t wm = warp_or(zmask);
+            constexpr bool VOTE = !(SM <= 4 && SIMB_OPT_NOVOTE);
+            const uint32_t wm = VOTE ? warp_or(zmask) : 0xFFFFFFFFu;
 #define SIMB_INT_ONE(m)                                                                 \
     if ((m) < M && net.models[m].type != MT_PASSIVE && ((wm >> (m)) & 1u)) {            \
         if (((zmask >> (m)) & 1u) && !ln.err) {                                         \
