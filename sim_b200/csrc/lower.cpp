@@ -976,6 +976,13 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
             }
             if (want > 65535u) want = 65535u;
             if (want > pm[i].ring_cap) pm[i].ring_cap = want;
+            // a ParallelGateway with ONE input completes every collection on arrival and sends it in the same step
+            // (parallel_gateway.rs:100-143): its table never holds more than one step's arrivals, not queue_capacity
+            if (net.models[i].type == MT_PARALLEL_GATEWAY && net.models[i].n_in == 1) {
+                uint32_t cap = std::max<uint32_t>(8u, 2u * burst_in[i]);
+                if (cap < pm[i].preload.size()) cap = (uint32_t)pm[i].preload.size();
+                if (cap < pm[i].ring_cap) pm[i].ring_cap = cap;
+            }
         }
     }
     // mailbox bound: messages one firing of a model can emit = jobs per firing x deliveries per port (a
