@@ -81,6 +81,17 @@ def workload(name):
     return models, conns, stat
 
 
+def json_safe(v):
+    """NaN / infinity are not JSON: null."""
+    if isinstance(v, dict):
+        return {k: json_safe(x) for k, x in v.items()}
+    if isinstance(v, (list, tuple)):
+        return [json_safe(x) for x in v]
+    if isinstance(v, float) and (v != v or v in (float("inf"), float("-inf"))):
+        return None
+    return v
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -451,7 +462,7 @@ def main():
                "sample": "%d replications x step_until(%g), one replication per thread, %d threads, %.1f s" % (nreps, args.until, cores, cdt)}
 
     if rank == 0:
-        print(json.dumps({
+        print(json.dumps(json_safe({
             "metric": metric_name(args.network, args.until), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt_max / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -465,7 +476,7 @@ def main():
             "gpu_launches": int(launches * world + 2 * args.steps * world),
             "clocks": clocks, "roofline": roofline, "hbm_streaming_k1": k1, "configs": configs, "strong_scaling": strong,
             "cpu_baseline": cpu, "e2e": e2e, "statistic": ci,
-        }))
+        }), allow_nan=False))
     if world > 1:
         dist.destroy_process_group()
 

@@ -1476,29 +1476,79 @@ int model_state(simb_sim* s, uint64_t rep, uint32_t m, const std::vector<uint32_
 // Simulation { models, connectors, messages, services } (mod.rs:37-45) of one replication
 int simulation_doc(simb_sim* s, uint64_t rep, json::Value* doc) {
     if (rep >= s->st.n) return fail(SIMB_ERR_INVALID_ARGUMENT, "replication index out of range");
-    if (s->hn.desc.n_coupled)
-        return fail(SIMB_ERR_UNSUPPORTED_MODEL, "get_json / get_yaml of a simulation with Coupled models is not implemented "
-                                                "(use simb_get_state for checkpoints)");
+
     CUDA_TRY(cudaSetDevice(s->cfg.device));
     std::vector<uint32_t> w;
     std::vector<double> d;
     int e = column_w(s, rep, &w);
     if (e) return e;
     if ((e = column_d(s, rep, &d))) return e;
-    json::Value models = jarr();
-    for (uint32_t m = 0; m < s->hn.desc.n_models; m++) {
-        // Model::serialize (model.rs:28-41): id, type, then the model's own fields -- the posted document's, with
-        // `state` replaced by the live state
+    // Model::serialize (model.rs:28-41): id, type, then the model's own fields -- the posted document's, with `state`
+    // replaced by the live state
+    auto model_doc = [&](uint32_t m, const json::Value* src, json::Value* out) -> int {
         json::Value mo = jobj();
-        const json::Value* src = (s->models_doc.is_array() && m < s->models_doc.arr.size()) ? &s->models_doc.arr[m] : nullptr;
         mo.obj.push_back({"id", jstr(s->hn.models[m].id)});
         mo.obj.push_back({"type", jstr(s->hn.models[m].type)});
         if (src && src->is_object())
             for (auto& kv : src->obj)
                 if (kv.first != "id" && kv.first != "type" && kv.first != "state") mo.obj.push_back(kv);
         json::Value st;
-        if ((e = model_state(s, rep, m, w, d, &st))) return e;
+        int e2 = model_state(s, rep, m, w, d, &st);
+        if (e2) return e2;
         if (st.kind == json::Value::Object) mo.obj.push_back({"state", st});
+        *out = mo;
+        return 0;
+    };
+    json::Value models = jarr();
+    for (size_t t = 0; t < s->hn.tops.size(); t++) {
+        const HostTop& top = s->hn.tops[t];
+        const json::Value* src = (s->models_doc.is_array() && t < s->models_doc.arr.size()) ? &s->models_doc.arr[t] : nullptr;
+        json::Value mo;
+        if (top.coupled < 0) {
+            if ((e = model_doc((uint32_t)top.flat, src, &mo))) return e;
+            models.arr.push_back(mo);
+            continue;
+        }
+        // Coupled (coupled.rs:14-25): its fields as posted, the components with their live state, and its own state:
+        // the parked messages (:69-84)
+        const HostCoupled& hc = s->hn.coupled[top.coupled];
+        const SimbCoupledDesc& cd = s->hn.desc.coupled[top.coupled];
+        mo = jobj();
+        mo.obj.push_back({"id", jstr(hc.id)});
+        mo.obj.push_back({"type", jstr("Coupled")});
+        const json::Value* comps_src = src ? src->get("components") : nullptr;
+        if (src && src->is_object())
+            for (auto& kv : src->obj) {
+                if (kv.first == "id" || kv.first == "type" || kv.first == "state") continue;
+                if (kv.first != "components") {
+                    mo.obj.push_back(kv);
+                    continue;
+                }
+                json::Value comps = jarr();
+                for (int k = 0; k < hc.count; k++) {
+                    json::Value cm;
+                    const json::Value* csrc = (comps_src && comps_src->is_array() && (size_t)k < comps_src->arr.size()) ? &comps_src->arr[k] : nullptr;
+                    if ((e = model_doc((uint32_t)(hc.first + k), csrc, &cm))) return e;
+                    comps.arr.push_back(cm);
+                }
+                mo.obj.push_back({"components", comps});
+            }
+        json::Value st = jobj(), parked = jarr();
+        for (uint32_t i = 0; i < w[cd.wrow]; i++) {
+            uint32_t c = 0, tp = 0;
+            CUDA_TRY(cudaMemcpy(&c, s->st.ring_w + (uint64_t)(cd.ring_w0 + i) * s->st.stride + rep, 4, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(&tp, s->st.ring_w + (uint64_t)(cd.ring_w1 + i) * s->st.stride + rep, 4, cudaMemcpyDeviceToHost));
+            const uint32_t comp = tp & 0xFFu, port = (tp >> 8) & 0xFFu;
+            json::Value pm = jobj();
+            pm.obj.push_back({"componentId", jstr(comp < s->hn.models.size() ? s->hn.models[comp].id : std::string())});
+            pm.obj.push_back({"port", jstr(comp < s->hn.models.size() && port < s->hn.models[comp].ports_in.size()
+                                               ? s->hn.models[comp].ports_in[port] : std::string())});
+            pm.obj.push_back({"content", jstr(s->hn.render(c))});
+            parked.arr.push_back(pm);
+        }
+        st.obj.push_back({"parkedMessages", parked});
+        st.obj.push_back({"records", jarr()});
+        mo.obj.push_back({"state", st});
         models.arr.push_back(mo);
     }
     json::Value msgs = jarr();

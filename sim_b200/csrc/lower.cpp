@@ -526,6 +526,17 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
         if (!couplings("externalInputCouplings", false, true, &hc.eic) || !couplings("externalOutputCouplings", true, false, &hc.eoc) ||
             !couplings("internalCouplings", true, true, &hc.ic))
             return c.fail(13, hc.id + ": externalInputCouplings / externalOutputCouplings / internalCouplings missing or malformed");
+        if (const Value* cst = j.get("state"))
+            if (const Value* pk = cst->get("parkedMessages")) {
+                if (!pk->is_array()) return c.fail(13, hc.id + ": state.parkedMessages must be an array");
+                for (auto& e : pk->arr) {
+                    HostCoupled::Parked pm_;
+                    if (!e.is_object() || !get_str(e, "componentId", &pm_.component_id) || !get_str(e, "port", &pm_.port) ||
+                        !get_str(e, "content", &pm_.content))
+                        return c.fail(13, hc.id + ": state.parkedMessages entries need componentId, port and content");
+                    hc.parked.push_back(pm_);
+                }
+            }
         top.coupled = (int)hn.coupled.size();
         hn.coupled.push_back(hc);
         hn.tops.push_back(top);
@@ -1088,6 +1099,7 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
         cd.count = (uint8_t)hn.coupled[k].count;
         // what one firing parks stays until the next firing, which first delivers it: twice the per-firing bound
         cd.ring_cap = opt.queue_capacity ? tcap : clamp_u32(std::max<uint64_t>(16, 2 * park_bound[k]), 65535);
+        if (cd.ring_cap < hn.coupled[k].parked.size()) cd.ring_cap = clamp_u32(hn.coupled[k].parked.size(), 65535);
         cd.ring_w0 = rw;
         rw += cd.ring_cap;
         cd.ring_w1 = rw;
@@ -1130,6 +1142,18 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
         if (net.models[i].dist_kind == DK_NORMAL || net.models[i].dist_kind == DK_GAMMA ||
             net.models[i].dist_kind == DK_LOGNORMAL)
             net.uses_normal = 1;
+    }
+    for (size_t k = 0; k < hn.coupled.size(); k++) {  // parked messages given on input
+        const SimbCoupledDesc& cd = net.coupled[k];
+        uint32_t n = 0;
+        for (auto& pmsg : hn.coupled[k].parked) {
+            const int comp = hn.find_component((int)k, pmsg.component_id);
+            if (comp < 0) return c.fail(1, hn.coupled[k].id + ": a parked message names the unknown component `" + pmsg.component_id + "`");
+            hn.ring_preload.push_back(RingPreload{cd.ring_w0 + n, hn.content_code(pmsg.content, &overflow)});
+            hn.ring_preload.push_back(RingPreload{cd.ring_w1 + n, (uint32_t)comp | (hn.resolve_in_port(comp, pmsg.port) << 8)});
+            n++;
+        }
+        hn.w_init[cd.wrow] = n;
     }
     for (uint32_t k = 0; k < net.n_phase_words; k++) hn.w_init[net.wrow_phase + k] = phase_words[k];
     if (overflow) return c.fail(32, "content intern table overflow (more than 255 distinct names)");

@@ -33,6 +33,10 @@ struct HostCoupled {
     struct Coupling {
         std::string source_id, target_id, source_port, target_port;
     };
+    struct Parked {
+        std::string component_id, port, content;
+    };
+    std::vector<Parked> parked;          // `state.parkedMessages` given on input (coupled.rs:69-84)
     std::vector<Coupling> eic, eoc, ic;  // external input (target_id, source_port, target_port), external output
                                          // (source_id, source_port, target_port), internal
 };

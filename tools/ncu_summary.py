@@ -40,11 +40,22 @@ def summarise(path):
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     data = [r for r in rows[2:] if "simb_step_kernel" in r[hdr.index("Kernel Name")]]
-    r = data[-1]
+    def complete(row):  # ncu leaves metrics of a launch it could not replay fully as nan / empty
+        try:
+            v = float(row[hdr.index("dram__bytes_read.sum")].replace(",", ""))
+            return v == v
+        except (ValueError, IndexError):
+            return False
+    r = ([x for x in data if complete(x)] or data)[-1]
     res = {"kernel": r[hdr.index("Kernel Name")].split("(")[0], "launches_profiled": len(data), "source": os.path.basename(path)}
     for k, name in WANT.items():
         if k in hdr:
-            v = float(r[hdr.index(k)])
+            try:
+                v = float(r[hdr.index(k)].replace(",", ""))
+            except ValueError:
+                continue
+            if v != v:  # ncu prints nan for a metric it could not collect: leave it out (NaN is not JSON)
+                continue
             u = units[hdr.index(k)]
             if name == "duration_us" and u == "ms":
                 v *= 1e3
