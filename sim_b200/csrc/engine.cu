@@ -419,23 +419,29 @@ int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool inst
     // prefer the wider tile (fewer, larger bulk copies), and keep half of the SM's unified storage for L1
     // when that costs no occupancy (the ring slots live in L1 between steps).
     uint32_t tile = 256, best_warps = 0;
-    for (uint32_t cand = 256; cand >= 32; cand >>= 1) {
-        const uint32_t smem = smem_plan(net, cand, 0, true).total;
-        if (smem > 227u * 1024u) continue;
-        uint32_t ctas = (227u * 1024u) / smem;
-        const uint32_t regs = (cand <= 128u && !instrument && rng_kind == 0) ? 96u : 64u;  // narrow-tile variant
-        const uint32_t by_regs = 65536u / (regs * cand), by_threads = 2048u / cand;
-        if (ctas > by_regs) ctas = by_regs;
-        if (ctas > by_threads) ctas = by_threads;
-        if (ctas > 32u) ctas = 32u;
-        const uint32_t warps = ctas * cand / 32u;
-        // among equals prefer the wider tile (fewer, larger bulk copies) -- except that 128 beats 256: the narrow-tile
-        // instantiation has 96 registers and does not spill (gateway network: 3.7e9 vs 2.8e9 replication-steps/s)
-        if (warps > best_warps || (warps == best_warps && cand == 128u && tile == 256u)) {
-            best_warps = warps;
-            tile = cand;
+    bool zig_global = false;
+    for (int zg = 0; zg < 2; zg++) {  // second round: the ziggurat tables leave shared memory -- taken only if that keeps
+                                      // MORE warps resident
+        for (uint32_t cand = 256; cand >= 32; cand >>= 1) {
+            const uint32_t smem = smem_plan(net, cand, 0, true, zg == 0).total;
+            if (smem > 227u * 1024u) continue;
+            uint32_t ctas = (227u * 1024u) / smem;
+            const uint32_t regs = (cand <= 128u && !instrument && rng_kind == 0) ? 96u : 64u;  // narrow-tile variant
+            const uint32_t by_regs = 65536u / (regs * cand), by_threads = 2048u / cand;
+            if (ctas > by_regs) ctas = by_regs;
+            if (ctas > by_threads) ctas = by_threads;
+            if (ctas > 32u) ctas = 32u;
+            const uint32_t warps = ctas * cand / 32u;
+            // among equals prefer the wider tile (fewer, larger bulk copies) -- except that 128 beats 256: the narrow-tile
+            // instantiation has 96 registers and does not spill (gateway network: 3.7e9 vs 2.8e9 replication-steps/s)
+            if (warps > best_warps || (zg == (zig_global ? 1 : 0) && warps == best_warps && cand == 128u && tile == 256u)) {
+                best_warps = warps;
+                tile = cand;
+                zig_global = zg == 1;
+            }
         }
     }
+    if (const char* zf = getenv("SIMB_ZIG_GLOBAL")) zig_global = *zf == '1';  // A/B switch
     if (best_warps == 0) return (int)cudaErrorInvalidConfiguration;
     if (dims->shape >= 0) tile = SIMB_SHAPE_TILE;  // a baked shape's kernel is compiled for the full tile width
     if (n && n < tile) {
@@ -449,7 +455,9 @@ int engine_configure(const SimbNetDesc& net, uint64_t n, int rng_kind, bool inst
     }
     if (dims->shape >= 0 && tile != SIMB_SHAPE_TILE) dims->shape = -1;  // baked-shape kernels assume the full tile width
     // baked-shape kernels add their Philox draw cache: SIMB_RNG_CACHE draws per replication on fused launches
-    SmemPlan sp = smem_plan(net, tile, dims->shape >= 0 ? SIMB_RNG_CACHE : 0u, dims->shape < 0);
+    if (dims->shape >= 0) zig_global = false;
+    dims->zig_global = zig_global;
+    SmemPlan sp = smem_plan(net, tile, dims->shape >= 0 ? SIMB_RNG_CACHE : 0u, dims->shape < 0, !zig_global);
     if (sp.total > 227u * 1024u) return (int)cudaErrorInvalidConfiguration;
     dims->tile = tile;
     dims->smem_bytes = sp.total;
@@ -478,6 +486,7 @@ int engine_launch_step(const SimbNetDesc& net, const SimbDevState& st, const Sim
     la.tile0 = tile0;
     const bool streaming = la.k <= SIMB_STREAM_MAX_K;
     la.rng_slots = dims.shape >= 0 ? (streaming ? 2u : SIMB_RNG_CACHE) : 0u;
+    la.zig_global = dims.zig_global ? 1u : 0u;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(grid);

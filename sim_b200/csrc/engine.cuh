@@ -13,6 +13,7 @@ struct EngineDims {
     uint32_t grid;        // reserved (the launch uses one CTA per tile)
     int shape;            // baked shape id whose specialised kernel is used, or -1 (generic interpreter)
     bool rare;            // the network draws from Beta / Gamma / LogNormal / Weibull (generic kernel variant)
+    bool zig_global;      // ziggurat x tables read through the L1 (frees 2-4 KB of shared memory per CTA)
     bool basic;           // only Generator / Processor / Storage / LoadBalancer / Passive models (generic kernel variant)
 };
 int engine_match_shape(const SimbNetDesc& net, int rng_kind, bool instrument);

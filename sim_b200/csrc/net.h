@@ -230,6 +230,7 @@ struct SimbLaunch {
     uint32_t l2_keep;     // 1 = the state tile copies carry the L2 evict_last hint (streaming passes)
     uint32_t lockstep;    // generic interpreter, A/B switch: 1 = the lanes of a warp wait for each other at every step
                           // boundary (0 = each lane runs through its own steps)
-    uint32_t reserved;
+    uint32_t zig_global;  // generic interpreter: the ziggurat x tables are read through the L1 instead of being staged in
+                          // shared memory (EngineDims::zig_global: chosen when it lets one more CTA stay resident)
     double until;
 };

@@ -82,7 +82,10 @@ struct SmemPlan {
 // from global memory) and the value table are copied to shared memory at the start of a launch
 #define SIMB_TAB_SMEM_WORDS SIMB_TAB_CONN
 // `rng_slots`: Philox draws cached per replication in shared memory (baked-shape kernels; 0 = none)
-__host__ __device__ inline SmemPlan smem_plan(const SimbNetDesc& net, uint32_t tile, uint32_t rng_slots, bool tables) {
+// `zig`: the ziggurat x tables are staged in shared memory (else read through the L1: 4 KB less per CTA, which buys the
+// 16-model networks a fifth resident CTA)
+__host__ __device__ inline SmemPlan smem_plan(const SimbNetDesc& net, uint32_t tile, uint32_t rng_slots, bool tables,
+                                              bool zig = true) {
     SmemPlan p;
     uint32_t o = 0;
     p.off_bar = o;  // three mbarriers: one per stage + one for the tables
@@ -90,9 +93,9 @@ __host__ __device__ inline SmemPlan smem_plan(const SimbNetDesc& net, uint32_t t
     p.off_red = o;
     o += 32;
     p.off_expx = o;
-    if (net.uses_exp) o += 2064;
+    if (net.uses_exp && zig) o += 2064;
     p.off_normx = o;
-    if (net.uses_normal) o += 2064;
+    if (net.uses_normal && zig) o += 2064;
     o = (o + 15u) & ~15u;
     p.off_tab = o;
     if (tables) o += SIMB_TAB_SMEM_WORDS * 4u;
@@ -173,7 +176,8 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
     const uint32_t tile = SHAPE >= 0 ? SIMB_SHAPE_TILE : blockDim.x;
     const uint32_t tid = threadIdx.x;
     const uint32_t rng_slots = SHAPE >= 0 ? la.rng_slots : 0u;
-    const SmemPlan sp = smem_plan(net, tile, rng_slots, SHAPE < 0);
+    const bool zig_smem = SHAPE >= 0 || la.zig_global == 0u;
+    const SmemPlan sp = smem_plan(net, tile, rng_slots, SHAPE < 0, zig_smem);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + sp.off_bar);
     unsigned long long* s_red = reinterpret_cast<unsigned long long*>(smem + sp.off_red);
     double* s_expx = reinterpret_cast<double*>(smem + sp.off_expx);
@@ -203,10 +207,10 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
     if (tid < 32) {
         if (tid == 0) {
             mbar_expect_tx(bar, net.n_drows * tile * 8u + net.n_wrows * tile * 4u +
-                                    (net.uses_exp ? ZIG_BYTES : 0u) + (net.uses_normal ? ZIG_BYTES : 0u));
+                                    (net.uses_exp && zig_smem ? ZIG_BYTES : 0u) + (net.uses_normal && zig_smem ? ZIG_BYTES : 0u));
             // ziggurat x tables ride on the same barrier (random per-lane index -> shared memory, not constant)
-            if (net.uses_exp) bulk_g2s(s_expx, ZIG_EXP_X, ZIG_BYTES, bar);
-            if (net.uses_normal) bulk_g2s(s_normx, ZIG_NORM_X, ZIG_BYTES, bar);
+            if (net.uses_exp && zig_smem) bulk_g2s(s_expx, ZIG_EXP_X, ZIG_BYTES, bar);
+            if (net.uses_normal && zig_smem) bulk_g2s(s_normx, ZIG_NORM_X, ZIG_BYTES, bar);
         }
         __syncwarp();
         const uint64_t pol = l2_policy_evict_last();
@@ -232,9 +236,9 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
         for (uint32_t i = tid; i < SIMB_VTAB_WORDS; i += tile) s_vt[i] = __ldg(st.vtab + i);
         __syncthreads();
     }
-    tab.exp_x = s_expx;
+    tab.exp_x = zig_smem ? s_expx : ZIG_EXP_X;
     tab.exp_f = ZIG_EXP_F;
-    tab.norm_x = s_normx;
+    tab.norm_x = zig_smem ? s_normx : ZIG_NORM_X;
     tab.norm_f = ZIG_NORM_F;
     tab.rng_cache = reinterpret_cast<uint64_t*>(smem + sp.off_rng);
     tab.rng_slots = rng_slots;
