@@ -402,6 +402,8 @@ def main():
         w = Simulation.post_json(mj_, cj_, min(sub, 1 << 16), seed=42, device=local_rank, stat_model_id=stat_, **post_kw)
         w.step_until(until)
         w.close()
+        if sub > (1 << 16):  # ... and one post of a full shard, so that the device memory pool has its size before the clock starts
+            Simulation.post_json(mj_, cj_, sub, seed=42, device=local_rank, stat_model_id=stat_, **post_kw).close()
         barrier()
         t1 = time.perf_counter()
         done = 0
