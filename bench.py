@@ -166,7 +166,7 @@ def job_config(network, replications_per_gpu, until):
     """The `config` object of the JSON line: what the job IS (identical in both arms; how each arm runs it is
     described in `engine` / `cpu_baseline.sample`)."""
     return {"workload": WORKLOADS.get(network, network), "replications_per_gpu": replications_per_gpu, "until": until,
-            "rng": "philox4x32-10, key = (global replication index, seed 42)",
+            "rng": "philox4x32-10, key = seed 42, counter = (block, global replication index)",
             "parallelism": "independent replications, contiguous index blocks per GPU, no data-path collective"}
 
 
