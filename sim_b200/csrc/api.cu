@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -522,49 +523,100 @@ int read_mail(simb_sim* s, CarriedMail* cm) {
     }
     return 0;
 }
-// old -> new (content code, route word); the interned names of `old` must already be interned in `nw` (name_map)
+// Simulation::put keeps `messages` as they are -- strings (mod.rs:82-85) -- and the next step hands each to whatever
+// models of the NEW network carry its target id (mod.rs:203-221).  So: every Message in flight (the later deliveries of
+// one Message, flagged RT_CONT / ROUTE_INJECTED_CONT, are dropped first) goes back to its (target id, target port)
+// names and is expanded into the deliveries those names have in the new network, in the order the messages were sent.
+// The interned names of `old` must already be interned in `nw` (name_map).
 void remap_mail(const HostNet& old, const HostNet& nw, const std::vector<uint32_t>& name_map, CarriedMail* cm) {
-    // route index of the old network -> route word (without sequence number) in the new one
-    std::vector<uint32_t> route_map(SIMB_MAX_ROUTES, 0);
+    const std::string lost = "\x01(no such port)";
+    auto by_name = [&](const std::string& id, const std::string& port) {
+        std::vector<uint32_t> w;
+        for (const HostNet::Delivery& d : nw.deliveries(id, port))
+            w.push_back(ROUTE_WORD(d.model, d.port, w.empty() ? ROUTE_INJECTED : ROUTE_INJECTED_CONT, 0));
+        if (w.empty()) w.push_back(ROUTE_WORD(0xFF, SIMB_PORT_UNKNOWN, ROUTE_INJECTED, 0));
+        return w;
+    };
+    // a message sent over a connector: the same connector of the new network carries it (its deliveries are consecutive
+    // routes, the first plain); if there is none it renders as an injected message
+    std::vector<std::vector<uint32_t>> of_route(old.desc.n_routes);
     for (uint32_t r = 0; r < old.desc.n_routes; r++) {
+        if (old.desc.routes[r].connector & (RT_PARK | RT_CONT)) continue;
         const HostConnector& oc = old.connectors[RT_CONN(old.desc.routes[r].connector)];
-        const int tm = nw.find_model(oc.target_id);
-        const uint32_t port = tm < 0 ? SIMB_PORT_UNKNOWN : nw.resolve_in_port(tm, oc.target_port);
-        uint32_t nr = ROUTE_INJECTED;  // no connector of the new network carries it: it renders as an injected message
-        for (uint32_t q = 0; q < nw.desc.n_routes; q++) {
+        for (uint32_t q = 0; q < nw.desc.n_routes && of_route[r].empty(); q++) {
+            if (nw.desc.routes[q].connector & (RT_PARK | RT_CONT)) continue;
             const HostConnector& nc = nw.connectors[RT_CONN(nw.desc.routes[q].connector)];
-            if (nc.source_id == oc.source_id && nc.source_port == oc.source_port && nc.target_id == oc.target_id &&
-                nc.target_port == oc.target_port) {
-                nr = q;
-                break;
+            if (nc.source_id != oc.source_id || nc.source_port != oc.source_port || nc.target_id != oc.target_id ||
+                nc.target_port != oc.target_port)
+                continue;
+            for (uint32_t k = q; k < nw.desc.n_routes; k++) {
+                if (k > q && !(nw.desc.routes[k].connector & RT_CONT)) break;
+                of_route[r].push_back(ROUTE_WORD(nw.desc.routes[k].tgt_model, nw.desc.routes[k].tgt_port, k, 0));
             }
         }
-        route_map[r] = ROUTE_WORD(tm < 0 ? 0xFF : tm, port, nr, 0);
+        if (of_route[r].empty()) of_route[r] = by_name(oc.target_id, oc.target_port);
     }
-    for (uint32_t j = 0; j < cm->max_np; j++)
-        for (size_t r = 0; r < cm->npend.size(); r++) {
-            if (j >= cm->npend[r]) continue;
-            uint32_t& c = cm->content[j][r];
+    // an injected message: (model, port) indices back to the names inject_input was given
+    std::map<uint32_t, std::vector<uint32_t>> of_injected;
+    auto injected = [&](uint32_t tgt, uint32_t op) -> const std::vector<uint32_t>& {
+        const uint32_t key = tgt << 8 | op;
+        auto it = of_injected.find(key);
+        if (it != of_injected.end()) return it->second;
+        std::string id = lost, port = lost;
+        if (tgt < old.models.size()) {
+            const HostModel& om = old.models[tgt];
+            if (om.coupled < 0) {
+                id = om.id;
+                if (op < om.ports_in.size()) port = om.ports_in[op];
+            } else {
+                id = old.coupled[om.coupled].id;
+                for (auto& e : old.coupled[om.coupled].eic)
+                    if (e.target_id == om.id && old.resolve_in_port((int)tgt, e.target_port) == op) {
+                        port = e.source_port;
+                        break;
+                    }
+            }
+        }
+        return of_injected[key] = by_name(id, port);
+    };
+    const size_t n = cm->npend.size();
+    std::vector<std::vector<uint32_t>> content, route;
+    std::vector<uint32_t> npend(n, 0), order;
+    uint32_t max_np = 0;
+    for (size_t r = 0; r < n; r++) {
+        order.clear();
+        for (uint32_t j = 0; j < cm->npend[r]; j++) order.push_back(j);
+        std::stable_sort(order.begin(), order.end(),
+                         [&](uint32_t x, uint32_t y) { return ROUTE_SEQ(cm->route[x][r]) < ROUTE_SEQ(cm->route[y][r]); });
+        uint32_t np = 0;
+        for (uint32_t j : order) {
+            const uint32_t rw = cm->route[j][r], rr = ROUTE_R(rw);
+            if (rr == ROUTE_INJECTED_CONT) continue;
+            if (rr != ROUTE_INJECTED && rr < old.desc.n_routes && (old.desc.routes[rr].connector & RT_CONT)) continue;
+            uint32_t c = cm->content[j][r];
             if (c != SIMB_CONTENT_NONE) {
                 const uint32_t pfx = c >> 24;
                 c = ((pfx < name_map.size() ? name_map[pfx] : pfx) << 24) | (c & 0xFFFFFFu);
             }
-            uint32_t& rw = cm->route[j][r];
-            const uint32_t seq = ROUTE_SEQ(rw);
-            if (ROUTE_R(rw) == ROUTE_INJECTED || ROUTE_R(rw) >= old.desc.n_routes) {  // inject_input: (model, port) by name
-                const uint32_t tgt = ROUTE_TGT(rw);
-                int tm = -1;
-                uint32_t port = SIMB_PORT_UNKNOWN;
-                if (tgt < old.models.size()) {
-                    tm = nw.find_model(old.models[tgt].id);
-                    const uint32_t op = ROUTE_PORT(rw);
-                    if (tm >= 0 && op < old.models[tgt].ports_in.size()) port = nw.resolve_in_port(tm, old.models[tgt].ports_in[op]);
+            const std::vector<uint32_t>& words =
+                (rr == ROUTE_INJECTED || rr >= old.desc.n_routes) ? injected(ROUTE_TGT(rw), ROUTE_PORT(rw)) : of_route[rr];
+            for (uint32_t w : words) {
+                if (np >= content.size()) {
+                    content.emplace_back(n, 0u);
+                    route.emplace_back(n, 0u);
                 }
-                rw = ROUTE_WORD(tm < 0 ? 0xFF : tm, port, ROUTE_INJECTED, seq);
-            } else {
-                rw = route_map[ROUTE_R(rw)] | (seq << 24);
+                content[np][r] = c;
+                route[np][r] = w | ((np & 0xFFu) << 24);
+                np++;
             }
         }
+        npend[r] = np;
+        max_np = std::max(max_np, np);
+    }
+    cm->npend.swap(npend);
+    cm->content.swap(content);
+    cm->route.swap(route);
+    cm->max_np = max_np;
 }
 int write_mail(simb_sim* s, const CarriedMail& cm) {
     const SimbNetDesc& net = s->hn.desc;
@@ -638,10 +690,11 @@ int simb_put_json(simb_sim* s, const char* models_json, const char* connectors_j
         // carry the pending messages over by name; the new mailbox must hold what is in flight (the reference's Vec
         // has no bound): lower once more with that as the explicit bound if the derived one is smaller
         if ((e = read_mail(s, &cm))) return e;
+        if (cm.max_np) remap_mail(s->hn, hn, name_map, &cm);
         if (cm.max_np <= hn.desc.max_pending) break;
+        // (capacities only: the second lowering has the same models, routes and names, so the remapped words stand)
         opt.max_pending = cm.max_np;
     }
-    if (!same_meaning && cm.max_np) remap_mail(s->hn, hn, name_map, &cm);
     const SimbNetDesc& o = s->hn.desc;
     const SimbNetDesc& nw = hn.desc;
     int e = 0;
@@ -762,23 +815,11 @@ int simb_inject_input(simb_sim* s, const char* target_id, const char* target_por
     bool overflow = false;
     const uint32_t code = s->hn.content_code(content, &overflow);
     if (overflow) return fail(SIMB_ERR_CAPACITY, "content intern table overflow");
-    // deliveries: the named model, or -- for a Coupled model -- the components its external input couplings name for
-    // that port, in coupling order (coupled.rs:102-131); an unknown target is kept and never delivered (mod.rs:204-216)
+    // deliveries: every posted model of that id (mod.rs:203-221), for a Coupled model the components its external input
+    // couplings name for that port (coupled.rs:102-131); an unknown target is kept and never delivered
     std::vector<uint32_t> words;
-    const int tt = s->hn.find_top(target_id);
-    if (tt >= 0 && s->hn.tops[tt].coupled >= 0) {
-        const int cpl = s->hn.tops[tt].coupled;
-        for (auto& e : s->hn.coupled[cpl].eic) {
-            if (e.source_port != target_port) continue;
-            const int comp = s->hn.find_component(cpl, e.target_id);
-            if (comp < 0) continue;
-            words.push_back(ROUTE_WORD(comp, s->hn.resolve_in_port(comp, e.target_port),
-                                       words.empty() ? ROUTE_INJECTED : ROUTE_INJECTED_CONT, 0));
-        }
-    } else if (tt >= 0) {
-        const int tm = s->hn.tops[tt].flat;
-        words.push_back(ROUTE_WORD(tm, s->hn.resolve_in_port(tm, target_port), ROUTE_INJECTED, 0));
-    }
+    for (const HostNet::Delivery& d : s->hn.deliveries(target_id, target_port))
+        words.push_back(ROUTE_WORD(d.model, d.port, words.empty() ? ROUTE_INJECTED : ROUTE_INJECTED_CONT, 0));
     if (words.empty()) words.push_back(ROUTE_WORD(0xFF, SIMB_PORT_UNKNOWN, ROUTE_INJECTED, 0));
     uint8_t* d_mask = nullptr;
     if (replica_mask) {
@@ -868,7 +909,8 @@ int simb_get_messages(simb_sim* s, uint64_t rep, simb_message* out, uint64_t cap
                      [](const std::pair<uint32_t, uint32_t>& a, const std::pair<uint32_t, uint32_t>& b) {
                          return ROUTE_SEQ(a.second) < ROUTE_SEQ(b.second);
                      });
-    if (net.n_coupled) {  // one Message to a Coupled model sits in the mailbox once per component it reaches: show it once
+    {  // one Message that several models receive (a Coupled model's components, posted models sharing an id) sits in
+       // the mailbox once per delivery: show it once
         std::vector<std::pair<uint32_t, uint32_t>> shown;
         for (auto& mw : mail) {
             const uint32_t r = ROUTE_R(mw.second);

@@ -376,6 +376,10 @@ static bool uses_rare_variables(const SimbNetDesc& net) {
         const uint32_t k = net.models[m].dist_kind;
         if (k == DK_GAMMA || k == DK_LOGNORMAL || k == DK_WEIBULL || k == DK_BETA) return true;
     }
+    // one Message delivered more than once (posted models sharing an id; the components of a Coupled model): the lean
+    // builds compile the "not traced, not counted" rule of the later deliveries out
+    for (uint32_t r = 0; r < net.n_routes; r++)
+        if (net.routes[r].connector & (RT_CONT | RT_PARK)) return true;
     return false;
 }
 

@@ -73,6 +73,27 @@ int HostNet::find_component(int ci, const std::string& id) const {
         if (models[k].id == id) return k;
     return -1;
 }
+std::vector<HostNet::Delivery> HostNet::deliveries(const std::string& id, const std::string& port, bool* bad_coupling) const {
+    std::vector<Delivery> out;
+    for (size_t t = 0; t < tops.size(); t++) {
+        if (tops[t].id != id) continue;
+        if (tops[t].coupled < 0) {
+            out.push_back(Delivery{tops[t].flat, resolve_in_port(tops[t].flat, port)});
+            continue;
+        }
+        const int cpl = tops[t].coupled;
+        for (auto& e : coupled[cpl].eic) {
+            if (e.source_port != port) continue;
+            const int comp = find_component(cpl, e.target_id);
+            if (comp < 0) {  // the reference unwraps a None here (coupled.rs:173-176)
+                if (bad_coupling) *bad_coupling = true;
+                continue;
+            }
+            out.push_back(Delivery{comp, resolve_in_port(comp, e.target_port)});
+        }
+    }
+    return out;
+}
 uint32_t HostNet::intern(const std::string& s, bool* overflow) {
     for (size_t i = 0; i < names.size(); i++)
         if (names[i] == s) return (uint32_t)i;
@@ -468,7 +489,8 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
         if (!q.parse(jc)) return c.fail(13, "connectors: " + q.err);
     }
     if (!jm.is_array() || !jc.is_array()) return c.fail(13, "models and connectors must be JSON arrays");
-    if (jm.arr.empty()) return c.fail(1, "a simulation needs at least one model");
+    // (an empty model list is a simulation too: Simulation::post does not look, and every step adds +INF to the clock,
+    // mod.rs:225-236)
 
     HostNet& hn = *out;
     hn = HostNet();
@@ -542,7 +564,6 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
         hn.tops.push_back(top);
     }
     if (flat.size() > SIMB_MAX_MODELS) return c.fail(32, "more than 32 models");
-    if (flat.empty()) return c.fail(1, "a simulation needs at least one atomic model");
     net.n_models = (uint32_t)flat.size();
     std::vector<PendingModel> pm(flat.size());
     uint32_t n_wcum = 0;
@@ -844,9 +865,8 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
         if (hm.ports_out.size() > 64) return c.fail(32, hm.id + ": too many output ports");
         hn.models.push_back(hm);
     }
-    for (size_t i = 0; i < hn.tops.size(); i++)
-        for (size_t k = i + 1; k < hn.tops.size(); k++)
-            if (hn.tops[i].id == hn.tops[k].id) return c.fail(1, "duplicate model id `" + hn.tops[i].id + "`");
+    // (two posted models may share an id: Simulation::post does not look, and step() hands a message to every model
+    // whose id matches, mod.rs:203-221 -- see HostNet::deliveries)
     for (auto& hc : hn.coupled)
         for (int i = hc.first; i < hc.first + hc.count; i++)
             for (int k = i + 1; k < hc.first + hc.count; k++)
@@ -883,29 +903,17 @@ int lower_network(const char* models_json, const char* connectors_json, const Lo
         net.routes[n_routes++] = r;
         return true;
     };
-    // the deliveries of one message over top-level connector ci: one model, or -- for a Coupled target -- every
-    // component its external input couplings name for that port, in coupling order (coupled.rs:102-131, 166-184)
+    // the deliveries of one message over top-level connector ci: the first is the Message of the reference (traced,
+    // counted), the others -- a second model with the same id, further components of a Coupled model -- ride along
+    // flagged RT_CONT; no model of that id: the message is kept for one step and never delivered
     auto send_over = [&](size_t ci) -> bool {
         const HostConnector& hc = hn.connectors[ci];
-        const int tt = hn.find_top(hc.target_id);
-        if (tt >= 0 && hn.tops[tt].coupled >= 0) {
-            const int cpl = hn.tops[tt].coupled;
-            uint32_t k = 0;
-            for (auto& e : hn.coupled[cpl].eic) {
-                if (e.source_port != hc.target_port) continue;
-                const int comp = hn.find_component(cpl, e.target_id);
-                if (comp < 0) {
-                    bad_eic = true;  // the reference unwraps a None here (coupled.rs:173-176)
-                    return false;
-                }
-                if (!push_route(comp, hn.resolve_in_port(comp, e.target_port), (uint32_t)ci | (k ? RT_CONT : 0u))) return false;
-                k++;
-            }
-            if (k == 0) return push_route(-1, 0, (uint32_t)ci);  // no coupling takes that port: the message evaporates
-            return true;
-        }
-        const int tm = tt >= 0 ? hn.tops[tt].flat : -1;
-        return push_route(tm, tm < 0 ? 0u : hn.resolve_in_port(tm, hc.target_port), (uint32_t)ci);
+        const std::vector<HostNet::Delivery> dv = hn.deliveries(hc.target_id, hc.target_port, &bad_eic);
+        if (bad_eic) return false;
+        if (dv.empty()) return push_route(-1, 0, (uint32_t)ci);
+        for (size_t k = 0; k < dv.size(); k++)
+            if (!push_route(dv[k].model, dv[k].port, (uint32_t)ci | (k ? RT_CONT : 0u))) return false;
+        return true;
     };
     for (size_t i = 0; i < hn.models.size(); i++) {
         SimbModelDesc& md = net.models[i];

@@ -71,6 +71,14 @@ struct HostNet {
     int find_model(const std::string& id) const;  // a TOP-LEVEL atomic model (what Simulation::get_status etc. can name)
     int find_top(const std::string& id) const;
     int find_component(int coupled_index, const std::string& id) const;  // flat index, or -1
+    // Every events_ext call one Message addressed to (id, port) leads to, in the order the reference makes them
+    // (mod.rs:203-221: EVERY posted model whose id matches, in model order; coupled.rs:102-131, 166-184: for a Coupled
+    // model the components its external input couplings name for that port, in coupling order).
+    struct Delivery {
+        int model;      // flat index
+        uint32_t port;  // input-port index as the device sees it
+    };
+    std::vector<Delivery> deliveries(const std::string& id, const std::string& port, bool* bad_coupling = nullptr) const;
     uint32_t intern(const std::string& s, bool* overflow);
     // canonical content code of an arbitrary string (DESIGN.md "content codes")
     uint32_t content_code(const std::string& content, bool* overflow);

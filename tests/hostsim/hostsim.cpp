@@ -213,25 +213,27 @@ void hs_step_until(void* hv, double until) { dispatch((HS*)hv, 1, 0, until); }
 int hs_inject(void* hv, const char* tgt, const char* port, const char* content) {
     HS* h = (HS*)hv;
     const SimbNetDesc& net = h->hn.desc;
-    int tm = h->hn.find_model(tgt);
     bool ov = false;
     uint32_t code = h->hn.content_code(content, &ov);
-    uint32_t pidx = tm < 0 ? SIMB_PORT_UNKNOWN : h->hn.resolve_in_port(tm, port);
-    uint32_t rw0 = ROUTE_WORD(tm < 0 ? 0xFF : tm, pidx, ROUTE_INJECTED, 0);
-    for (uint64_t r = 0; r < h->n; r++) {
-        uint32_t& ctl = h->w[(size_t)net.wrow_ctl * h->n + r];
-        uint32_t np = CTL_NPEND(ctl);
-        if (np >= net.max_pending) return 32;
-        const uint32_t rw = rw0 | (np << 24);
-        if (np < net.pend_tile) {
-            h->w[(size_t)(net.wrow_pend + 2 * np) * h->n + r] = code;
-            h->w[(size_t)(net.wrow_pend + 2 * np + 1) * h->n + r] = rw;
-        } else {
-            h->mail[(size_t)(2 * (np - net.pend_tile)) * h->n + r] = code;
-            h->mail[(size_t)(2 * (np - net.pend_tile) + 1) * h->n + r] = rw;
+    std::vector<uint32_t> words;  // as simb_inject_input (api.cu): every model of that id, the components of a Coupled one
+    for (const HostNet::Delivery& d : h->hn.deliveries(tgt, port))
+        words.push_back(ROUTE_WORD(d.model, d.port, words.empty() ? ROUTE_INJECTED : ROUTE_INJECTED_CONT, 0));
+    if (words.empty()) words.push_back(ROUTE_WORD(0xFF, SIMB_PORT_UNKNOWN, ROUTE_INJECTED, 0));
+    for (uint32_t rw0 : words)
+        for (uint64_t r = 0; r < h->n; r++) {
+            uint32_t& ctl = h->w[(size_t)net.wrow_ctl * h->n + r];
+            uint32_t np = CTL_NPEND(ctl);
+            if (np >= net.max_pending) return 32;
+            const uint32_t rw = rw0 | (np << 24);
+            if (np < net.pend_tile) {
+                h->w[(size_t)(net.wrow_pend + 2 * np) * h->n + r] = code;
+                h->w[(size_t)(net.wrow_pend + 2 * np + 1) * h->n + r] = rw;
+            } else {
+                h->mail[(size_t)(2 * (np - net.pend_tile)) * h->n + r] = code;
+                h->mail[(size_t)(2 * (np - net.pend_tile) + 1) * h->n + r] = rw;
+            }
+            ctl = CTL_MAKE(CTL_ERR(ctl), CTL_EPOCH(ctl), np + 1, 0);
         }
-        ctl = CTL_MAKE(CTL_ERR(ctl), CTL_EPOCH(ctl), np + 1, 0);
-    }
     return 0;
 }
 void hs_get_time(void* hv, double* out) {

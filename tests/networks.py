@@ -562,6 +562,27 @@ def coupled_pipeline(store_records=False):
     return models, connectors
 
 
+def shared_ids():
+    """Two posted models may share an id: `Simulation::post` does not look (mod.rs:49-56), and `step` hands a message
+    to EVERY model whose id matches (mod.rs:203-221), while `get_message_target_ids` finds the connectors of both by
+    their common source id (mod.rs:155-182).  One connector therefore feeds both processors, and one collects from both."""
+    T = ContinuousRandomVariable
+    models = [
+        Model.new("gen", Generator.new(T.Exp(0.8), None, "job", False, None)),
+        Model.new("twin", Processor.new(T.Exp(1.5), 6, "job", "done", False, None)),
+        Model.new("gate", Gate.new("job", "activation", "deactivation", "job", False)),
+        Model.new("twin", Processor.new(T.Uniform(0.4, 1.1), 3, "job", "done", False, None)),
+        Model.new("store", Storage.new("store", "read", "stored", False)),
+    ]
+    C = Connector.new
+    connectors = [
+        C("c-in", "gen", "twin", "job", "job"),
+        C("c-out", "twin", "gate", "done", "job"),
+        C("c-store", "gate", "store", "job", "store"),
+    ]
+    return models, connectors
+
+
 COUPLED = {"coupled_closure": coupled_closure, "coupled_pipeline": coupled_pipeline}
 
 ALL = {
@@ -572,4 +593,5 @@ ALL = {
     "generator_passive": generator_passive, "more_variables": more_variables, "beta_variables": beta_variables, "state_injection": state_injection,
     "state_injection_tables": state_injection_tables, "batch_bursts": batch_bursts, "tandem": tandem, "gateway_network": gateway_network,
     "large_mixed": large_mixed, "own_rngs": own_rngs, "coupled_closure": coupled_closure, "coupled_pipeline": coupled_pipeline,
+    "shared_ids": shared_ids,
 }

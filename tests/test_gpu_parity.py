@@ -680,6 +680,34 @@ def test_put_keeps_pending_messages_when_models_are_reordered():
         assert ref[r][0] == 0 and h[r] == ref[r][1] and st[r] == ref[r][2] and _close(t[r], ref[r][3])
 
 
+def test_put_hands_pending_messages_to_every_model_of_their_id():
+    """The messages `put` keeps are strings (mod.rs:82-85); if the new model list has two models of the target id, the
+    next step delivers the kept message to both (mod.rs:203-221) -- and a later `put` back to one model undoes that."""
+    from sim_b200 import Model, Processor, Simulation
+    base, conns = networks.mm1()
+    models = list(base) + [Model.new("processor-01", Processor.new(Exp(2.0), 3, "job", "processed", False, None))]
+    sim, pend, err, ref = _put_case(models, conns)
+    assert pend == [("processor-01", "job", "x 1"), ("storage-01", "store", "y 2")] and err is None
+    h, st, t = sim.get_trace_hash(), sim.get_steps(), sim.get_global_time()
+    for r in range(2):
+        assert ref[r][0] == 0 and h[r] == ref[r][1] and st[r] == ref[r][2] and _close(t[r], ref[r][3])
+    # put twice before stepping: two models of the id, then one again -- one delivery per kept message is left
+    sim = Simulation.post(base, conns, replications=32, seed=17, instrument=True)
+    sim.inject_input(Message("manual", "manual", "processor-01", "job", 0.0, "x 1"))
+    sim.put(models, conns)
+    assert len(sim.get_messages(0)) == 1
+    sim.put(base, conns)
+    sim.step()
+    plain = Simulation.post(base, conns, replications=32, seed=17, instrument=True)
+    plain.inject_input(Message("manual", "manual", "processor-01", "job", 0.0, "x 1"))
+    plain.step()
+    assert (sim.get_events() == plain.get_events()).all() and (sim.get_trace_hash() == plain.get_trace_hash()).all()
+    twins = Simulation.post(models, conns, replications=32, seed=17, instrument=True)
+    twins.inject_input(Message("manual", "manual", "processor-01", "job", 0.0, "x 1"))
+    twins.step()
+    assert (twins.get_events() == plain.get_events() + 1).all()   # one more events_ext: the second processor-01
+
+
 def test_put_re_resolves_ports_and_layout_changes():
     from sim_b200 import Generator, Model, Processor, Storage
     # (a) the processor's input port is renamed: the pending "job" message now names a port it does not have
@@ -706,3 +734,15 @@ def test_put_re_resolves_ports_and_layout_changes():
     h, st, t = sim.get_trace_hash(), sim.get_steps(), sim.get_global_time()
     for r in range(2):
         assert h[r] == ref[r][1] and st[r] == ref[r][2] and _close(t[r], ref[r][3])
+
+
+def test_empty_model_list_on_device():
+    """Simulation::post(vec![], vec![]) (mod.rs:49-56): nothing is ever scheduled, each step adds +INF to the clock."""
+    from sim_b200 import Simulation
+    sim = Simulation.post([], [], replications=100)
+    sim.step()
+    sim.step_n(2)
+    assert np.isinf(sim.get_global_time()).all() and (sim.get_steps() == 3).all() and (sim.get_events() == 0).all()
+    sim.inject_input(Message("manual", "manual", "nobody", "in", 0.0, "x 1"))
+    sim.step()
+    assert (sim.get_errors() == 0).all() and len(sim.get_messages(0)) == 0

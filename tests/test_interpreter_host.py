@@ -286,3 +286,30 @@ def test_streaming_batch_means_match_the_oracle_series():
     short.step_until(60.0)  # fewer than warm-up + one batch
     sm, sq, open_sum = short.batch()
     assert (sm == 0).all() and (sq == 0).all()
+
+
+def test_models_sharing_an_id_all_receive_the_message():
+    """mod.rs:203-221: `step` filters the messages by id for EVERY model in turn, so two posted models with one id both
+    run events_ext on a message addressed to it -- over a connector and through inject_input -- while the reference
+    still holds ONE Message (one trace entry, one count on the connector)."""
+    models, conns = networks.shared_ids()
+    hs = H.HostSim(models, conns, n=2, seed=9, trace_reps=2, trace_cap=20000)
+    assert hs.inject_input("twin", "job", "manual 1") == 0
+    hs.step_n(600)
+    for r in range(2):
+        o = O.OracleSimulation(models, conns)
+        o.set_rng_philox(9, r)
+        o.trace_enable(True)
+        o.trace_intern("manual 1")
+        o.inject_input("twin", "job", "manual 1")
+        e, _ = o.step_n(600, collect=False)
+        assert e == 0 and hs.errors()[r] == 0
+        assert o.trace() == hs.trace(r) and o.trace_hash() == int(hs.hash()[r])
+        assert o.counters()["events"] == int(hs.events()[r])
+    sent = int(hs.conn_counts()[0])                      # Messages on c-in, both replications
+    rec = hs.record_counts()
+    # every job sent over c-in, plus the injected one of each replication, reached BOTH twins (Arrival or Drop; the
+    # jobs of the last step are still in the mailbox)
+    got = [int(rec[m][2] + rec[m][4]) for m in (1, 3)]
+    in_flight = sum(1 for r in range(2) for p in hs.pending(r) if p[1] == 1)
+    assert got[0] == got[1] == sent + 2 - in_flight and sent > 100

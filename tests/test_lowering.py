@@ -6,6 +6,7 @@ import pytest
 
 import hostsim_api as H
 import networks
+import oracle_api as O
 
 
 def _lower(models_json, connectors_json="[]", **kw):
@@ -39,12 +40,22 @@ def test_field_order_is_irrelevant_and_unknown_fields_are_ignored():
     ("[{\"id\": \"g\", \"type\": \"Generator\", \"portsIn\": {}, \"portsOut\": {\"job\": \"job\"}, "
      "\"messageInterdepartureTime\": {\"cauchy\": {\"median\": 1, \"scale\": 1}}}]", 13),  # unknown variant
     ("not json", 13),
-    ("[]", 1),
 ])
 def test_rejections(doc, status):
     with pytest.raises(RuntimeError) as ei:
         _lower(doc)
     assert "(%d)" % status in str(ei.value)
+
+
+def test_an_empty_model_list_is_a_simulation():
+    # Simulation::post(vec![], vec![]) is accepted (mod.rs:49-56); each step adds the +INF minimum to the clock (:225-236)
+    hs = _lower("[]", n=2)
+    assert hs.layout()["n_models"] == 0
+    hs.step_n(2)
+    assert (hs.time() == float("inf")).all() and (hs.steps() == 2).all() and (hs.events() == 0).all() and (hs.errors() == 0).all()
+    o = O.OracleSimulation([], [])
+    o.set_rng_philox(42, 0)
+    assert o.step_n(2, collect=False)[0] == 0 and o.get_global_time() == float("inf")
 
 
 def test_stat_model_must_be_a_processor():
