@@ -798,6 +798,16 @@ struct Engine {
         }
     }
 
+    // The draws owed at the flush site belong to handlers that ran BEFORE whatever has just failed (a debt of the
+    // previous step's events_int, of an earlier events_ext of this step): the reference made them, so they are paid in
+    // full -- with the error set aside, because the samplers' rejection loops stop early on a failed replication.
+    SIMB_HD void flush_owed(Lane& ln) {
+        const uint32_t e = ln.err;
+        ln.err = 0;
+        flush_draws(ln);
+        if (e) ln.err = e;
+    }
+
     // ---- instrumentation ---------------------------------------------------------------------------
     template <bool INSTR>
     SIMB_HD void record(Lane& ln, uint32_t m, uint32_t action, uint32_t content, uint32_t aux = 0) {
@@ -1900,7 +1910,7 @@ struct Engine {
         if (ext_done || pg.flush) {  // (pg.flush without act: the settle pass at the end of a launch)
             pg.flush = false;
             if (RNG == 0 && ln.ccount <= 1u) philox_refill(ln);
-            flush_draws(ln);
+            flush_owed(ln);
         }
         if (ext_done) {
             pg.stage = 2u;
@@ -2081,7 +2091,11 @@ struct Engine {
         }
         // ---- pay the deferred draws (and top up the Philox prefetch) at this converged point ----
         if (RNG == 0) philox_topup(ln, live);
-        if (live) flush_draws(ln);
+        if (live) {
+            if (STATIC) flush_draws(ln);  // (baked shapes: the one loop that looks at the error is the ziggurat's rare
+                                          // rejection branch; not worth three instructions per step of the fused kernel)
+            else flush_owed(ln);
+        }
         // A failed events_ext aborts the step (`?` at :222); the replication freezes.
         const bool go = live && !ln.err;
         // ---- time advance (:225-236) ----
