@@ -130,6 +130,8 @@ struct Lane {
     uint32_t dm_int, dm_ext;  // deferred continuous draws: "until_next_event[m] = sample(dist[m])" still
                               // owed from the previous internal phase / this external phase
     uint32_t traced;
+    bool hold;       // the messages being sent come from a component of a Coupled model: they enter the trace when the
+                     // whole model has fired (Engine::close_group), as the reference routes them then (mod.rs:241-263)
     double u[4];     // baked shapes of <= 4 models: until_next_event of model m, in registers for the whole launch
     uint64_t kseed;  // RARE builds: Philox key while a model draws from its OWN stream (`own`), see own_begin
     bool own;
@@ -951,6 +953,7 @@ struct Engine {
         ln.c0 = ln.c1 = ln.c2 = 0;
         ln.ccount = 0;
         ln.traced = instr && ln.rep < st.trace_reps;
+        ln.hold = false;
         ln.rb = 0;
         ln.kseed = 0;
         ln.own = false;
@@ -1440,6 +1443,8 @@ struct Engine {
         // Coupled models (RARE builds): coupled models that have opened (delivered their parked messages) in this
         // step, the one delivering now (+1), and the scan position in its parked list (component << 16 | index)
         uint32_t copen, cdel, cpos;
+        // ... and the one whose components are firing (+1) with the mailbox fill when the first of them began
+        uint32_t cgrp, cseq0;
     };
 #define REL_RING 0x10000u
 #define REL_PORTS 0x20000u
@@ -1451,6 +1456,7 @@ struct Engine {
         pg.flush = false;
         pg.rel = pg.rel_mp = pg.rel_one = 0;
         pg.copen = pg.cdel = pg.cpos = 0;
+        pg.cgrp = pg.cseq0 = 0;
     }
     // ---- Coupled models (sim/src/models/coupled.rs; RARE builds only) ---------------------------------------------
     // order key of a mailbox slot: events_ext runs over the TOP-LEVEL models in order, so the components of a Coupled
@@ -1639,6 +1645,11 @@ struct Engine {
             ln.err = (a & 3u) == 1u ? 7u : 5u;  // InvalidMessage / InvalidModelState
             return true;
         }
+        // Owed draws are paid lowest model first, which is the order events_ext ran in -- except inside a Coupled
+        // model, whose external input couplings may reach a later component before an earlier one (coupled.rs:166-184):
+        // a component that comes after one still owing pays that debt first, so the stream is consumed in the
+        // reference's order.
+        if (RARE && net.n_coupled != 0u && (ln.dm_ext >> m) > 1u) return false;
         if (!BASIC && ((a >> XA_SPECIAL_SHIFT) & 3u)) {
             const uint32_t sp = (a >> XA_SPECIAL_SHIFT) & 3u;
             if (sp == XS_SGATE && (ln.dm_int | ln.dm_ext)) return false;
@@ -1698,29 +1709,51 @@ struct Engine {
             mail_word(ln, j, 0) = content;
             mail_word(ln, j, 1) = rw;
             ln.npend++;
-            if (INSTR && !(RARE && (tw & RTW_CONT))) {  // one Message of the reference = one trace entry
-                const uint32_t conn = SIMB_LDG(st.tab + SIMB_TAB_CONN + r);
-                ln.hash = (ln.hash ^ TRACE_MESSAGE_WORD(conn, content)) * TRACE_HASH_PRIME;
-#if SIMB_ON_DEVICE
-                atomicAdd(&st.conn_count[conn], 1ull);
-#else
-                st.conn_count[conn] += 1ull;
-#endif
-                if (ln.traced) {
-                    uint32_t k = st.trace_count[ln.rep];
-                    if (k < st.trace_cap) {
-                        SimbTraceRec t;
-                        t.step = ln.steps + 1u;
-                        t.meta = conn;
-                        t.content = content;
-                        t.aux = 0;
-                        t.time = ln.time;
-                        st.trace[(uint64_t)ln.rep * st.trace_cap + k] = t;
-                    }
-                    st.trace_count[ln.rep] = k + 1u;
-                }
-            }
+            // one Message of the reference = one trace entry
+            if (INSTR && !(RARE && (tw & RTW_CONT)) && !(RARE && ln.hold)) trace_message(ln, r, content);
         }
+    }
+    // the trace entry / hash contribution / connector count of one Message sent over route r
+    SIMB_HD void trace_message(Lane& ln, uint32_t r, uint32_t content) {
+        const uint32_t conn = SIMB_LDG(st.tab + SIMB_TAB_CONN + r);
+        ln.hash = (ln.hash ^ TRACE_MESSAGE_WORD(conn, content)) * TRACE_HASH_PRIME;
+#if SIMB_ON_DEVICE
+        atomicAdd(&st.conn_count[conn], 1ull);
+#else
+        st.conn_count[conn] += 1ull;
+#endif
+        if (ln.traced) {
+            uint32_t k = st.trace_count[ln.rep];
+            if (k < st.trace_cap) {
+                SimbTraceRec t;
+                t.step = ln.steps + 1u;
+                t.meta = conn;
+                t.content = content;
+                t.aux = 0;
+                t.time = ln.time;
+                st.trace[(uint64_t)ln.rep * st.trace_cap + k] = t;
+            }
+            st.trace_count[ln.rep] = k + 1u;
+        }
+    }
+    // A Coupled model has fired -- every imminent component has run events_int (coupled.rs:234-255) -- and only now
+    // does the reference's step() see the messages it returned and route them (mod.rs:241-263): the trace entries of
+    // what its components sent since `cseq0`, in sending order.  A failed component (`?` inside the Coupled model)
+    // loses them all.
+    template <bool INSTR>
+    SIMB_HD void close_group(Lane& ln, Prog& pg) {
+        if (INSTR && !ln.err) {
+            for (uint32_t q = pg.cseq0; q < ln.npend; q++)
+                for (uint32_t j = 0; j < ln.npend; j++) {
+                    const uint32_t rw = mail_word(ln, j, 1);
+                    if (ROUTE_SEQ(rw) != q) continue;
+                    const uint32_t r = ROUTE_R(rw);
+                    if (!(tab.mt[SIMB_TAB_ROUTES + r] & RTW_CONT)) trace_message(ln, r, mail_word(ln, j, 0));
+                    break;
+                }
+        }
+        pg.cgrp = 0;
+        ln.hold = false;
     }
 
     // events_int of model m (any type).  false: nothing was done because the handler draws inline
@@ -1956,6 +1989,9 @@ struct Engine {
         // ---- a Coupled model whose turn has come (coupled.rs:186-255): before any of its components fires, its
         // parked messages are delivered -- component order, then parked order --, the draws they owe are paid, and
         // the components that are imminent NOW are the ones that fire ----
+        if (RARE && INSTR && net.n_coupled != 0u && act && pg.cgrp != 0u && pg.stage == 2u && pg.rel == 0u && !pg.flush &&
+            !ln.err && (pg.zmk == 0u || (TF(TF_GROUP, (uint32_t)lowest_bit(pg.zmk)) >> 8) != pg.cgrp - 1u))
+            close_group<INSTR>(ln, pg);
         if (RARE && net.n_coupled != 0u && act && !ln.err && pg.rel == 0u && !pg.flush) {
             if (pg.stage == 2u && pg.zmk) {
                 const uint32_t cpl = TF(TF_GROUP, (uint32_t)lowest_bit(pg.zmk)) >> 8;
@@ -2009,6 +2045,11 @@ struct Engine {
             !(RARE && net.n_coupled != 0u && (TF(TF_GROUP, (uint32_t)lowest_bit(pg.zmk)) >> 8) < SIMB_MAX_COUPLED &&
               !(pg.copen & (1u << (TF(TF_GROUP, (uint32_t)lowest_bit(pg.zmk)) >> 8))))) {
             const uint32_t m = (uint32_t)lowest_bit(pg.zmk);
+            if (RARE && INSTR && net.n_coupled != 0u && pg.cgrp == 0u && (TF(TF_GROUP, m) >> 8) < SIMB_MAX_COUPLED) {
+                pg.cgrp = (TF(TF_GROUP, m) >> 8) + 1u;  // the first component of a Coupled model to fire in this step
+                pg.cseq0 = ln.npend;
+                ln.hold = true;
+            }
             if (int2<INSTR>(ln, pg, m)) {
                 pg.zmk &= pg.zmk - 1u;
                 pg.nev++;
@@ -2020,6 +2061,11 @@ struct Engine {
         if (act && pg.rel != 0u && !ln.err) release_one<INSTR>(ln, pg);
         // ---- step end ----
         if (act && ((pg.stage == 2u && pg.zmk == 0u && pg.rel == 0u) || (pg.stage >= 2u && ln.err))) {
+            if (RARE && INSTR && pg.cgrp != 0u) close_group<INSTR>(ln, pg);
+            if (ln.err && (ln.dm_int | ln.dm_ext)) {  // what ran before the failure has drawn (flush_owed)
+                if (RNG == 0 && ln.ccount <= 1u) philox_refill(ln);
+                flush_owed(ln);
+            }
             pg.stage = 0u;
             pg.rel = 0;
             pg.cdel = 0;
