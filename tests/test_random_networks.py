@@ -99,6 +99,41 @@ def test_engine_matches_oracle_on_random_coupled_networks(block):
     assert compared >= 20
 
 
+def test_random_networks_with_shared_ids_and_step_until():
+    """Some models take the id of an earlier one (every model of an id receives the message, mod.rs:203-221), and the
+    run is `step_until` on acyclic networks (a zero-time cycle never reaches `until`, in the reference as here)."""
+    import random
+    compared = 0
+    for seed in range(11000, 11150):
+        rnd = random.Random(seed + 99)
+        models, conns = random_network(seed, acyclic=True)
+        for m in models:              # (oracle_api binds a model's own generator by id)
+            if hasattr(m.inner, "rng"):
+                m.inner.rng = None
+        for i in range(1, len(models)):
+            if rnd.random() < 0.25:
+                models[i].id = models[rnd.randrange(i)].id
+        until = rnd.choice([0.0, 0.5, 3.0, 17.0, 60.0])
+        hs = H.HostSim(models, conns, n=2, seed=seed)
+        hs.set_reload_every(1 + seed % 7)
+        hs.step_until(until)
+        stopwatch = _holds_stopwatch(models)
+        for r in range(2):
+            he = int(hs.errors()[r])
+            if he == 32:
+                continue
+            e, o = _oracle(models, conns, seed, r, until=until)
+            c = o.counters()
+            if stopwatch and o.trace_hash() != int(hs.hash()[r]):
+                continue
+            what = "seed %d replication %d until %g" % (seed, r, until)
+            assert e == he, what
+            assert (c["steps"], c["events"], o.rng_draws()) == (int(hs.steps()[r]), int(hs.events()[r]), int(hs.draws()[r])), what
+            assert _same_time(o.get_global_time(), float(hs.time()[r])) and o.trace_hash() == int(hs.hash()[r]), what
+            compared += 1
+    assert compared >= 100
+
+
 def test_regressions_found_by_the_random_networks():
     """Seeds that once disagreed: 57 (the messages of a Coupled model's components were traced before its later
     components' records), 2548 (two components reached in coupling order drew in index order), 75191 (a component
