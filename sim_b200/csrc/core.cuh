@@ -317,6 +317,9 @@ struct Engine {
         }
         ln.ccount += odd ? 1u : 2u;
     }
+    // the external stream (rng_kind 2) has run dry: the samplers' rejection loops stop instead of spinning on zeros.
+    // (Not "the replication has failed": draws owed by handlers that ran before a failure are still made in full.)
+    SIMB_HD bool dry(const Lane& ln) const { return RNG == 2 && ln.draw_idx > st.ext_len; }
     SIMB_HD void philox_refill(Lane& ln) {
         const uint32_t nxt = ln.draw_idx + ln.ccount;
         uint64_t a, b;
@@ -426,12 +429,12 @@ struct Engine {
                 const double chord = f0 + (f1 - f0) * ((xi - x) / (xi - xj));
                 if (y < tangent * (1.0 - 1e-9)) return x;
                 if (y > chord * (1.0 + 1e-9)) {
-                    if (ln.err) return x;
+                    if (dry(ln)) return x;
                     continue;
                 }
             }
             if (y < exp(-x)) return x;
-            if (ln.err) return x;  // external stream ran dry: do not spin
+            if (dry(ln)) return x;  // external stream ran dry: do not spin
         }
     }
     // rand_distr 0.4 StandardNormal (symmetric ziggurat + Marsaglia tail)
@@ -450,13 +453,13 @@ struct Engine {
                     double y_ = open01(ln);
                     tx = log(x_) / R;
                     ty = log(y_);
-                    if (ln.err) break;
+                    if (dry(ln)) break;
                 }
                 return (u < 0.0) ? tx - R : R - tx;
             }
             double f1 = tab.norm_f[i + 1], f0 = tab.norm_f[i];
             if (f1 + (f0 - f1) * standard_f64(ln) < exp(-x * x / 2.0)) return x;
-            if (ln.err) return x;
+            if (dry(ln)) return x;
         }
     }
     template <class P>
@@ -471,7 +474,7 @@ struct Engine {
                     const double x = sample_standard_normal(ln);
                     const double v_cbrt = 1.0 + cc * x;
                     if (v_cbrt <= 0.0) {
-                        if (ln.err) break;
+                        if (dry(ln)) break;
                         continue;
                     }
                     const double v = v_cbrt * v_cbrt * v_cbrt;
@@ -481,7 +484,7 @@ struct Engine {
                         g = d * v * scale;
                         break;
                     }
-                    if (ln.err) break;
+                    if (dry(ln)) break;
                 }
                 return pd.q0() ? g * pow(u_small, bits_f64(pd.q1())) : g;
             }
@@ -513,7 +516,7 @@ struct Engine {
                         const double t = log(z);
                         if (s_ >= t) break;
                         if (!(r + alpha * log(alpha / (bb + w)) < t)) break;
-                        if (ln.err) break;
+                        if (dry(ln)) break;
                     }
                 } else {  // BC
                     const double beta = 1.0 / bb;
@@ -524,7 +527,7 @@ struct Engine {
                         double z;
                         const double u1 = open01(ln);
                         const double u2 = open01(ln);
-                        if (ln.err) break;
+                        if (dry(ln)) break;
                         if (u1 < 0.5) {
                             const double y = u1 * u2;
                             z = u1 * y;
@@ -621,7 +624,7 @@ struct Engine {
                 uint64_t failures = 0;
                 for (;;) {
                     const double u = standard_f64(ln);
-                    if (u <= p || ln.err) break;
+                    if (u <= p || dry(ln)) break;
                     failures++;
                 }
                 return failures;
@@ -629,13 +632,13 @@ struct Engine {
             if (p == 0.0) return 0xFFFFFFFFFFFFFFFFull;
             const uint64_t k = pd.q0();
             uint64_t d = 0;  // D ~ Geo(pi) = Geo(p) / 2^k
-            while (standard_f64(ln) < pi && !ln.err) d++;
+            while (standard_f64(ln) < pi && !dry(ln)) d++;
             uint64_t m;  // M ~ Geo(p) % 2^k by rejection
             for (;;) {
                 m = next_u64(ln) & ((1ull << k) - 1ull);
                 const double p_reject = m <= 0x7FFFFFFFull ? powi_f64(1.0 - p, (int)m) : pow(1.0 - p, (double)m);
                 const double u = standard_f64(ln);
-                if (u < p_reject || ln.err) break;
+                if (u < p_reject || dry(ln)) break;
             }
             return (d << k) + m;
         }
@@ -646,7 +649,7 @@ struct Engine {
                 const double exp_lambda = pd.p1();
                 double prod = 1.0;
                 result = 0.0;
-                while (prod > exp_lambda && !ln.err) {
+                while (prod > exp_lambda && !dry(ln)) {
                     prod = prod * standard_f64(ln);
                     result = result + 1.0;
                 }
@@ -658,12 +661,12 @@ struct Engine {
                     for (;;) {
                         comp_dev = tan(3.14159265358979323846 * standard_f64(ln));
                         result = sqrt_2lambda * comp_dev + lambda;
-                        if (result >= 0.0 || ln.err) break;
+                        if (result >= 0.0 || dry(ln)) break;
                     }
                     result = floor(result);
                     const double check = 0.9 * (1.0 + comp_dev * comp_dev) *
                                          exp(result * log_lambda - log_gamma(1.0 + result) - magic_val);
-                    if (standard_f64(ln) <= check || ln.err) break;
+                    if (standard_f64(ln) <= check || dry(ln)) break;
                 }
             }
             return result >= 18446744073709551615.0 ? 0xFFFFFFFFFFFFFFFFull : result > 0.0 ? (uint64_t)result : 0ull;
@@ -676,7 +679,7 @@ struct Engine {
             uint64_t v = next_u64(ln);
             uint64_t hi = mulhi64(v, range), lo = v * range;
             if (lo <= zone) return low + hi;
-            if (ln.err) return low;
+            if (dry(ln)) return low;
         }
     }
     // Index::random_variate (random_variable.rs:122-130)
@@ -798,16 +801,6 @@ struct Engine {
             if (dv == 0.0) ln.zm |= 1u << m;  // a variate of exactly zero makes the model imminent at once
             else ln.nmin = fmin(ln.nmin, dv);
         }
-    }
-
-    // The draws owed at the flush site belong to handlers that ran BEFORE whatever has just failed (a debt of the
-    // previous step's events_int, of an earlier events_ext of this step): the reference made them, so they are paid in
-    // full -- with the error set aside, because the samplers' rejection loops stop early on a failed replication.
-    SIMB_HD void flush_owed(Lane& ln) {
-        const uint32_t e = ln.err;
-        ln.err = 0;
-        flush_draws(ln);
-        if (e) ln.err = e;
     }
 
     // ---- instrumentation ---------------------------------------------------------------------------
@@ -1943,7 +1936,7 @@ struct Engine {
         if (ext_done || pg.flush) {  // (pg.flush without act: the settle pass at the end of a launch)
             pg.flush = false;
             if (RNG == 0 && ln.ccount <= 1u) philox_refill(ln);
-            flush_owed(ln);
+            flush_draws(ln);
         }
         if (ext_done) {
             pg.stage = 2u;
@@ -2061,11 +2054,9 @@ struct Engine {
         if (act && pg.rel != 0u && !ln.err) release_one<INSTR>(ln, pg);
         // ---- step end ----
         if (act && ((pg.stage == 2u && pg.zmk == 0u && pg.rel == 0u) || (pg.stage >= 2u && ln.err))) {
+            // (a failed step may leave draws owed by the handlers that ran before the failure: the reference made
+            // them, and the launch pays them before it stores the lane -- step_kernel.cuh, "settle")
             if (RARE && INSTR && pg.cgrp != 0u) close_group<INSTR>(ln, pg);
-            if (ln.err && (ln.dm_int | ln.dm_ext)) {  // what ran before the failure has drawn (flush_owed)
-                if (RNG == 0 && ln.ccount <= 1u) philox_refill(ln);
-                flush_owed(ln);
-            }
             pg.stage = 0u;
             pg.rel = 0;
             pg.cdel = 0;
@@ -2137,11 +2128,7 @@ struct Engine {
         }
         // ---- pay the deferred draws (and top up the Philox prefetch) at this converged point ----
         if (RNG == 0) philox_topup(ln, live);
-        if (live) {
-            if (STATIC) flush_draws(ln);  // (baked shapes: the one loop that looks at the error is the ziggurat's rare
-                                          // rejection branch; not worth three instructions per step of the fused kernel)
-            else flush_owed(ln);
-        }
+        if (live) flush_draws(ln);
         // A failed events_ext aborts the step (`?` at :222); the replication freezes.
         const bool go = live && !ln.err;
         // ---- time advance (:225-236) ----

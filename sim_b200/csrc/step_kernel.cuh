@@ -279,7 +279,9 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
         }
         // last launch of an API call: pay the deferred draws so the stored state is observable as is -- through the
         // loop's own flush site (one more pass of micro with no lane active)
-        pg.flush = la.settle && !absent && (ln.dm_int | ln.dm_ext) != 0u;
+        // -- and, in any launch, what a replication that has just failed still owes: the handlers that ran before the
+        // failure drew in the reference, and dm_ext does not survive the store
+        pg.flush = (la.settle || ln.err != 0u) && !absent && (ln.dm_int | ln.dm_ext) != 0u;
         if (__ballot_sync(0xFFFFFFFFu, pg.flush) != 0u) {
             stepped = true;
             eng.template micro<INSTR>(ln, pg, false);
@@ -294,7 +296,7 @@ simb_step_kernel(const __grid_constant__ SimbNetDesc net_param, const __grid_con
         }
     }
     // last launch of an API call: pay the deferred draws so the stored state is observable as is
-    if (SHAPE >= 0 && la.settle && !absent && (ln.dm_int | ln.dm_ext)) {
+    if (SHAPE >= 0 && (la.settle || ln.err != 0u) && !absent && (ln.dm_int | ln.dm_ext)) {
         eng.flush_draws(ln);
         stepped = true;
     }

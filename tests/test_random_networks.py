@@ -134,6 +134,42 @@ def test_random_networks_with_shared_ids_and_step_until():
     assert compared >= 100
 
 
+def test_waiting_time_statistic_on_random_networks():
+    """The per-replication waiting-time accumulator (simb_config.stat_model_id) against the oracle's records of that
+    processor: Processing Start - Arrival, paired in queue order (the k-th start belongs to the k-th arrival that was
+    not dropped -- the pairing by job name of tests/web.rs:588-597 is the same thing while names are unique)."""
+    compared = 0
+    for seed in range(12000, 12200):
+        models, conns = random_network(seed, acyclic=(seed % 2 == 0))
+        procs = [m for m in models if m.inner.type_name == "Processor"]
+        if not procs:
+            continue
+        pid = procs[seed % len(procs)].id
+        for m in models:
+            m.inner.store_records = True
+        hs = H.HostSim(models, conns, n=2, seed=seed, stat_model_id=pid)
+        hs.set_reload_every(1 + seed % 7)
+        hs.step_n(STEPS)
+        total, count = hs.wait()
+        stopwatch = _holds_stopwatch(models)
+        for r in range(2):
+            if int(hs.errors()[r]) == 32:
+                continue
+            e, o = _oracle(models, conns, seed, r)
+            if stopwatch and o.trace_hash() != int(hs.hash()[r]):
+                continue
+            arrivals, ws, wn = [], 0.0, 0
+            for t, action, subject in o.get_records(pid)[1]:
+                if action == "Arrival":
+                    arrivals.append(t)
+                elif action == "Processing Start":
+                    ws += t - arrivals.pop(0)
+                    wn += 1
+            assert wn == count[r] and abs(ws - total[r]) <= 1e-9 * max(1.0, abs(ws)), (seed, r, pid)
+            compared += 1
+    assert compared >= 100
+
+
 def test_regressions_found_by_the_random_networks():
     """Seeds that once disagreed: 57 (the messages of a Coupled model's components were traced before its later
     components' records), 2548 (two components reached in coupling order drew in index order), 75191 (a component
