@@ -4,7 +4,7 @@
 //
 // Reader: the block-style subset that serde_yaml 0.8 emits and that the reference's fixtures use
 // (sim/tests/web.rs:322-407): block mappings and sequences by indentation, `- key: value` compact entries, plain /
-// single- / double-quoted scalars, the flow forms `{}`, `[]` and one-line `[a, b]` / `{a: b}`, `~` / null, booleans,
+// single- / double-quoted scalars, flow collections `[a, b]` / `{a: b}` (nested, over several lines too), `~` / null, booleans,
 // integers, floats, `.inf` / `-.inf` / `.nan`, `#` comments, a leading `---`.  Anchors, tags, block scalars and
 // multi-document streams are not part of that wire format and are rejected.
 // Writer: the layout of serde_yaml 0.8 (`---` header, two-space indentation, sequences indented under their key,
@@ -135,9 +135,62 @@ struct Reader {
             std::string body = s.substr(ind);
             if (body == "---" && lines.empty()) continue;
             if (body == "---" || body == "...") return fail("multi-document streams are not supported", number);
+            if (open_depth > 0) {  // continuation of a flow collection that did not close on the line it opened
+                lines.back().text += ' ';
+                lines.back().text += body;
+                open_depth += flow_depth(body, 0);
+                continue;
+            }
             lines.push_back(Line{(int)ind, body, number});
+            const size_t v = value_start(body);
+            if (v < body.size() && (body[v] == '[' || body[v] == '{')) open_depth = flow_depth(body, v);
         }
+        if (open_depth > 0) return fail("unterminated flow collection", number);
         return true;
+    }
+    int open_depth = 0;
+    // where the value of a line begins: after any "- " entries and a "key: " prefix
+    static size_t value_start(const std::string& b) {
+        size_t i = 0;
+        while (i + 1 < b.size() && b[i] == '-' && b[i + 1] == ' ') {
+            i += 2;
+            while (i < b.size() && b[i] == ' ') i++;
+        }
+        if (i < b.size() && (b[i] == '[' || b[i] == '{')) return i;
+        char q = 0;
+        for (size_t k = i; k < b.size(); k++) {
+            const char c = b[k];
+            if (q) {
+                if (c == '\\' && q == '"') k++;
+                else if (c == q) q = 0;
+            } else if ((c == '"' || c == '\'') && k == i) {
+                q = c;
+            } else if (c == ':' && k + 1 < b.size() && b[k + 1] == ' ') {
+                k += 2;
+                while (k < b.size() && b[k] == ' ') k++;
+                return k;
+            }
+        }
+        return b.size();
+    }
+    // brackets opened minus brackets closed from position `from`, outside quotes
+    static int flow_depth(const std::string& b, size_t from) {
+        int d = 0;
+        char q = 0;
+        for (size_t k = from; k < b.size(); k++) {
+            const char c = b[k];
+            if (q) {
+                if (c == '\\' && q == '"') k++;
+                else if (c == q) q = 0;
+            } else if (c == '"' || c == '\'') {
+                q = c;
+            } else if (c == '[' || c == '{') {
+                d++;
+            } else if (c == ']' || c == '}') {
+                d--;
+            }
+        }
+        return d;
     }
 
     // ---- scalars and one-line flow collections ----
@@ -219,7 +272,7 @@ struct Reader {
     }
     bool flow(const std::string& s, Value* out, int line) {
         const char open = s[0], close = open == '[' ? ']' : '}';
-        if (s.back() != close) return fail("flow collections must close on the line they open", line);
+        if (s.back() != close) return fail("text after the end of a flow collection", line);
         const std::vector<std::string> items = flow_items(s.substr(1, s.size() - 2));
         if (open == '[') {
             out->kind = Value::Array;

@@ -84,6 +84,23 @@ def test_yaml_writer_reader_round_trip_against_pyyaml():
         "---\nmodels:\n  - id: a\n    state:\n      job: ~\n      jobs: []\n"
 
 
+def test_yaml_documents_of_random_networks():
+    """Model and connector documents of seeded random networks (Coupled ones included) through the writer and the
+    reader, and through PyYAML in both directions -- its block style and its flow style, which wraps long collections
+    over several lines."""
+    import yaml
+    from random_networks import random_coupled_network, random_network
+    from sim_b200.simulator import _json_to_yaml, _yaml_to_json, connectors_to_json, models_to_json
+    for seed in range(14000, 14060):
+        models, conns = random_network(seed) if seed % 2 else random_coupled_network(seed)
+        for text in (models_to_json(models), connectors_to_json(conns)):
+            doc = json.loads(text)
+            y = _json_to_yaml(text)
+            assert json.loads(_yaml_to_json(y)) == doc and yaml.safe_load(y) == doc, seed
+            for flow in (False, True):
+                assert json.loads(_yaml_to_json(yaml.safe_dump(doc, default_flow_style=flow, sort_keys=False))) == doc, (seed, flow)
+
+
 def test_yaml_errors_are_reported():
     from sim_b200 import SimulationError
     from sim_b200.simulator import _yaml_to_json
