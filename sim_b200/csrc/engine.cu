@@ -289,7 +289,11 @@ simb_sample_kernel(const __grid_constant__ SimbNetDesc net, const __grid_constan
         if (family == FAM_CONTINUOUS) out_d[i * st.n + r] = eng.sample_continuous_kind(ln, md.dist_kind, pd);
         else if (family == FAM_BOOLEAN) out_u[i * st.n + r] = eng.sample_bernoulli_p(ln, md.flags, pd) ? 1ull : 0ull;
         else if (family == FAM_DISCRETE) out_u[i * st.n + r] = eng.sample_discrete_kind(ln, md.dist_kind, pd);
-        else out_u[i * st.n + r] = eng.sample_index_p(ln, md.flags, md.n_w, md.wtab, pd);
+        else if (md.flags & MF_INDEX_WEIGHTED) out_u[i * st.n + r] = eng.sample_index_p(ln, md.flags, md.n_w, md.wtab, pd);
+        else if (pd.dist_err()) ln.err = ln.err ? ln.err : pd.dist_err();
+        else out_u[i * st.n + r] = eng.sample_uniform_int(ln, pd.q0(), pd.q1(), pd.q2());  // Index::Uniform is a usize:
+                                                                                          // all 64 bits (the models clamp
+                                                                                          // it to a port count)
     }
     if (draws) draws[r] = ln.draw_idx;
     if (ln.err) atomicCAS(status, 0, (int32_t)ln.err);

@@ -153,3 +153,49 @@ def test_a_model_with_its_own_rng_is_independent_of_the_other_draws():
     a, b = shared(1.5), shared(4.0)
     n = min(len(a), len(b))
     assert not np.allclose(a[:n], b[:n], rtol=1e-6, atol=0.0)
+
+
+@pytest.mark.gpu
+def test_device_variates_equal_the_oracle_for_random_parameters():
+    """Seeded random parameters of every family -- small and large shapes, both Geometric and both Poisson algorithms,
+    wide integer ranges, lop-sided weights, and parameters the reference rejects at draw time: the device's variates
+    and draw counts equal the oracle's on the same stream, and a rejected parameter raises the same error."""
+    import random
+    from sim_b200 import SimulationError
+    from sim_b200.input_modeling import sample
+    T, D, I = ContinuousRandomVariable, DiscreteRandomVariable, IndexRandomVariable
+    rnd = random.Random(2024)
+    def logu(lo, hi):
+        return float(np.exp(rnd.uniform(np.log(lo), np.log(hi))))
+    makers = [
+        lambda: ("continuous", T.Exp(logu(1e-3, 1e3) if rnd.random() < 0.9 else -1.0)),
+        lambda: ("continuous", T.Normal(rnd.uniform(-50, 50), logu(1e-3, 10) if rnd.random() < 0.9 else -1.0)),
+        lambda: ("continuous", T.Uniform(rnd.uniform(-5, 5), rnd.uniform(5.1, 50))),
+        lambda: ("continuous", (lambda a, b: T.Triangular(a, b, rnd.uniform(a, b)))(rnd.uniform(-3, 3), rnd.uniform(3.5, 9))),
+        lambda: ("continuous", T.Gamma(logu(0.05, 40), logu(0.01, 20))),
+        lambda: ("continuous", T.LogNormal(rnd.uniform(-2, 2), logu(0.01, 1.5))),
+        lambda: ("continuous", T.Weibull(logu(0.2, 8), logu(0.1, 10))),
+        lambda: ("continuous", T.Beta(logu(0.05, 30), logu(0.05, 30))),
+        lambda: ("boolean", BooleanRandomVariable.Bernoulli(rnd.choice([0.0, 1.0, rnd.random(), 1.5]))),
+        lambda: ("discrete", D.Geometric(rnd.choice([logu(1e-4, 0.66), rnd.uniform(0.67, 1.0), 1.0, 0.0, -0.1]))),
+        lambda: ("discrete", D.Poisson(rnd.choice([logu(0.01, 11.9), logu(12.0, 5000.0), 0.0]))),
+        lambda: ("discrete", (lambda a: D.Uniform(a, a + rnd.choice([0, 1, 2, 1000, 2**40])))(rnd.randrange(0, 10**6))),
+        lambda: ("index", (lambda a: I.Uniform(a, a + rnd.choice([1, 3, 2**33])))(rnd.randrange(0, 1000))),
+        lambda: ("index", I.WeightedIndex([rnd.choice([0, 1, 1, 7, 10**6]) for _ in range(rnd.randint(1, 12))])),
+    ]
+    for case in range(140):
+        family, var = makers[case % len(makers)]()
+        reps, count, seed = 5, 300, 1000 + case
+        e, want, used = _oracle(family, var, count, seed, 3)
+        what = "%s %s %s" % (family, var.variant, var.params)
+        if e:
+            with pytest.raises(SimulationError) as ei:
+                sample(family, var, reps, count, seed=seed)
+            assert ei.value.status == e, what
+            continue
+        got, draws = sample(family, var, reps, count, seed=seed, with_draws=True)
+        assert used == draws[3], what
+        if family == "continuous":
+            assert np.allclose(got[:, 3], want, rtol=1e-11, atol=0.0, equal_nan=True), what
+        else:
+            assert np.array_equal(got[:, 3], want.astype(np.uint64)), what
