@@ -1989,10 +1989,21 @@ struct Engine {
             if (pg.stage == 2u && pg.zmk) {
                 const uint32_t cpl = TF(TF_GROUP, (uint32_t)lowest_bit(pg.zmk)) >> 8;
                 if (cpl < SIMB_MAX_COUPLED && !(pg.copen & (1u << cpl))) {
-                    pg.copen |= 1u << cpl;
-                    pg.cdel = cpl + 1u;
-                    pg.cpos = (uint32_t)net.coupled[cpl].first << 16;
-                    pg.stage = 3u;
+                    // the Coupled model fires when ITS until_next_event is 0.0, and that is the minimum over its
+                    // components (coupled.rs:277-283): one component below zero (a negative variate was drawn) keeps
+                    // the whole model from firing in this step
+                    const SimbCoupledDesc& cd = net.coupled[cpl];
+                    bool below = false;
+                    for (uint32_t c = cd.first; c < (uint32_t)cd.first + cd.count; c++)
+                        if (ln.D(net.drow_until + c) < 0.0) below = true;
+                    if (below) {
+                        pg.zmk &= ~((cd.count >= 32u ? 0xFFFFFFFFu : ((1u << cd.count) - 1u)) << cd.first);
+                    } else {
+                        pg.copen |= 1u << cpl;
+                        pg.cdel = cpl + 1u;
+                        pg.cpos = (uint32_t)cd.first << 16;
+                        pg.stage = 3u;
+                    }
                 }
             }
             if (pg.stage == 3u) {
