@@ -231,7 +231,7 @@ def test_regressions_found_by_the_random_networks():
 def test_device_matches_oracle_on_random_coupled_networks():
     from sim_b200 import Simulation
     compared = 0
-    for seed in list(range(9000, 9030)) + [57, 2548, 75191, 33118]:
+    for seed in list(range(9000, 9120)) + [57, 2548, 75191, 33118, 8124]:
         models, conns = random_coupled_network(seed)
         sim = Simulation.post(models, conns, replications=64, seed=seed, instrument=True, steps_per_launch=1 + seed % 5)
         try:
@@ -262,7 +262,7 @@ def test_device_matches_oracle_on_random_coupled_networks():
 def test_device_matches_oracle_on_random_networks(acyclic):
     from sim_b200 import Message, Simulation
     compared = 0
-    for seed in range(7000, 7030):
+    for seed in range(7000, 7120):
         models, conns = random_network(seed, acyclic=acyclic)
         inject = random_injections(seed, models)
         room = H.HostSim(models, conns, n=1).layout()["max_pending"] + len(inject)   # the derived bound, plus ours
