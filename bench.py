@@ -339,23 +339,34 @@ def main():
     # ---- end to end through the public API with host buffers: post (JSON in), run, waits read back to the host ----
     e2e = None
     if not args.no_e2e:
-        barrier()
-        e_ev = 0
-        h2d = len(mj) + len(cj) + 8 * desc["f64_rows"] + 4 * desc["u32_rows"]
-        d2h = n * 12
-        t1 = time.perf_counter()
-        for _ in range(max(1, min(args.steps, 2))):
+        # (the clock sampler belongs to the timed region above: an nvidia-smi query takes a driver lock that device
+        # allocations wait for, and this region allocates)
+        clocks = sampler.stop() if rank == 0 else None
+        sampler = None
+
+        def one_call():
             s2 = Simulation.post_json(mj, cj, n, seed=4242, replication_offset=rank * n, device=local_rank,
                                       steps_per_launch=args.k, stat_model_id=stat)
             s2.step_until(args.until)
             if stat:
                 s2.get_wait_stats()
-            e_ev += s2.get_counters()["events"]
+            ev = s2.get_counters()["events"]
             s2.close()
+            return ev
+
+        one_call()  # warm-up: the device memory pool grows to hold this handle next to the resident one
+        barrier()
+        e_ev = 0
+        h2d = len(mj) + len(cj) + 8 * desc["f64_rows"] + 4 * desc["u32_rows"]
+        d2h = n * 12
+        t1 = time.perf_counter()
+        for _ in range(max(1, min(args.steps, 3))):
+            e_ev += one_call()
         barrier()
         e_dt = reduce_max(time.perf_counter() - t1)
         e2e = {"value": reduce_sum([e_ev])[0] / e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
-    clocks = sampler.stop() if rank == 0 else None
+    if sampler is not None:
+        clocks = sampler.stop() if rank == 0 else None
     sim.close()
 
     # ---- the same workload with ONE step per launch (API-faithful Simulation::step granularity): every launch
