@@ -199,11 +199,20 @@ def run_reference(args):
                           "each step is a bounded sample of the job: " + sample,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }), file=OUT, flush=True)
+
+
+OUT = sys.stdout
 
 
 def main():
+    global OUT
     args = parse()
+    # stdout carries ONE JSON line: whatever libraries write to file descriptor 1 on the way (NCCL's version banner)
+    # goes to stderr instead
+    sys.stdout.flush()
+    OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
         return
@@ -489,7 +498,7 @@ def main():
             "gpu_launches": int(launches * world + 2 * args.steps * world),
             "clocks": clocks, "roofline": roofline, "hbm_streaming_k1": k1, "configs": configs, "strong_scaling": strong,
             "cpu_baseline": cpu, "e2e": e2e, "statistic": ci,
-        }), allow_nan=False))
+        }), allow_nan=False), file=OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
