@@ -2,7 +2,7 @@
 """Differential fuzz on the device: seeded random networks (tests/random_networks.py) through the C ABI against the
 oracle, the long-running sibling of tests/test_random_networks.py.  Usage (from the repo root, on a GPU box):
     python tools/fuzz_device.py [first_seed] [last_seed]
-Prints every disagreement and a summary line; see DESIGN.md section 5 for the two allowances."""
+Steps per launch cycle through 1..9, 32, 128 and the engine's own choice.  Prints every disagreement and a summary line; see DESIGN.md section 5 for the two allowances."""
 import os
 import sys
 import time
@@ -23,7 +23,7 @@ for seed in range(FIRST, LAST):
     models, conns = random_coupled_network(seed) if mode == 0 else random_network(seed, acyclic=(mode == 1))
     inject = random_injections(seed, models) if mode else []
     room = H.HostSim(models, conns, n=1).layout()["max_pending"] + len(inject)
-    sim = Simulation.post(models, conns, replications=96, seed=seed, instrument=True, steps_per_launch=1 + seed % 9, max_pending=room)
+    sim = Simulation.post(models, conns, replications=96, seed=seed, instrument=True, steps_per_launch=(1 + seed % 9, 32, 128, 0)[(seed // 9) % 4], max_pending=room)
     for tid, port, content in inject:
         sim.inject_input(Message("manual", "manual", tid, port, 0.0, content))
     try: sim.step_n(300)
