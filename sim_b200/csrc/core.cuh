@@ -1990,7 +1990,7 @@ struct Engine {
                 const uint32_t cpl = TF(TF_GROUP, (uint32_t)lowest_bit(pg.zmk)) >> 8;
                 if (cpl < SIMB_MAX_COUPLED && !(pg.copen & (1u << cpl))) {
                     // the Coupled model fires when ITS until_next_event is 0.0, and that is the minimum over its
-                    // components (coupled.rs:277-283): one component below zero (a negative variate was drawn) keeps
+                    // components (coupled.rs:304-310): one component below zero (a negative variate was drawn) keeps
                     // the whole model from firing in this step
                     const SimbCoupledDesc& cd = net.coupled[cpl];
                     bool below = false;
