@@ -232,3 +232,65 @@ def test_non_stationary_generation_replication_loop():
     ci = oa.IndependentSample.post(counts).confidence_interval_mean(0.05)
     emp = oa.IndependentSample.post([47.0, 42.0, 45.0, 34.0, 37.0]).confidence_interval_mean(0.05)
     assert ci.lower() < emp.upper() and ci.upper() > emp.lower()
+
+
+@pytest.mark.gpu
+def test_string_api_on_random_networks():
+    """step_json / get_messages_json / step_n_json / get_records_json of seeded random networks (tests/random_networks.py;
+    Coupled models and shared ids among them) against the oracle's own Vec<Message> and records: what a caller of
+    WebSimulation sees, message by message."""
+    from random_networks import random_coupled_network, random_network
+    from sim_b200 import SimulationError
+    compared = 0
+    for seed in range(16000, 16060):
+        models, conns = random_coupled_network(seed) if seed % 3 == 0 else random_network(seed, acyclic=(seed % 2 == 0))
+        def strip(ms):  # (oracle_api binds a model's own generator by id; records on, to read them back)
+            for m in ms:
+                if getattr(m.inner, "rng", None) is not None:
+                    m.inner.rng = None
+                if m.inner.type_name == "Coupled":
+                    strip(m.inner.components)
+                else:
+                    m.inner.store_records = True
+        strip(models)
+        if any(m.inner.type_name == "Stopwatch" for m in models) or \
+                any(m.inner.type_name == "Coupled" and any(c.inner.type_name == "Stopwatch" for c in m.inner.components) for m in models):
+            continue  # (job names reused across generators: DESIGN.md ledger)
+        web = _web(models, conns, n=1, replication=0, seed=seed, trace_capacity=1 << 14)   # (one replication: an error
+        o = _oracle(models, conns, seed, 0)                                                 # of another one would surface too)
+        try:
+            failed = False
+            for _ in range(12):
+                e, want = o.step()
+                if e:
+                    with pytest.raises(SimulationError) as ei:
+                        web.step_json()
+                    assert ei.value.status == e, seed
+                    failed = True
+                    break
+                _same(json.loads(web.step_json()), want)
+                _same(json.loads(web.get_messages_json()), o.get_messages())
+            if failed:
+                compared += 1
+                continue
+            e, want = o.step_n(60)
+            if e:
+                with pytest.raises(SimulationError) as ei:
+                    web.step_n_json(60)
+                assert ei.value.status == e, seed
+                compared += 1
+                continue
+            _same(json.loads(web.step_n_json(60)), want)
+        except SimulationError as err:
+            assert err.status == 32, (seed, str(err))   # a bounded container filled: not comparable
+            continue
+        for m in models:
+            if m.inner.type_name == "Coupled":
+                continue
+            if sum(1 for x in models if x.id == m.id) > 1:
+                continue
+            e, want = o.get_records(m.id)
+            got = json.loads(web.get_records_json(m.id))
+            assert e == 0 and [(g["action"], g["subject"]) for g in got] == [(w[1], w[2]) for w in want], (seed, m.id)
+        compared += 1
+    assert compared >= 25
