@@ -746,3 +746,63 @@ def test_empty_model_list_on_device():
     sim.inject_input(Message("manual", "manual", "nobody", "in", 0.0, "x 1"))
     sim.step()
     assert (sim.get_errors() == 0).all() and len(sim.get_messages(0)) == 0
+
+
+def test_c_abi_rejects_bad_arguments_without_touching_memory():
+    """Every entry point takes plain pointers and sizes; a null handle, a null or short output buffer, a replication
+    index past the batch, a model the network does not have -- each is an error return (InvalidArgument /
+    ModelNotFound), never a write past the buffer or a crash."""
+    import ctypes as C
+    from sim_b200 import Simulation
+    from sim_b200.simulator import load_library
+    L = load_library()
+    models, conns = networks.mm1()
+    sim = Simulation.post(models, conns, replications=8, seed=1, instrument=True, trace_replications=1, trace_capacity=64,
+                          stat_model_id="processor-01")
+    sim.step_n(20)
+    h = sim._h
+    NULL = None
+    INVALID, NOT_FOUND = 36, 2   # SIMB_ERR_INVALID_ARGUMENT, SIMB_ERR_MODEL_NOT_FOUND (include/simb.h)
+    guard = np.full(16, -7.0)
+    p = guard.ctypes.data
+    vp, u64, cp, dbl = C.c_void_p, C.c_uint64, C.c_char_p, C.c_double
+    def call(fn, types, *a):
+        fn.argtypes = types
+        fn.restype = C.c_int
+        return fn(*a)
+    assert call(L.simb_get_global_time, [vp, vp, u64], NULL, p, 16) == INVALID
+    assert call(L.simb_get_global_time, [vp, vp, u64], h, NULL, 16) == INVALID
+    assert call(L.simb_get_global_time, [vp, vp, u64], h, p, 7) == INVALID and (guard == -7.0).all()   # 8 replications
+    assert call(L.simb_get_global_time, [vp, vp, u64], h, p, 8) == 0 and (guard[8:] == -7.0).all()
+    assert call(L.simb_get_steps, [vp, vp, u64], h, p, 3) == INVALID
+    assert call(L.simb_get_until_next_event, [vp, cp, vp, u64], h, b"nobody", p, 16) == NOT_FOUND
+    assert call(L.simb_get_until_next_event, [vp, cp, vp, u64], h, NULL, p, 16) == INVALID
+    n = C.c_uint64(99)
+    assert call(L.simb_get_messages, [vp, u64, vp, u64, vp], h, 8, NULL, 0, C.byref(n)) == INVALID       # replication 8 of 8
+    assert call(L.simb_get_messages, [vp, u64, vp, u64, vp], h, 0, NULL, 0, NULL) == INVALID
+    assert call(L.simb_get_messages, [vp, u64, vp, u64, vp], h, 0, NULL, 0, C.byref(n)) == 0 and n.value <= 2
+    assert call(L.simb_get_records, [vp, cp, u64, vp, u64, vp], h, b"nobody", 0, NULL, 0, C.byref(n)) == NOT_FOUND
+    assert call(L.simb_get_records, [vp, cp, u64, vp, u64, vp], h, b"processor-01", 1, NULL, 0, C.byref(n)) != 0  # not a traced one
+    assert call(L.simb_get_trace, [vp, u64, vp, u64, vp], h, 5, NULL, 0, C.byref(n)) != 0
+    buf = C.create_string_buffer(4)
+    assert call(L.simb_get_status, [vp, cp, u64, vp, u64], h, b"nobody", 0, buf, 4) == NOT_FOUND
+    assert call(L.simb_get_status, [vp, cp, u64, vp, u64], h, b"processor-01", 0, buf, 4) == 0 and len(buf.value) <= 3  # truncated, terminated
+    out = C.c_char_p()
+    assert call(L.simb_get_json, [vp, u64, vp], h, 8, C.byref(out)) == INVALID
+    assert call(L.simb_get_json, [vp, u64, vp], h, 0, NULL) == INVALID
+    assert call(L.simb_step_n, [vp, u64], NULL, 1) == INVALID and call(L.simb_step_until, [vp, dbl], NULL, 1.0) == INVALID
+    assert call(L.simb_inject_input, [vp, cp, cp, cp, vp], h, NULL, b"job", b"x", NULL) == INVALID
+    assert call(L.simb_put_json, [vp, cp, cp], h, b"not json", b"[]") == 13
+    size = C.c_uint64()
+    assert call(L.simb_state_size, [vp, vp], h, C.byref(size)) == 0 and size.value > 0
+    blob = C.create_string_buffer(int(size.value))
+    written = C.c_uint64()
+    assert call(L.simb_get_state, [vp, vp, u64, vp], h, blob, size.value - 1, C.byref(written)) == INVALID
+    assert call(L.simb_get_state, [vp, vp, u64, vp], h, blob, size.value, C.byref(written)) == 0 and written.value == size.value
+    assert call(L.simb_put_state, [vp, vp, u64], h, blob, size.value - 8) != 0        # truncated checkpoint
+    assert call(L.simb_put_state, [vp, vp, u64], h, b"\x00" * int(size.value), size.value) != 0   # not a checkpoint
+    assert call(L.simb_put_state, [vp, vp, u64], h, blob, size.value) == 0
+    assert call(L.simb_get_wait_stats, [vp, vp, vp, u64], h, p, p, 2) == INVALID
+    # the handle still works
+    sim.step_n(5)
+    assert (sim.get_steps() == 25).all() and (sim.get_errors() == 0).all()
